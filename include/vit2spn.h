@@ -1,0 +1,171 @@
+/*
+ * vit2spn.h — C ABI of the B200-native ViT-2SPN dual-stream SSP hot path (libvit2spn.so).
+ *
+ * The reference (mrsaraei/ViT-2SPN) has no FFI layer: its hot path sits behind the
+ * torch.nn.Module protocol of ViTBackbone / DualStreamNetwork (ref:ssp_vit2spn_tiny.py:109-166),
+ * torch autograd, torch.optim.Adam (ref:173,216) and a Python EMA loop (ref:162-166).  Each entry
+ * point below replaces one of those call sites; the Python host mirror (vit-2spn_b200/) binds them
+ * with ctypes (see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - the caller (torch) owns all memory, including one workspace buffer sized by
+ *     v2s_workspace_bytes(); the library never allocates or frees device memory and keeps no
+ *     reference to caller memory after a call returns (it does cache TMA descriptors keyed by
+ *     address, which are re-validated on every call);
+ *   - all work is enqueued asynchronously on the cudaStream_t passed as `stream` (void*);
+ *   - return value 0 = ok, non-zero = error; message via v2s_last_error(); no C++ exceptions
+ *     cross the boundary; there is NO CPU fallback: a non-sm_100 device is an error.
+ */
+#ifndef VIT2SPN_H_
+#define VIT2SPN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define V2S_ABI_VERSION 1
+
+/* compute modes */
+#define V2S_MODE_FP32 0 /* fp32 activations + fp32 SIMT GEMMs: the "fp32 check mode" of north_star */
+#define V2S_MODE_BF16 1 /* bf16 GEMM operands (tcgen05), fp32 accumulate / residual / LN / softmax */
+
+/* model constants: ViT-Tiny/16 @224 (ref:ssp_ssl/ssl_vit2spn_scratch.py:100-108) */
+#define V2S_HIDDEN 192
+#define V2S_LAYERS 12
+#define V2S_HEADS 3
+#define V2S_HEAD_DIM 64
+#define V2S_MLP 768
+#define V2S_TOKENS 197
+#define V2S_PATCHES 196
+#define V2S_PATCH_K 768   /* 3*16*16 */
+#define V2S_IMG 224
+#define V2S_PROJ_IN 384   /* ref:ssp_vit2spn_tiny.py:134 */
+#define V2S_PROJ_HID 1024
+#define V2S_PROJ_OUT 128
+#define V2S_MAX_GROUPS 4
+
+int v2s_abi_version(void);
+const char* v2s_last_error(void);
+
+/* Verifies that `device` is an sm_100 part and selects it.  Replaces nothing in the reference
+ * (torch picks the device, ref:ssp_vit2spn_tiny.py:32); exists so that the product fails loudly. */
+int v2s_init(int device);
+
+/* ---- flat parameter layout --------------------------------------------------------------
+ * One backbone = one flat fp32 buffer of v2s_backbone_numel() elements.  The 200 HF tensors of
+ * transformers.ViTModel (ref:ssp_vit2spn_tiny.py:112) are views at the offsets returned by
+ * v2s_backbone_layout(): q/k/v weights (and biases) of a block are adjacent so that they form one
+ * fused [576,192] matrix; the final LayerNorm + pooler (never used by the reference's forward,
+ * SURVEY D6) sit at the tail, after v2s_backbone_active_numel() elements. */
+int64_t v2s_backbone_numel(void);        /* 5 561 472 */
+int64_t v2s_backbone_active_numel(void); /* 5 524 032 */
+int64_t v2s_heads_numel(void);           /* 558 464 : proj W1,b1,W2,b2, pred W3,b3,W4,b4 */
+/* offsets[i] = element offset of the i-th HF parameter (registration order) in the flat buffer */
+int v2s_backbone_layout(int64_t* host_offsets200);
+int v2s_heads_layout(int64_t* host_offsets8);
+
+/* ---- workspace --------------------------------------------------------------------------- */
+/* bytes of workspace for `n_groups` backbones run together at `batch` images each, of which
+ * `n_saved` keep their activations for a backward pass. */
+int64_t v2s_workspace_bytes(int batch, int mode, int n_groups, int n_saved);
+
+/* One backbone instance in a grouped launch (online_1, online_2, target_1, target_2 are four
+ * groups of one call: ref:ssp_vit2spn_tiny.py:146-151). */
+typedef struct v2s_group {
+  const float* params;    /* flat fp32 parameters (layout above) */
+  const void* params_lp;  /* bf16 copy of `params` (same element offsets); NULL in fp32 mode */
+  float* grads;           /* flat fp32 gradient buffer, accumulated (+=); NULL if no backward */
+  const float* x;         /* images fp32 NCHW [batch,3,224,224] */
+  float* hidden;          /* out (optional): hidden_states[-1], fp32 [batch,197,192] */
+  float* feat;            /* out (optional): mean over tokens, row i at feat + i*feat_stride */
+  int64_t feat_stride;    /* 192, or 384 when writing straight into the concatenated feature */
+  const float* dfeat;     /* backward in: d loss / d feat, row stride dfeat_stride (or NULL) */
+  int64_t dfeat_stride;
+  const float* dhidden;   /* backward in (optional): d loss / d hidden [batch,197,192]; added */
+  int32_t slot;           /* activation-stash slot (0..n_saved-1), or -1: nothing saved */
+  int32_t reserved;
+} v2s_group_t;
+
+/* ViTBackbone.forward for up to 4 backbones (ref:ssp_vit2spn_tiny.py:114-118; HF
+ * modeling_vit.py:100-128,328-346): patch-embed, 12 pre-LN blocks, mean over 197 tokens. */
+int v2s_backbone_forward(const v2s_group_t* host_groups, int n_groups, int batch, int mode,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+/* autograd backward of the above for the groups with slot >= 0 (ref:213 loss.backward()) */
+int v2s_backbone_backward(const v2s_group_t* host_groups, int n_groups, int batch, int mode,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/* projection_head + prediction_head on the concatenated online features and projection_head on
+ * the target features (ref:ssp_vit2spn_tiny.py:153-158), fused with the loss
+ *   -mean(cos(p, z)) / accumulation_steps   (ref:174,211; eps 1e-8)
+ * and its backward through both heads down to d loss / d online features.
+ *   head_params / head_grads: flat fp32 (v2s_heads_layout); grads accumulated (+=)
+ *   feat_online / feat_target: [batch,384] fp32;  dfeat_online: out [batch,384]
+ *   mask_online / mask_target: dropout multipliers [batch,1024] (0 or 1/(1-p)); NULL = no dropout
+ *   pred / target_proj: optional outs [batch,128];  loss: out, 1 float (already / accum)
+ *   grad_scale: upstream gradient of the loss (1.0, or GradScaler's scale; ref:213) */
+int v2s_heads_loss_fwd_bwd(const float* head_params, float* head_grads, const float* feat_online,
+                           const float* feat_target, const float* mask_online,
+                           const float* mask_target, float* dfeat_online, float* pred,
+                           float* target_proj, float* loss, int batch, int accumulation_steps,
+                           float grad_scale, int with_backward, void* workspace,
+                           int64_t workspace_bytes, void* stream);
+
+/* The same three stages as separate calls, for the autograd-compatible path where the script's
+ * own criterion computes the loss between forward and backward (ref:210-213).  The heads'
+ * intermediates stay in the first batch*32768 bytes of `workspace` between the two calls. */
+int v2s_heads_forward(const float* head_params, const float* feat_online, const float* feat_target,
+                      const float* mask_online, const float* mask_target, float* pred,
+                      float* target_proj, int batch, void* workspace, int64_t workspace_bytes,
+                      void* stream);
+int v2s_heads_backward(const float* head_params, float* head_grads, const float* feat_online,
+                       const float* mask_online, const float* dpred, float* dfeat_online, int batch,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+/* nn.CosineSimilarity(dim=1) loss of ref:174,211 and (optionally, dpred != NULL) its gradient */
+int v2s_cosine_loss(const float* pred, const float* target_proj, float* loss, float* dpred, int batch,
+                    int accumulation_steps, float grad_scale, void* stream);
+
+/* dropout multipliers for the projection head: out[i] = keep ? 1/(1-p) : 0, counter-based RNG */
+int v2s_dropout_mask(float* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+
+/* torch.optim.Adam.step (ref:173,216) over up to 4 flat ranges: defaults betas (0.9,0.999),
+ * eps 1e-8, no weight decay unless weight_decay != 0 (L2, as the fine-tune scripts use).
+ * `step` is the 1-based step count; grads are multiplied by grad_scale first (1/world, 1/scale).
+ * If params_lp != NULL the bf16 shadow copy is refreshed in the same pass. */
+typedef struct v2s_range {
+  float* params;
+  const float* grads;
+  float* exp_avg;
+  float* exp_avg_sq;
+  void* params_lp;
+  int64_t numel;
+} v2s_range_t;
+int v2s_adam_step(const v2s_range_t* host_ranges, int n_ranges, int64_t step, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, float grad_scale, void* stream);
+
+/* update_target_network (ref:162-166): target = m*target + (1-m)*online over flat buffers */
+int v2s_ema_update(float* const* host_targets, const float* const* host_onlines,
+                   void* const* host_targets_lp, int n_pairs, int64_t numel, float momentum,
+                   void* stream);
+
+/* fp32 → bf16 shadow copy of a flat buffer */
+int v2s_cast_bf16(const float* src, void* dst, int64_t numel, void* stream);
+
+/* synthetic OCTMNIST-shaped input pipeline (ref:ssp_vit2spn_tiny.py:84-96, deterministic part):
+ * uint8 [batch,1,28,28] → bilinear 224x224 → 3 channels → ImageNet normalise → fp32 NCHW */
+int v2s_preprocess_u8(const uint8_t* src, float* dst, int batch, void* stream);
+
+/* test hooks: individual operators, used by tests/ to localise a parity failure */
+int v2s_test_gemm(int which, const void* a, const void* b, void* c, int m, int n, int k,
+                  int variant, void* stream);
+int64_t v2s_launch_count(void); /* kernels launched by this library since load (bench: gpu_launches) */
+/* device-event timing per kernel class (bench.py roofline); off by default, enabling resets it */
+int v2s_prof_enable(int on);
+int v2s_prof_report(char* host_buf, int64_t buf_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIT2SPN_H_ */

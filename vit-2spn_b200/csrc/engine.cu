@@ -1,0 +1,765 @@
+// Host-side orchestration of the grouped ViT-Tiny backbone forward / backward and of the
+// heads + loss step, plus the extern "C" boundary (include/vit2spn.h).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+namespace v2s {
+
+static thread_local char g_err[1024] = "";
+int64_t g_launch_count = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---- optional per-kernel-class device timing (bench.py roofline; off by default) -------------
+namespace prof {
+constexpr int MAX_REC = 8192;
+struct Rec { int cls; double work; cudaEvent_t a, b; };
+static bool enabled = false;
+static Rec recs[MAX_REC];
+static int n_recs = 0;
+static int n_events = 0;   // events created so far (recs[i].a/b valid for i < n_events)
+static const char* names[] = {"gemm_patch", "gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_dgrad",
+                              "gemm_wgrad", "attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd", "colsum", "misc", "heads"};
+enum { C_PATCH, C_QKV, C_PROJ, C_FC1, C_FC2, C_DGRAD, C_WGRAD, C_ATTN_F, C_ATTN_B, C_LN_F, C_LN_B, C_COLSUM, C_MISC,
+       C_HEADS, C_COUNT };
+struct Scope {
+  int idx = -1;
+  cudaStream_t st;
+  Scope(int cls, double work, cudaStream_t s) : st(s) {
+    if (!enabled || n_recs >= MAX_REC) return;
+    idx = n_recs++;
+    if (idx >= n_events) { cudaEventCreate(&recs[idx].a); cudaEventCreate(&recs[idx].b); n_events = idx + 1; }
+    recs[idx].cls = cls; recs[idx].work = work;
+    cudaEventRecord(recs[idx].a, st);
+  }
+  ~Scope() { if (idx >= 0) cudaEventRecord(recs[idx].b, st); }
+};
+}  // namespace prof
+
+namespace {
+
+inline int64_t align_up(int64_t v, int64_t a = 1024) { return (v + a - 1) / a * a; }
+
+// ---- workspace carve-up ---------------------------------------------------------------------
+struct LayerStash {   // byte offsets relative to the slot base
+  int64_t mean1, rstd1, xn1, qkv, ctx, lse, x_mid, mean2, rstd2, xn2, u, h;
+};
+struct Plan {
+  int B, at;
+  int64_t es;          // activation element size
+  int64_t M, MP;
+  int64_t heads_bytes;
+  // per-group forward scratch (groups that do not save activations)
+  int64_t f_patches, f_xa, f_xb, f_xn, f_qkv, f_ctx, f_h, f_bytes;
+  // per-slot stash
+  int64_t s_patches, s_x[NL + 1];
+  LayerStash s_layer[NL];
+  int64_t s_bytes;
+  // per-slot backward scratch
+  int64_t b_dx, b_dxlp, b_big, b_tmp, b_bytes;
+};
+
+Plan make_plan(int B, int mode) {
+  Plan p;
+  memset(&p, 0, sizeof(p));
+  p.B = B;
+  p.at = mode == V2S_MODE_BF16 ? 1 : 0;
+  p.es = p.at ? 2 : 4;
+  p.M = (int64_t)B * NT;
+  p.MP = (int64_t)B * NP;
+  p.heads_bytes = align_up((int64_t)B * 8192 * 4 + 4096);
+  int64_t o = 0;
+  auto take = [&](int64_t bytes) { int64_t r = o; o += align_up(bytes); return r; };
+  p.f_patches = take(p.MP * KPE * p.es);
+  p.f_xa = take(p.M * D * 4);
+  p.f_xb = take(p.M * D * 4);
+  p.f_xn = take(p.M * D * p.es);
+  p.f_qkv = take(p.M * 3 * D * p.es);
+  p.f_ctx = take(p.M * D * p.es);
+  p.f_h = take(p.M * DF * p.es);
+  p.f_bytes = o;
+  o = 0;
+  p.s_patches = take(p.MP * KPE * p.es);
+  for (int l = 0; l <= NL; ++l) p.s_x[l] = take(p.M * D * 4);
+  for (int l = 0; l < NL; ++l) {
+    LayerStash& s = p.s_layer[l];
+    s.mean1 = take(p.M * 4); s.rstd1 = take(p.M * 4);
+    s.xn1 = take(p.M * D * p.es);
+    s.qkv = take(p.M * 3 * D * p.es);
+    s.ctx = take(p.M * D * p.es);
+    s.lse = take((int64_t)B * NH * NT * 4);
+    s.x_mid = take(p.M * D * 4);
+    s.mean2 = take(p.M * 4); s.rstd2 = take(p.M * 4);
+    s.xn2 = take(p.M * D * p.es);
+    s.u = take(p.M * DF * p.es);
+    s.h = take(p.M * DF * p.es);
+  }
+  p.s_bytes = o;
+  o = 0;
+  p.b_dx = take(p.M * D * 4);
+  p.b_dxlp = take(p.M * D * p.es);
+  p.b_big = take(p.M * DF * p.es);
+  p.b_tmp = take(p.M * D * p.es);
+  p.b_bytes = o;
+  return p;
+}
+
+int64_t plan_total(const Plan& p, int n_groups, int n_saved) {
+  return p.heads_bytes + (int64_t)n_groups * p.f_bytes + (int64_t)n_saved * (p.s_bytes + p.b_bytes);
+}
+
+// base addresses inside the workspace; regions are laid out for the maximum MAXG groups so that
+// forward and backward calls agree regardless of how many groups each call carries
+struct Regions {
+  char* heads;
+  char* fwd[MAXG];
+  char* stash[MAXG];
+  char* bwd[MAXG];
+};
+
+int resolve_regions(const Plan& p, void* ws, int64_t ws_bytes, int n_groups, int n_saved, Regions* r) {
+  if (n_groups < 0 || n_groups > MAXG || n_saved < 0 || n_saved > MAXG) {
+    set_error("workspace: bad group counts");
+    return 1;
+  }
+  // layout: heads | stash[0..n_saved) | bwd[0..n_saved) | fwd[0..n_groups)
+  // (stash first so that its addresses do not depend on n_groups)
+  const int64_t need = plan_total(p, n_groups, n_saved);
+  if (!ws || ws_bytes < need) {
+    set_error("workspace too small: have %lld bytes, need %lld", (long long)ws_bytes, (long long)need);
+    return 1;
+  }
+  char* base = static_cast<char*>(ws);
+  if ((reinterpret_cast<uintptr_t>(base) & 1023) != 0) {
+    set_error("workspace must be 1024-byte aligned");
+    return 1;
+  }
+  r->heads = base;
+  char* q = base + p.heads_bytes;
+  for (int i = 0; i < MAXG; ++i) { r->stash[i] = i < n_saved ? q : nullptr; if (i < n_saved) q += p.s_bytes; }
+  for (int i = 0; i < MAXG; ++i) { r->bwd[i] = i < n_saved ? q : nullptr; if (i < n_saved) q += p.b_bytes; }
+  for (int i = 0; i < MAXG; ++i) { r->fwd[i] = i < n_groups ? q : nullptr; if (i < n_groups) q += p.f_bytes; }
+  return 0;
+}
+
+// number of stash slots the workspace was sized for is implied by the highest slot in use:
+// the Python side always allocates with n_saved = 2 (two online streams) or 1; slots index the
+// stash region directly, so forward and backward agree as long as the same workspace is passed.
+int max_slot(const v2s_group_t* g, int n) {
+  int m = -1;
+  for (int i = 0; i < n; ++i) if (g[i].slot > m) m = g[i].slot;
+  return m;
+}
+
+int run_gemm(const GemmDesc& d, int ta, int tb, int to, cudaStream_t s, int cls = prof::C_MISC) {
+  prof::Scope scope(cls, 2.0 * d.M * d.N * (double)d.K * d.groups, s);
+  int handled = 0;
+  V2S_TRY(launch_gemm_tc(d, ta, tb, to, s, &handled));
+  if (handled) return 0;
+  return launch_gemm_simt(d, ta, tb, to, s);
+}
+
+inline const void* weight_ptr(const v2s_group_t& g, int at, int64_t off) {
+  return at ? static_cast<const void*>(static_cast<const bf16*>(g.params_lp) + off)
+            : static_cast<const void*>(g.params + off);
+}
+
+int launch_attention_fwd(const void* const* qkv, void* const* ctx, float* const* lse, int groups, int B, int at,
+                         cudaStream_t s) {
+  prof::Scope scope(prof::C_ATTN_F, 4.0 * B * NH * (double)NT * NT * DH * groups, s);
+  return launch_attn_fwd_simt(qkv, ctx, lse, groups, B, at, s);
+}
+int launch_attention_bwd(const void* const* qkv, const void* const* ctx, const float* const* lse,
+                         const void* const* dctx, void* const* dqkv, int groups, int B, int at, cudaStream_t s) {
+  prof::Scope scope(prof::C_ATTN_B, 8.0 * B * NH * (double)NT * NT * DH * groups, s);
+  return launch_attn_bwd_simt(qkv, ctx, lse, dctx, dqkv, groups, B, at, s);
+}
+
+int wgrad_split(int64_t rows) {
+  int64_t s = rows / 1024;
+  if (s < 1) s = 1;
+  if (s > 16) s = 16;
+  return (int)s;
+}
+
+}  // namespace
+
+// =============================================================================================
+// backbone forward
+// =============================================================================================
+static int backbone_forward_impl(const v2s_group_t* gs, int G, int B, int mode, void* ws, int64_t ws_bytes,
+                                 cudaStream_t st) {
+  if (G < 1 || G > MAXG) { set_error("backbone_forward: 1..4 groups"); return 1; }
+  if (B < 1) { set_error("backbone_forward: batch must be >= 1"); return 1; }
+  const Plan p = make_plan(B, mode);
+  const int at = p.at;
+  const int n_saved = max_slot(gs, G) + 1;
+  Regions R;
+  V2S_TRY(resolve_regions(p, ws, ws_bytes, G, n_saved, &R));
+  for (int g = 0; g < G; ++g) {
+    if (!gs[g].params || !gs[g].x) { set_error("backbone_forward: group %d has null params/x", g); return 1; }
+    if (at && !gs[g].params_lp) { set_error("backbone_forward: bf16 mode needs params_lp (group %d)", g); return 1; }
+    if (gs[g].slot >= MAXG) { set_error("backbone_forward: bad slot"); return 1; }
+  }
+  const int64_t M = p.M, MP = p.MP;
+
+  // ---- buffer resolution ----
+  auto saved = [&](int g) { return gs[g].slot >= 0; };
+  auto sb = [&](int g, int64_t off) -> char* { return R.stash[gs[g].slot] + off; };
+  auto fb = [&](int g, int64_t off) -> char* { return R.fwd[g] + off; };
+
+  // ---- patch embedding: im2col (shared between groups that read the same images) ----
+  void* patches[MAXG];
+  {
+    const float* ux[MAXG]; void* uo[MAXG]; int nu = 0;
+    for (int g = 0; g < G; ++g) {
+      patches[g] = saved(g) ? sb(g, p.s_patches) : fb(g, p.f_patches);
+      int dup = -1;
+      // a saved group must own its copy (it outlives the call); unsaved groups may alias
+      if (!saved(g))
+        for (int k = 0; k < g; ++k) if (gs[k].x == gs[g].x) { dup = k; break; }
+      if (dup >= 0) { patches[g] = patches[dup]; continue; }
+      ux[nu] = gs[g].x; uo[nu] = patches[g]; ++nu;
+    }
+    V2S_TRY(launch_im2col(ux, uo, nu, B, at, st));
+  }
+  float* x_cur[MAXG];
+  {
+    GemmDesc d = make_gemm_desc();
+    d.M = (int)MP; d.N = D; d.K = KPE; d.groups = G;
+    d.a_rs = KPE; d.a_cs = 1; d.b_rs = 1; d.b_cs = KPE;
+    d.epi = EPI_PATCH; d.ldc = D;
+    const float* pp[MAXG];
+    for (int g = 0; g < G; ++g) {
+      x_cur[g] = reinterpret_cast<float*>(saved(g) ? sb(g, p.s_x[0]) : fb(g, p.f_xa));
+      d.A[g] = patches[g];
+      d.B[g] = weight_ptr(gs[g], at, OFF_WPE);
+      d.bias[g] = gs[g].params + OFF_BPE;
+      d.aux[g] = gs[g].params + OFF_POS;
+      d.out[g] = x_cur[g];
+      pp[g] = gs[g].params;
+    }
+    V2S_TRY(run_gemm(d, at, at, 0, st, prof::C_PATCH));
+    V2S_TRY(launch_cls_rows(pp, x_cur, G, B, st));
+  }
+
+  // ---- 12 pre-LN blocks ----
+  for (int l = 0; l < NL; ++l) {
+    const int64_t lo = layer_off(l);
+    const float *xin[MAXG], *gam[MAXG], *bet[MAXG];
+    void *xn[MAXG], *qkv[MAXG], *ctx[MAXG], *u[MAXG], *h[MAXG];
+    float *mean[MAXG], *rstd[MAXG], *lse[MAXG], *xmid[MAXG], *xout[MAXG];
+    for (int g = 0; g < G; ++g) {
+      xin[g] = x_cur[g];
+      if (saved(g)) {
+        const LayerStash& s = p.s_layer[l];
+        xn[g] = sb(g, s.xn1); qkv[g] = sb(g, s.qkv); ctx[g] = sb(g, s.ctx);
+        mean[g] = (float*)sb(g, s.mean1); rstd[g] = (float*)sb(g, s.rstd1); lse[g] = (float*)sb(g, s.lse);
+        xmid[g] = (float*)sb(g, s.x_mid); u[g] = sb(g, s.u); h[g] = sb(g, s.h);
+        xout[g] = (float*)sb(g, p.s_x[l + 1]);
+      } else {
+        xn[g] = fb(g, p.f_xn); qkv[g] = fb(g, p.f_qkv); ctx[g] = fb(g, p.f_ctx);
+        mean[g] = nullptr; rstd[g] = nullptr; lse[g] = nullptr;
+        xmid[g] = (float*)fb(g, p.f_xb); u[g] = nullptr; h[g] = fb(g, p.f_h);
+        xout[g] = (float*)fb(g, p.f_xa);   // in place: x_in is dead once x_mid exists
+      }
+      gam[g] = gs[g].params + lo + L_LN1W; bet[g] = gs[g].params + lo + L_LN1B;
+    }
+    { prof::Scope sc(prof::C_LN_F, (double)M * D * (4 + p.es) * G, st);
+      V2S_TRY(launch_ln_fwd(xin, gam, bet, xn, mean, rstd, G, (int)M, at, st)); }
+    {  // fused QKV projection
+      GemmDesc d = make_gemm_desc();
+      d.M = (int)M; d.N = 3 * D; d.K = D; d.groups = G;
+      d.a_rs = D; d.a_cs = 1; d.b_rs = 1; d.b_cs = D; d.epi = EPI_STORE; d.ldc = 3 * D;
+      for (int g = 0; g < G; ++g) {
+        d.A[g] = xn[g]; d.B[g] = weight_ptr(gs[g], at, lo + L_WQKV);
+        d.bias[g] = gs[g].params + lo + L_BQKV; d.out[g] = qkv[g];
+      }
+      V2S_TRY(run_gemm(d, at, at, at, st, prof::C_QKV));
+    }
+    {
+      const void* cq[MAXG];
+      for (int g = 0; g < G; ++g) cq[g] = qkv[g];
+      V2S_TRY(launch_attention_fwd(cq, ctx, lse, G, B, at, st));
+    }
+    {  // attention output projection + residual
+      GemmDesc d = make_gemm_desc();
+      d.M = (int)M; d.N = D; d.K = D; d.groups = G;
+      d.a_rs = D; d.a_cs = 1; d.b_rs = 1; d.b_cs = D; d.epi = EPI_BIAS_RESID; d.ldc = D;
+      for (int g = 0; g < G; ++g) {
+        d.A[g] = ctx[g]; d.B[g] = weight_ptr(gs[g], at, lo + L_WO);
+        d.bias[g] = gs[g].params + lo + L_BO; d.resid[g] = xin[g]; d.out[g] = xmid[g];
+      }
+      V2S_TRY(run_gemm(d, at, at, 0, st, prof::C_PROJ));
+    }
+    {
+      const float* xm[MAXG];
+      void* xn2[MAXG]; float *m2[MAXG], *r2[MAXG];
+      for (int g = 0; g < G; ++g) {
+        xm[g] = xmid[g];
+        gam[g] = gs[g].params + lo + L_LN2W; bet[g] = gs[g].params + lo + L_LN2B;
+        if (saved(g)) { xn2[g] = sb(g, p.s_layer[l].xn2); m2[g] = (float*)sb(g, p.s_layer[l].mean2); r2[g] = (float*)sb(g, p.s_layer[l].rstd2); }
+        else { xn2[g] = fb(g, p.f_xn); m2[g] = nullptr; r2[g] = nullptr; }
+      }
+      { prof::Scope sc(prof::C_LN_F, (double)M * D * (4 + p.es) * G, st);
+        V2S_TRY(launch_ln_fwd(xm, gam, bet, xn2, m2, r2, G, (int)M, at, st)); }
+      GemmDesc d = make_gemm_desc();   // fc1 + GELU
+      d.M = (int)M; d.N = DF; d.K = D; d.groups = G;
+      d.a_rs = D; d.a_cs = 1; d.b_rs = 1; d.b_cs = D; d.epi = EPI_BIAS_GELU; d.ldc = DF;
+      for (int g = 0; g < G; ++g) {
+        d.A[g] = xn2[g]; d.B[g] = weight_ptr(gs[g], at, lo + L_W1);
+        d.bias[g] = gs[g].params + lo + L_B1; d.out[g] = u[g]; d.out2[g] = h[g];
+      }
+      V2S_TRY(run_gemm(d, at, at, at, st, prof::C_FC1));
+    }
+    {  // fc2 + residual
+      GemmDesc d = make_gemm_desc();
+      d.M = (int)M; d.N = D; d.K = DF; d.groups = G;
+      d.a_rs = DF; d.a_cs = 1; d.b_rs = 1; d.b_cs = DF; d.epi = EPI_BIAS_RESID; d.ldc = D;
+      for (int g = 0; g < G; ++g) {
+        d.A[g] = h[g]; d.B[g] = weight_ptr(gs[g], at, lo + L_W2);
+        d.bias[g] = gs[g].params + lo + L_B2; d.resid[g] = xmid[g]; d.out[g] = xout[g];
+      }
+      V2S_TRY(run_gemm(d, at, at, 0, st, prof::C_FC2));
+    }
+    for (int g = 0; g < G; ++g) x_cur[g] = xout[g];
+  }
+
+  // ---- outputs: hidden_states[-1] and its mean over the 197 tokens ----
+  {
+    const float* hid[MAXG]; float* feat[MAXG]; int64_t fs[MAXG]; int nf = 0;
+    for (int g = 0; g < G; ++g) {
+      if (gs[g].hidden)
+        V2S_CUDA_OK(cudaMemcpyAsync(gs[g].hidden, x_cur[g], (size_t)M * D * 4, cudaMemcpyDeviceToDevice, st));
+      if (gs[g].feat) { hid[nf] = x_cur[g]; feat[nf] = gs[g].feat; fs[nf] = gs[g].feat_stride > 0 ? gs[g].feat_stride : D; ++nf; }
+    }
+    if (nf) V2S_TRY(launch_pool_fwd(hid, feat, fs, nf, B, st));
+  }
+  return 0;
+}
+
+// =============================================================================================
+// backbone backward
+// =============================================================================================
+static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int mode, void* ws, int64_t ws_bytes,
+                                  cudaStream_t st) {
+  // keep only the groups that saved activations and want gradients
+  v2s_group_t gs[MAXG];
+  int G = 0;
+  for (int i = 0; i < G_in && i < MAXG; ++i)
+    if (gs_in[i].slot >= 0 && gs_in[i].grads) gs[G++] = gs_in[i];
+  if (G == 0) { set_error("backbone_backward: no group with slot >= 0 and grads"); return 1; }
+  const Plan p = make_plan(B, mode);
+  const int at = p.at;
+  const int n_saved = max_slot(gs_in, G_in) + 1;
+  Regions R;
+  V2S_TRY(resolve_regions(p, ws, ws_bytes, 0, n_saved, &R));
+  const int64_t M = p.M, MP = p.MP;
+  auto sb = [&](int g, int64_t off) -> char* { return R.stash[gs[g].slot] + off; };
+  auto bb = [&](int g, int64_t off) -> char* { return R.bwd[gs[g].slot] + off; };
+
+  float* dx[MAXG]; void* dxlp[MAXG]; void* big[MAXG]; void* tmp[MAXG];
+  {
+    const float *df[MAXG], *dh[MAXG]; int64_t dfs[MAXG]; void* lp[MAXG];
+    for (int g = 0; g < G; ++g) {
+      if (!gs[g].dfeat && !gs[g].dhidden) { set_error("backbone_backward: group needs dfeat or dhidden"); return 1; }
+      dx[g] = (float*)bb(g, p.b_dx);
+      dxlp[g] = at ? (void*)bb(g, p.b_dxlp) : (void*)dx[g];
+      big[g] = bb(g, p.b_big); tmp[g] = bb(g, p.b_tmp);
+      df[g] = gs[g].dfeat; dfs[g] = gs[g].dfeat_stride > 0 ? gs[g].dfeat_stride : D; dh[g] = gs[g].dhidden;
+      lp[g] = at ? dxlp[g] : nullptr;
+    }
+    V2S_TRY(launch_pool_bwd(df, dfs, dh, dx, lp, G, B, at, st));
+  }
+
+  const int split = wgrad_split(M);
+  // dW[N_out, K_in] += dY[M, N_out]^T * X[M, K_in]   (token dimension is the reduction)
+  auto wgrad = [&](void* const* dy, int n_out, void* const* x, int k_in, int64_t goff, bool remap) -> int {
+    GemmDesc d = make_gemm_desc();
+    d.M = n_out; d.N = k_in; d.K = remap ? (int)MP : (int)M; d.groups = G;
+    d.a_rs = 1; d.a_cs = n_out; d.b_rs = k_in; d.b_cs = 1;
+    d.a_remap = remap ? 2 : 0;
+    d.epi = EPI_ACCUM; d.ldc = k_in; d.split_k = split;
+    for (int g = 0; g < G; ++g) { d.A[g] = dy[g]; d.B[g] = x[g]; d.out[g] = gs[g].grads + goff; }
+    return run_gemm(d, at, at, 0, st, prof::C_WGRAD);
+  };
+  // dX[M, K_in] = dY[M, N_out] * W[N_out, K_in]
+  auto dgrad = [&](void* const* dy, int n_out, int64_t woff, int k_in, void* const* out, int epi,
+                   void* const* aux) -> int {
+    GemmDesc d = make_gemm_desc();
+    d.M = (int)M; d.N = k_in; d.K = n_out; d.groups = G;
+    d.a_rs = n_out; d.a_cs = 1; d.b_rs = k_in; d.b_cs = 1;
+    d.epi = epi; d.ldc = k_in;
+    for (int g = 0; g < G; ++g) {
+      d.A[g] = dy[g]; d.B[g] = weight_ptr(gs[g], at, woff); d.out[g] = out[g];
+      d.aux[g] = aux ? aux[g] : nullptr;
+    }
+    return run_gemm(d, at, at, at, st, prof::C_DGRAD);
+  };
+  auto bias_grad = [&](void* const* dy, int n, int64_t goff) -> int {
+    const void* src[MAXG]; float* dst[MAXG];
+    for (int g = 0; g < G; ++g) { src[g] = dy[g]; dst[g] = gs[g].grads + goff; }
+    prof::Scope sc(prof::C_COLSUM, (double)M * n * p.es * G, st);
+    return launch_colsum(src, dst, G, (int)M, n, at, st);
+  };
+
+  for (int l = NL - 1; l >= 0; --l) {
+    const int64_t lo = layer_off(l);
+    const LayerStash& s = p.s_layer[l];
+    void *u[MAXG], *h[MAXG], *xn2[MAXG], *ctx[MAXG], *qkv[MAXG], *xn1[MAXG];
+    for (int g = 0; g < G; ++g) {
+      u[g] = sb(g, s.u); h[g] = sb(g, s.h); xn2[g] = sb(g, s.xn2);
+      ctx[g] = sb(g, s.ctx); qkv[g] = sb(g, s.qkv); xn1[g] = sb(g, s.xn1);
+    }
+    // ---- MLP ----
+    V2S_TRY(wgrad(dxlp, D, h, DF, lo + L_W2, false));                      // dW2 [192,768]
+    V2S_TRY(bias_grad(dxlp, D, lo + L_B2));
+    V2S_TRY(dgrad(dxlp, D, lo + L_W2, DF, big, EPI_DGELU, u));             // du = (dx W2) * gelu'(u)
+    V2S_TRY(wgrad(big, DF, xn2, D, lo + L_W1, false));                     // dW1 [768,192]
+    V2S_TRY(bias_grad(big, DF, lo + L_B1));
+    V2S_TRY(dgrad(big, DF, lo + L_W1, D, tmp, EPI_STORE, nullptr));        // d xn2
+    {
+      const void* dy[MAXG]; const float *x[MAXG], *mu[MAXG], *rs[MAXG], *gm[MAXG];
+      float *dg[MAXG], *db[MAXG]; void* lp[MAXG];
+      for (int g = 0; g < G; ++g) {
+        dy[g] = tmp[g]; x[g] = (const float*)sb(g, s.x_mid); mu[g] = (const float*)sb(g, s.mean2);
+        rs[g] = (const float*)sb(g, s.rstd2); gm[g] = gs[g].params + lo + L_LN2W;
+        dg[g] = gs[g].grads + lo + L_LN2W; db[g] = gs[g].grads + lo + L_LN2B; lp[g] = at ? dxlp[g] : nullptr;
+      }
+      { prof::Scope sc(prof::C_LN_B, (double)M * D * (12 + 2 * p.es) * G, st);
+        V2S_TRY(launch_ln_bwd(dy, x, mu, rs, gm, dx, lp, dg, db, G, (int)M, at, st)); }
+    }
+    // ---- attention ----
+    V2S_TRY(wgrad(dxlp, D, ctx, D, lo + L_WO, false));                     // dWo
+    V2S_TRY(bias_grad(dxlp, D, lo + L_BO));
+    V2S_TRY(dgrad(dxlp, D, lo + L_WO, D, tmp, EPI_STORE, nullptr));        // d ctx
+    {
+      const void *cq[MAXG], *cc[MAXG], *cd[MAXG]; const float* ls[MAXG];
+      for (int g = 0; g < G; ++g) { cq[g] = qkv[g]; cc[g] = ctx[g]; cd[g] = tmp[g]; ls[g] = (const float*)sb(g, s.lse); }
+      V2S_TRY(launch_attention_bwd(cq, cc, ls, cd, big, G, B, at, st));    // d qkv in `big` [M,576]
+    }
+    V2S_TRY(wgrad(big, 3 * D, xn1, D, lo + L_WQKV, false));                // dWqkv [576,192]
+    V2S_TRY(bias_grad(big, 3 * D, lo + L_BQKV));
+    V2S_TRY(dgrad(big, 3 * D, lo + L_WQKV, D, tmp, EPI_STORE, nullptr));   // d xn1
+    {
+      const void* dy[MAXG]; const float *x[MAXG], *mu[MAXG], *rs[MAXG], *gm[MAXG];
+      float *dg[MAXG], *db[MAXG]; void* lp[MAXG];
+      for (int g = 0; g < G; ++g) {
+        dy[g] = tmp[g]; x[g] = (const float*)sb(g, p.s_x[l]); mu[g] = (const float*)sb(g, s.mean1);
+        rs[g] = (const float*)sb(g, s.rstd1); gm[g] = gs[g].params + lo + L_LN1W;
+        dg[g] = gs[g].grads + lo + L_LN1W; db[g] = gs[g].grads + lo + L_LN1B; lp[g] = at ? dxlp[g] : nullptr;
+      }
+      { prof::Scope sc(prof::C_LN_B, (double)M * D * (12 + 2 * p.es) * G, st);
+        V2S_TRY(launch_ln_bwd(dy, x, mu, rs, gm, dx, lp, dg, db, G, (int)M, at, st)); }
+    }
+  }
+  // ---- embeddings: d pos, d cls, d patch bias, d patch weight ----
+  {
+    const float* cdx[MAXG]; float* gr[MAXG]; void* pt[MAXG];
+    for (int g = 0; g < G; ++g) { cdx[g] = dx[g]; gr[g] = gs[g].grads; pt[g] = sb(g, p.s_patches); }
+    V2S_TRY(launch_embed_bwd(cdx, gr, G, B, st));
+    V2S_TRY(wgrad(dxlp, D, pt, KPE, OFF_WPE, true));
+  }
+  return 0;
+}
+
+// =============================================================================================
+// heads + loss
+// =============================================================================================
+namespace {
+struct HeadsBufs {
+  float *a1, *y1, *a1t, *y1t, *dy1, *z, *y2, *pr, *zt, *dp, *dy2, *dz, *y2b;
+};
+int heads_bufs(void* ws, int64_t ws_bytes, int B, HeadsBufs* hb) {
+  const int64_t need = (int64_t)B * 8192 * 4;
+  if (!ws || ws_bytes < need) {
+    set_error("heads: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
+    return 1;
+  }
+  float* w = static_cast<float*>(ws);
+  const int PH = V2S_PROJ_HID, PO = V2S_PROJ_OUT;
+  hb->a1 = w;  w += (int64_t)B * PH;   // relu(f W1^T + b1)
+  hb->y1 = w;  w += (int64_t)B * PH;   // a1 * dropout mask
+  hb->a1t = w; w += (int64_t)B * PH;
+  hb->y1t = w; w += (int64_t)B * PH;
+  hb->dy1 = w; w += (int64_t)B * PH;
+  hb->z = w;   w += (int64_t)B * PO;
+  hb->y2 = w;  w += (int64_t)B * PO;
+  hb->pr = w;  w += (int64_t)B * PO;
+  hb->zt = w;  w += (int64_t)B * PO;
+  hb->dp = w;  w += (int64_t)B * PO;
+  hb->dy2 = w; w += (int64_t)B * PO;
+  hb->dz = w;  w += (int64_t)B * PO;
+  hb->y2b = w; w += (int64_t)B * PO;
+  return 0;
+}
+}  // namespace
+
+// projection_head + prediction_head on the online features, projection_head on the target
+// features (ref:ssp_vit2spn_tiny.py:153-158).  Intermediates stay in the workspace heads region.
+static int heads_forward_impl(const float* hp, const float* fo, const float* ft, const float* mo, const float* mt,
+                              float* pred_out, float* tgt_out, int B, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  if (!hp || !fo || !ft) { set_error("heads_forward: null argument"); return 1; }
+  HeadsBufs hb;
+  V2S_TRY(heads_bufs(ws, ws_bytes, B, &hb));
+  const int PH = V2S_PROJ_HID, PO = V2S_PROJ_OUT, PI = V2S_PROJ_IN;
+  auto linear = [&](const float* x, int k, int64_t woff, int64_t boff, int n, int epi, float* out, float* out2,
+                    const float* mask) -> int {
+    GemmDesc d = make_gemm_desc();
+    d.M = B; d.N = n; d.K = k; d.a_rs = k; d.a_cs = 1; d.b_rs = 1; d.b_cs = k; d.epi = epi; d.ldc = n;
+    d.A[0] = x; d.B[0] = hp + woff; d.bias[0] = hp + boff; d.out[0] = out; d.out2[0] = out2; d.mask[0] = mask;
+    return launch_gemm_simt(d, 0, 0, 0, st);
+  };
+  V2S_TRY(linear(fo, PI, H_W1, H_B1, PH, EPI_BIAS_RELU_MASK, hb.a1, hb.y1, mo));
+  V2S_TRY(linear(hb.y1, PH, H_W2, H_B2, PO, EPI_STORE, hb.z, nullptr, nullptr));
+  V2S_TRY(linear(hb.z, PO, H_W3, H_B3, PO, EPI_BIAS_RELU_MASK, hb.y2, hb.y2b, nullptr));
+  V2S_TRY(linear(hb.y2, PO, H_W4, H_B4, PO, EPI_STORE, hb.pr, nullptr, nullptr));
+  V2S_TRY(linear(ft, PI, H_W1, H_B1, PH, EPI_BIAS_RELU_MASK, hb.a1t, hb.y1t, mt));
+  V2S_TRY(linear(hb.y1t, PH, H_W2, H_B2, PO, EPI_STORE, hb.zt, nullptr, nullptr));
+  if (pred_out) V2S_CUDA_OK(cudaMemcpyAsync(pred_out, hb.pr, (size_t)B * PO * 4, cudaMemcpyDeviceToDevice, st));
+  if (tgt_out) V2S_CUDA_OK(cudaMemcpyAsync(tgt_out, hb.zt, (size_t)B * PO * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// autograd backward of the online branch of the heads: dpred [B,128] -> head grads (+=), dfeat_online
+static int heads_backward_impl(const float* hp, float* hg, const float* fo, const float* mo, const float* dpred,
+                               float* dfo, int B, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  if (!hp || !hg || !fo || !dfo) { set_error("heads_backward: null argument"); return 1; }
+  HeadsBufs hb;
+  V2S_TRY(heads_bufs(ws, ws_bytes, B, &hb));
+  const float* dp = dpred ? dpred : hb.dp;
+  const int PH = V2S_PROJ_HID, PO = V2S_PROJ_OUT, PI = V2S_PROJ_IN;
+  auto wgrad = [&](const float* dy, int n, const float* x, int k, int64_t woff) -> int {
+    GemmDesc d = make_gemm_desc();
+    d.M = n; d.N = k; d.K = B; d.a_rs = 1; d.a_cs = n; d.b_rs = k; d.b_cs = 1; d.epi = EPI_ACCUM; d.ldc = k;
+    d.A[0] = dy; d.B[0] = x; d.out[0] = hg + woff;
+    return launch_gemm_simt(d, 0, 0, 0, st);
+  };
+  auto bgrad = [&](const float* dy, int n, int64_t boff) -> int {
+    const void* s[1] = {dy}; float* o[1] = {hg + boff};
+    return launch_colsum(s, o, 1, B, n, 0, st);
+  };
+  auto dgrad = [&](const float* dy, int n, int64_t woff, int k, float* out, int epi, const float* relu_src,
+                   const float* mask) -> int {
+    GemmDesc d = make_gemm_desc();
+    d.M = B; d.N = k; d.K = n; d.a_rs = n; d.a_cs = 1; d.b_rs = k; d.b_cs = 1; d.epi = epi; d.ldc = k;
+    d.A[0] = dy; d.B[0] = hp + woff; d.out[0] = out; d.aux[0] = relu_src; d.mask[0] = mask;
+    return launch_gemm_simt(d, 0, 0, 0, st);
+  };
+  V2S_TRY(wgrad(dp, PO, hb.y2, PO, H_W4));
+  V2S_TRY(bgrad(dp, PO, H_B4));
+  V2S_TRY(dgrad(dp, PO, H_W4, PO, hb.dy2, EPI_DRELU_MASK, hb.y2, nullptr));
+  V2S_TRY(wgrad(hb.dy2, PO, hb.z, PO, H_W3));
+  V2S_TRY(bgrad(hb.dy2, PO, H_B3));
+  V2S_TRY(dgrad(hb.dy2, PO, H_W3, PO, hb.dz, EPI_STORE, nullptr, nullptr));
+  V2S_TRY(wgrad(hb.dz, PO, hb.y1, PH, H_W2));
+  V2S_TRY(bgrad(hb.dz, PO, H_B2));
+  V2S_TRY(dgrad(hb.dz, PO, H_W2, PH, hb.dy1, EPI_DRELU_MASK, hb.a1, mo));
+  V2S_TRY(wgrad(hb.dy1, PH, fo, PI, H_W1));
+  V2S_TRY(bgrad(hb.dy1, PH, H_B1));
+  V2S_TRY(dgrad(hb.dy1, PH, H_W1, PI, dfo, EPI_STORE, nullptr, nullptr));
+  return 0;
+}
+
+static int heads_impl(const float* hp, float* hg, const float* fo, const float* ft, const float* mo, const float* mt,
+                      float* dfo, float* pred_out, float* tgt_out, float* loss, int B, int accum, float grad_scale,
+                      int with_backward, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  if (!loss) { set_error("heads: null loss"); return 1; }
+  V2S_TRY(heads_forward_impl(hp, fo, ft, mo, mt, pred_out, tgt_out, B, ws, ws_bytes, st));
+  HeadsBufs hb;
+  V2S_TRY(heads_bufs(ws, ws_bytes, B, &hb));
+  V2S_TRY(launch_cosine_loss(hb.pr, hb.zt, loss, with_backward ? hb.dp : nullptr, B, accum, grad_scale, st));
+  if (!with_backward) return 0;
+  return heads_backward_impl(hp, hg, fo, mo, nullptr, dfo, B, ws, ws_bytes, st);
+}
+
+}  // namespace v2s
+
+// =============================================================================================
+// extern "C" boundary
+// =============================================================================================
+using namespace v2s;
+
+extern "C" {
+
+int v2s_abi_version(void) { return V2S_ABI_VERSION; }
+const char* v2s_last_error(void) { return g_err; }
+
+int v2s_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) { set_error("no CUDA device: %s (there is no CPU fallback)", cudaGetErrorString(e)); return 1; }
+  if (device < 0 || device >= n) { set_error("device %d out of range (%d devices)", device, n); return 1; }
+  cudaDeviceProp prop;
+  V2S_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+    return 1;
+  }
+  V2S_CUDA_OK(cudaSetDevice(device));
+  return gemm_tc_init();
+}
+
+int64_t v2s_backbone_numel(void) { return BACKBONE_NUMEL; }
+int64_t v2s_backbone_active_numel(void) { return OFF_ACTIVE_END; }
+int64_t v2s_heads_numel(void) { return HEADS_NUMEL; }
+
+int v2s_backbone_layout(int64_t* o) {
+  if (!o) { set_error("null"); return 1; }
+  int i = 0;
+  o[i++] = OFF_CLS; o[i++] = OFF_POS; o[i++] = OFF_WPE; o[i++] = OFF_BPE;
+  for (int l = 0; l < NL; ++l) {
+    const int64_t lo = layer_off(l);
+    o[i++] = lo + L_WQKV;               o[i++] = lo + L_BQKV;            // query
+    o[i++] = lo + L_WQKV + D * D;       o[i++] = lo + L_BQKV + D;        // key
+    o[i++] = lo + L_WQKV + 2 * D * D;   o[i++] = lo + L_BQKV + 2 * D;    // value
+    o[i++] = lo + L_WO; o[i++] = lo + L_BO;
+    o[i++] = lo + L_W1; o[i++] = lo + L_B1;
+    o[i++] = lo + L_W2; o[i++] = lo + L_B2;
+    o[i++] = lo + L_LN1W; o[i++] = lo + L_LN1B; o[i++] = lo + L_LN2W; o[i++] = lo + L_LN2B;
+  }
+  o[i++] = OFF_LNF_W; o[i++] = OFF_LNF_B; o[i++] = OFF_POOL_W; o[i++] = OFF_POOL_B;
+  return i == 200 ? 0 : 1;
+}
+
+int v2s_heads_layout(int64_t* o) {
+  if (!o) { set_error("null"); return 1; }
+  o[0] = H_W1; o[1] = H_B1; o[2] = H_W2; o[3] = H_B2; o[4] = H_W3; o[5] = H_B3; o[6] = H_W4; o[7] = H_B4;
+  return 0;
+}
+
+int64_t v2s_workspace_bytes(int batch, int mode, int n_groups, int n_saved) {
+  if (batch < 1 || n_groups < 0 || n_groups > MAXG || n_saved < 0 || n_saved > MAXG) return -1;
+  return plan_total(make_plan(batch, mode), n_groups, n_saved);
+}
+
+int v2s_backbone_forward(const v2s_group_t* groups, int n_groups, int batch, int mode, void* workspace,
+                         int64_t workspace_bytes, void* stream) {
+  if (!groups) { set_error("null groups"); return 1; }
+  return backbone_forward_impl(groups, n_groups, batch, mode, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int v2s_backbone_backward(const v2s_group_t* groups, int n_groups, int batch, int mode, void* workspace,
+                          int64_t workspace_bytes, void* stream) {
+  if (!groups) { set_error("null groups"); return 1; }
+  return backbone_backward_impl(groups, n_groups, batch, mode, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int v2s_heads_loss_fwd_bwd(const float* head_params, float* head_grads, const float* feat_online,
+                           const float* feat_target, const float* mask_online, const float* mask_target,
+                           float* dfeat_online, float* pred, float* target_proj, float* loss, int batch,
+                           int accumulation_steps, float grad_scale, int with_backward, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
+  if (batch < 1 || accumulation_steps < 1) { set_error("heads: bad batch/accumulation_steps"); return 1; }
+  return heads_impl(head_params, head_grads, feat_online, feat_target, mask_online, mask_target, dfeat_online, pred,
+                    target_proj, loss, batch, accumulation_steps, grad_scale, with_backward, workspace,
+                    workspace_bytes, (cudaStream_t)stream);
+}
+
+int v2s_heads_forward(const float* head_params, const float* feat_online, const float* feat_target,
+                      const float* mask_online, const float* mask_target, float* pred, float* target_proj, int batch,
+                      void* workspace, int64_t workspace_bytes, void* stream) {
+  if (batch < 1) { set_error("heads_forward: bad batch"); return 1; }
+  return heads_forward_impl(head_params, feat_online, feat_target, mask_online, mask_target, pred, target_proj, batch,
+                            workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int v2s_heads_backward(const float* head_params, float* head_grads, const float* feat_online,
+                       const float* mask_online, const float* dpred, float* dfeat_online, int batch, void* workspace,
+                       int64_t workspace_bytes, void* stream) {
+  if (batch < 1 || !dpred) { set_error("heads_backward: bad argument"); return 1; }
+  return heads_backward_impl(head_params, head_grads, feat_online, mask_online, dpred, dfeat_online, batch, workspace,
+                             workspace_bytes, (cudaStream_t)stream);
+}
+
+int v2s_cosine_loss(const float* pred, const float* target_proj, float* loss, float* dpred, int batch,
+                    int accumulation_steps, float grad_scale, void* stream) {
+  if (!pred || !target_proj || !loss || batch < 1 || accumulation_steps < 1) { set_error("cosine_loss: bad argument"); return 1; }
+  return launch_cosine_loss(pred, target_proj, loss, dpred, batch, accumulation_steps, grad_scale, (cudaStream_t)stream);
+}
+
+int v2s_dropout_mask(float* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
+  if (!mask || n < 0 || p < 0.f || p >= 1.f) { set_error("dropout_mask: bad argument"); return 1; }
+  if (n == 0) return 0;
+  return launch_dropout_mask(mask, n, p, seed, offset, (cudaStream_t)stream);
+}
+
+int v2s_adam_step(const v2s_range_t* ranges, int n_ranges, int64_t step, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, float grad_scale, void* stream) {
+  if (!ranges || step < 1) { set_error("adam: bad argument"); return 1; }
+  for (int i = 0; i < n_ranges; ++i)
+    if ((reinterpret_cast<uintptr_t>(ranges[i].params) | reinterpret_cast<uintptr_t>(ranges[i].grads) |
+         reinterpret_cast<uintptr_t>(ranges[i].exp_avg) | reinterpret_cast<uintptr_t>(ranges[i].exp_avg_sq)) & 15) {
+      set_error("adam: range %d is not 16-byte aligned", i);
+      return 1;
+    }
+  return launch_adam(ranges, n_ranges, step, lr, beta1, beta2, eps, weight_decay, grad_scale, (cudaStream_t)stream);
+}
+
+int v2s_ema_update(float* const* targets, const float* const* onlines, void* const* targets_lp, int n_pairs,
+                   int64_t numel, float momentum, void* stream) {
+  if (!targets || !onlines) { set_error("ema: null"); return 1; }
+  return launch_ema(targets, onlines, targets_lp, n_pairs, numel, momentum, (cudaStream_t)stream);
+}
+
+int v2s_cast_bf16(const float* src, void* dst, int64_t numel, void* stream) {
+  if (!src || !dst || numel < 0) { set_error("cast: bad argument"); return 1; }
+  if (numel == 0) return 0;
+  return launch_cast_bf16(src, dst, numel, (cudaStream_t)stream);
+}
+
+int v2s_preprocess_u8(const uint8_t* src, float* dst, int batch, void* stream) {
+  if (!src || !dst || batch < 1) { set_error("preprocess: bad argument"); return 1; }
+  return launch_preprocess_u8(src, dst, batch, (cudaStream_t)stream);
+}
+
+int64_t v2s_launch_count(void) { return g_launch_count; }
+
+int v2s_prof_enable(int on) {
+  prof::enabled = on != 0;
+  prof::n_recs = 0;
+  return 0;
+}
+
+// writes one line per kernel class: "<name> <launches> <total_ms> <work>" (work = FLOPs for
+// GEMM/attention classes, bytes for the memory-bound ones); synchronises the device.
+int v2s_prof_report(char* host_buf, int64_t buf_bytes) {
+  if (!host_buf || buf_bytes < 64) { set_error("prof_report: buffer too small"); return 1; }
+  V2S_CUDA_OK(cudaDeviceSynchronize());
+  double ms[prof::C_COUNT] = {0}, work[prof::C_COUNT] = {0};
+  int cnt[prof::C_COUNT] = {0};
+  for (int i = 0; i < prof::n_recs; ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, prof::recs[i].a, prof::recs[i].b) != cudaSuccess) continue;
+    ms[prof::recs[i].cls] += t; work[prof::recs[i].cls] += prof::recs[i].work; cnt[prof::recs[i].cls]++;
+  }
+  int64_t off = 0;
+  host_buf[0] = 0;
+  for (int c = 0; c < prof::C_COUNT; ++c) {
+    if (!cnt[c]) continue;
+    int n = snprintf(host_buf + off, (size_t)(buf_bytes - off), "%s %d %.6f %.6e\n", prof::names[c], cnt[c], ms[c], work[c]);
+    if (n < 0 || off + n >= buf_bytes) break;
+    off += n;
+  }
+  prof::n_recs = 0;
+  return 0;
+}
+
+int v2s_test_gemm(int which, const void* a, const void* b, void* c, int m, int n, int k, int variant, void* stream) {
+  return gemm_tc_test(which, a, b, c, m, n, k, variant, (cudaStream_t)stream);
+}
+
+}  // extern "C"

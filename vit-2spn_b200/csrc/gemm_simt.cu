@@ -1,0 +1,168 @@
+// Generic grouped SIMT GEMM (fp32 accumulate) with fused epilogues.  See gemm_simt.cuh.
+#include <string.h>
+
+#include "gemm_simt.cuh"
+
+namespace v2s {
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;
+
+__device__ __forceinline__ int64_t remap_row(int64_t r) { return r + r / NP + 1; }
+
+template <typename TA, typename TB, typename TO>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
+  __shared__ float As[BK][BM + PAD];
+  __shared__ float Bs[BK][BN + PAD];
+  const int g = blockIdx.z;
+  const TA* __restrict__ A = static_cast<const TA*>(d.A[g]);
+  const TB* __restrict__ B = static_cast<const TB*>(d.B[g]);
+  const int tiles_n = (d.N + BN - 1) / BN;
+  const int tile_n = blockIdx.y % tiles_n;
+  const int split = blockIdx.y / tiles_n;
+  const int m0 = blockIdx.x * BM, n0 = tile_n * BN;
+  int k_begin = 0, k_end = d.K;
+  if (d.split_k > 1) {
+    int chunk = ((d.K + d.split_k - 1) / d.split_k + BK - 1) / BK * BK;
+    k_begin = split * chunk;
+    k_end = min(d.K, k_begin + chunk);
+  }
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const bool a_kfast = (d.a_cs == 1);
+  const bool b_kfast = (d.b_rs == 1);
+
+  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;
+      int kk, mm;
+      if (a_kfast) { kk = e % BK; mm = e / BK; } else { mm = e % BM; kk = e / BM; }
+      const int m = m0 + mm, k = k0 + kk;
+      float v = 0.f;
+      if (m < d.M && k < k_end) {
+        const int64_t row = d.a_remap == 1 ? remap_row(m) : (int64_t)m;
+        const int64_t col = d.a_remap == 2 ? remap_row(k) : (int64_t)k;
+        v = to_f<TA>(A[row * d.a_rs + col * d.a_cs]);
+      }
+      As[kk][mm] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;
+      int kk, nn;
+      if (b_kfast) { kk = e % BK; nn = e / BK; } else { nn = e % BN; kk = e / BN; }
+      const int n = n0 + nn, k = k0 + kk;
+      float v = 0.f;
+      if (n < d.N && k < k_end) {
+        const int64_t krow = d.b_remap ? remap_row(k) : (int64_t)k;
+        v = to_f<TB>(B[krow * d.b_rs + (int64_t)n * d.b_cs]);
+      }
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue ----
+  const float* __restrict__ bias = d.bias[g];
+  const float* __restrict__ resid = d.resid[g];
+  const float* __restrict__ mask = d.mask[g];
+  TO* __restrict__ out = static_cast<TO*>(d.out[g]);
+  TO* __restrict__ out2 = static_cast<TO*>(d.out2[g]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= d.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= d.N) continue;
+      float v = acc[i][j] * d.alpha;
+      const int64_t idx = (int64_t)m * d.ldc + n;
+      switch (d.epi) {
+        case EPI_STORE:
+          if (bias) v += bias[n];
+          out[idx] = from_f<TO>(v);
+          break;
+        case EPI_BIAS_RESID:
+          v += bias[n] + resid[idx];
+          out[idx] = from_f<TO>(v);
+          break;
+        case EPI_BIAS_GELU:
+          v += bias[n];
+          if (out) out[idx] = from_f<TO>(v);
+          out2[idx] = from_f<TO>(gelu_f(v));
+          break;
+        case EPI_PATCH: {
+          const int b = m / NP, p = m % NP;
+          const float* pos = static_cast<const float*>(d.aux[g]);
+          v += bias[n] + pos[(int64_t)(1 + p) * D + n];
+          out[((int64_t)b * NT + 1 + p) * d.ldc + n] = from_f<TO>(v);
+        } break;
+        case EPI_DGELU: {
+          const TO* u = static_cast<const TO*>(d.aux[g]);
+          out[idx] = from_f<TO>(v * gelu_grad_f(to_f<TO>(u[idx])));
+        } break;
+        case EPI_ACCUM:
+          atomicAdd(reinterpret_cast<float*>(d.out[g]) + idx, v);
+          break;
+        case EPI_BIAS_RELU_MASK: {
+          v = fmaxf(v + bias[n], 0.f);
+          out[idx] = from_f<TO>(v);
+          out2[idx] = from_f<TO>(mask ? v * mask[idx] : v);
+        } break;
+        case EPI_DRELU_MASK: {
+          const float* src = static_cast<const float*>(d.aux[g]);
+          float t = src[idx] > 0.f ? v : 0.f;
+          if (mask) t *= mask[idx];
+          out[idx] = from_f<TO>(t);
+        } break;
+        default: break;
+      }
+    }
+  }
+}
+
+template <typename TA, typename TB, typename TO>
+int launch_t(const GemmDesc& d, cudaStream_t stream) {
+  const int tiles_m = (d.M + BM - 1) / BM, tiles_n = (d.N + BN - 1) / BN;
+  dim3 grid(tiles_m, tiles_n * (d.split_k > 1 ? d.split_k : 1), d.groups);
+  gemm_simt_kernel<TA, TB, TO><<<grid, 256, 0, stream>>>(d);
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+int launch_gemm_simt(const GemmDesc& d, int ta, int tb, int to, cudaStream_t stream) {
+  if (d.M <= 0 || d.N <= 0 || d.K <= 0) return 0;
+  if (d.split_k > 1 && d.epi != EPI_ACCUM) {
+    set_error("gemm_simt: split_k requires EPI_ACCUM");
+    return 1;
+  }
+  if (ta == 0 && tb == 0 && to == 0) return launch_t<float, float, float>(d, stream);
+  if (ta == 1 && tb == 1 && to == 1) return launch_t<bf16, bf16, bf16>(d, stream);
+  if (ta == 1 && tb == 1 && to == 0) return launch_t<bf16, bf16, float>(d, stream);
+  set_error("gemm_simt: unsupported type combination %d %d %d", ta, tb, to);
+  return 1;
+}
+
+}  // namespace v2s

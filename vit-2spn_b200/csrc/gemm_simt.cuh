@@ -1,0 +1,52 @@
+// Generic grouped SIMT GEMM with fused epilogues: the fp32 check-mode GEMM and the debugging
+// reference for the tcgen05 kernels.  C[M,N] = sum_k A(m,k) * B(k,n), arbitrary strides.
+#pragma once
+#include "common.cuh"
+
+namespace v2s {
+
+enum GemmEpi : int {
+  EPI_STORE = 0,        // out = alpha*acc (+ bias)
+  EPI_BIAS_RESID = 1,   // out(fp32) = acc + bias + resid
+  EPI_BIAS_GELU = 2,    // u = acc + bias -> out (optional); gelu(u) -> out2
+  EPI_PATCH = 3,        // patch-embed: token-row remap, + bias + position embedding (aux)
+  EPI_DGELU = 4,        // out = acc * gelu'(aux)
+  EPI_ACCUM = 5,        // atomicAdd(out(fp32), alpha*acc)  (wgrad, split-K)
+  EPI_BIAS_RELU_MASK = 6,  // a = relu(acc+bias) -> out ; a*mask -> out2
+  EPI_DRELU_MASK = 7,      // out = acc * (aux > 0) * mask
+};
+
+struct GemmDesc {
+  int M, N, K;
+  int64_t a_rs, a_cs;  // A(m,k) = A[m*a_rs + k*a_cs]
+  int64_t b_rs, b_cs;  // B(k,n) = B[k*b_rs + n*b_cs]
+  int a_remap;         // patch index b*196+p -> token row b*197+1+p: 1 = on A's m index, 2 = on A's k index
+  int b_remap;         // same for the K index of B (wgrad of the patch embedding)
+  int split_k;         // number of K splits (EPI_ACCUM only)
+  int groups;
+  const void* A[MAXG];
+  const void* B[MAXG];
+  int epi;
+  const float* bias[MAXG];
+  const float* resid[MAXG];
+  const void* aux[MAXG];
+  const float* mask[MAXG];
+  void* out[MAXG];
+  void* out2[MAXG];
+  int64_t ldc;
+  float alpha;
+};
+
+inline GemmDesc make_gemm_desc() {
+  GemmDesc d;
+  memset(&d, 0, sizeof(d));
+  d.alpha = 1.0f;
+  d.split_k = 1;
+  d.groups = 1;
+  return d;
+}
+
+// type tags: 0 = fp32, 1 = bf16
+int launch_gemm_simt(const GemmDesc& d, int ta, int tb, int to, cudaStream_t stream);
+
+}  // namespace v2s

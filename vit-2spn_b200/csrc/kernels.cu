@@ -1,0 +1,730 @@
+// Memory-bound kernels of the SSP step: im2col, LayerNorm fwd/bwd, bias-gradient column sums,
+// token mean-pool, embedding backward, cosine loss (+backward), Adam, EMA, casts, dropout mask,
+// synthetic input pipeline.  All are coalesced / vectorised HBM kernels with warp-shuffle
+// reductions; grouped kernels use blockIdx.y|z as the backbone index.
+#include "kernels.cuh"
+
+namespace v2s {
+
+namespace {
+
+template <typename T> struct G4 { T p[MAXG]; };
+template <typename T, typename S> G4<T> pack4(S const* src, int groups) {
+  G4<T> r;
+  for (int i = 0; i < MAXG; ++i) r.p[i] = (src && i < groups) ? (T)src[i] : (T) nullptr;
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// im2col: NCHW fp32 image → patch matrix [B*196, 768], k = c*256 + ky*16 + kx
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void im2col_kernel(G4<const float*> x, G4<T*> out, int B) {
+  const int g = blockIdx.y;
+  const int64_t total = (int64_t)B * NP * (KPE / 4);
+  const float* __restrict__ xin = x.p[g];
+  T* __restrict__ o = out.p[g];
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int kx4 = idx % 4;
+    const int ky = (idx / 4) % 16;
+    const int c = (idx / 64) % 3;
+    const int p = (idx / 192) % NP;
+    const int b = idx / (192 * NP);
+    const int py = p / 14, px = p % 14;
+    const float4 v = *reinterpret_cast<const float4*>(
+        xin + (((int64_t)b * 3 + c) * V2S_IMG + py * 16 + ky) * V2S_IMG + px * 16 + kx4 * 4);
+    T* dst = o + ((int64_t)b * NP + p) * KPE + c * 256 + ky * 16 + kx4 * 4;
+    dst[0] = from_f<T>(v.x); dst[1] = from_f<T>(v.y); dst[2] = from_f<T>(v.z); dst[3] = from_f<T>(v.w);
+  }
+}
+
+__global__ void cls_rows_kernel(G4<const float*> params, G4<float*> hidden) {
+  const int g = blockIdx.y, b = blockIdx.x, n = threadIdx.x;
+  const float* p = params.p[g];
+  hidden.p[g][(int64_t)b * NT * D + n] = p[OFF_CLS + n] + p[OFF_POS + n];
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over D=192 (eps 1e-12): one warp per row, 6 elements per lane as 3 float2
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(G4<const float*> x, G4<const float*> gamma,
+                                                     G4<const float*> beta, G4<T*> y, G4<float*> mean,
+                                                     G4<float*> rstd, int M) {
+  const int g = blockIdx.y;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float2* xr = reinterpret_cast<const float2*>(x.p[g] + (int64_t)row * D);
+  float2 v[3];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { v[i] = xr[lane + 32 * i]; s += v[i].x + v[i].y; }
+  const float mu = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { const float a = v[i].x - mu, b = v[i].y - mu; q += a * a + b * b; }
+  const float var = warp_sum(q) * (1.0f / D);
+  const float rs = 1.0f / sqrtf(var + LN_EPS);
+  const float2* gm = reinterpret_cast<const float2*>(gamma.p[g]);
+  const float2* bt = reinterpret_cast<const float2*>(beta.p[g]);
+  T* yr = y.p[g] + (int64_t)row * D;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int c = lane + 32 * i;
+    const float2 gg = gm[c], bb = bt[c];
+    yr[2 * c] = from_f<T>((v[i].x - mu) * rs * gg.x + bb.x);
+    yr[2 * c + 1] = from_f<T>((v[i].y - mu) * rs * gg.y + bb.y);
+  }
+  if (lane == 0 && mean.p[g]) { mean.p[g][row] = mu; rstd.p[g][row] = rs; }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(G4<const T*> dy, G4<const float*> x,
+                                                     G4<const float*> mean, G4<const float*> rstd,
+                                                     G4<const float*> gamma, G4<float*> dres,
+                                                     G4<T*> dres_lp, G4<float*> dgamma, G4<float*> dbeta,
+                                                     int M) {
+  __shared__ float red[8][2 * D];
+  const int g = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float2* gm = reinterpret_cast<const float2*>(gamma.p[g]);
+  float2 gg[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) gg[i] = gm[lane + 32 * i];
+  float2 ag[3], ab[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { ag[i] = make_float2(0.f, 0.f); ab[i] = make_float2(0.f, 0.f); }
+
+  for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
+    const float mu = mean.p[g][row], rs = rstd.p[g][row];
+    const float2* xr = reinterpret_cast<const float2*>(x.p[g] + (int64_t)row * D);
+    const T* dyr = dy.p[g] + (int64_t)row * D;
+    float2 xh[3], gd[3];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int c = lane + 32 * i;
+      const float2 xv = xr[c];
+      const float d0 = to_f<T>(dyr[2 * c]), d1 = to_f<T>(dyr[2 * c + 1]);
+      xh[i] = make_float2((xv.x - mu) * rs, (xv.y - mu) * rs);
+      gd[i] = make_float2(d0 * gg[i].x, d1 * gg[i].y);
+      c1 += gd[i].x + gd[i].y;
+      c2 += gd[i].x * xh[i].x + gd[i].y * xh[i].y;
+      ag[i].x += d0 * xh[i].x; ag[i].y += d1 * xh[i].y;
+      ab[i].x += d0; ab[i].y += d1;
+    }
+    c1 = warp_sum(c1) * (1.0f / D);
+    c2 = warp_sum(c2) * (1.0f / D);
+    float2* dr = reinterpret_cast<float2*>(dres.p[g] + (int64_t)row * D);
+    T* dl = dres_lp.p[g] ? dres_lp.p[g] + (int64_t)row * D : nullptr;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int c = lane + 32 * i;
+      float2 o = dr[c];
+      o.x += rs * (gd[i].x - c1 - xh[i].x * c2);
+      o.y += rs * (gd[i].y - c1 - xh[i].y * c2);
+      dr[c] = o;
+      if (dl) { dl[2 * c] = from_f<T>(o.x); dl[2 * c + 1] = from_f<T>(o.y); }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int c = 2 * (lane + 32 * i);
+    red[warp][c] = ag[i].x; red[warp][c + 1] = ag[i].y;
+    red[warp][D + c] = ab[i].x; red[warp][D + c + 1] = ab[i].y;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][c];
+    if (c < D) atomicAdd(dgamma.p[g] + c, s); else atomicAdd(dbeta.p[g] + (c - D), s);
+  }
+}
+
+// db[n] += sum_m dy[m,n]
+template <typename T>
+__global__ void colsum_kernel(G4<const T*> dy, G4<float*> db, int M, int N, int rows_per_block) {
+  __shared__ float red[8][33];
+  const int g = blockIdx.z;
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float s = 0.f;
+  if (n < N)
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) s += to_f<T>(dy.p[g][(int64_t)r * N + n]);
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(db.p[g] + n, t);
+  }
+}
+
+__global__ void pool_fwd_kernel(G4<const float*> hidden, G4<float*> feat, G4<int64_t> stride) {
+  const int g = blockIdx.y, b = blockIdx.x, n = threadIdx.x;
+  const float* h = hidden.p[g] + (int64_t)b * NT * D + n;
+  float s = 0.f;
+  for (int t = 0; t < NT; ++t) s += h[(int64_t)t * D];
+  feat.p[g][(int64_t)b * stride.p[g] + n] = s * (1.0f / NT);
+}
+
+template <typename T>
+__global__ void pool_bwd_kernel(G4<const float*> dfeat, G4<int64_t> stride, G4<const float*> dhidden,
+                                G4<float*> dx, G4<T*> dx_lp) {
+  const int g = blockIdx.z, b = blockIdx.y, t = blockIdx.x, n = threadIdx.x;
+  const int64_t idx = ((int64_t)b * NT + t) * D + n;
+  float v = dfeat.p[g] ? dfeat.p[g][(int64_t)b * stride.p[g] + n] * (1.0f / NT) : 0.f;
+  if (dhidden.p[g]) v += dhidden.p[g][idx];
+  dx.p[g][idx] = v;
+  if (dx_lp.p[g]) dx_lp.p[g][idx] = from_f<T>(v);
+}
+
+// d pos / d cls / d patch-bias from the gradient of the embedding output
+__global__ void embed_bwd_kernel(G4<const float*> dx, G4<float*> grads, int B) {
+  const int g = blockIdx.y, t = blockIdx.x, n = threadIdx.x;
+  const float* d = dx.p[g] + (int64_t)t * D + n;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += d[(int64_t)b * NT * D];
+  float* gr = grads.p[g];
+  gr[OFF_POS + (int64_t)t * D + n] += s;
+  if (t == 0) gr[OFF_CLS + n] += s;
+  else atomicAdd(gr + OFF_BPE + n, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// SIMT attention (fp32 check mode / debugging reference).  One CTA per (head, image, group).
+// ------------------------------------------------------------------------------------------
+constexpr int ASTR = DH + 1;  // odd row stride: conflict-free when lanes walk rows
+
+template <typename T>
+__global__ void __launch_bounds__(256) attn_fwd_simt_kernel(G4<const T*> qkv, G4<T*> ctx, G4<float*> lse) {
+  extern __shared__ float sm[];
+  float* Ks = sm;                    // [197][65]
+  float* Vs = Ks + NT * ASTR;        // [197][65]
+  float* Ps = Vs + NT * ASTR;        // [8][200]
+  float* Qs = Ps + 8 * 200;          // [8][64]
+  const int h = blockIdx.x, b = blockIdx.y, g = blockIdx.z;
+  const T* base = qkv.p[g] + (int64_t)b * NT * 3 * D;
+  for (int i = threadIdx.x; i < NT * DH; i += blockDim.x) {
+    const int t = i / DH, d = i % DH;
+    Ks[t * ASTR + d] = to_f<T>(base[(int64_t)t * 3 * D + D + h * DH + d]);
+    Vs[t * ASTR + d] = to_f<T>(base[(int64_t)t * 3 * D + 2 * D + h * DH + d]);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* P = Ps + warp * 200;
+  float* Q = Qs + warp * DH;
+  const float scale = 0.125f;  // 64^-0.5
+  for (int i = warp; i < NT; i += 8) {
+    Q[lane] = to_f<T>(base[(int64_t)i * 3 * D + h * DH + lane]);
+    Q[lane + 32] = to_f<T>(base[(int64_t)i * 3 * D + h * DH + lane + 32]);
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int j = lane; j < NT; j += 32) {
+      float s = 0.f;
+#pragma unroll 16
+      for (int d = 0; d < DH; ++d) s = fmaf(Q[d], Ks[j * ASTR + d], s);
+      s *= scale;
+      P[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < NT; j += 32) { const float e = expf(P[j] - mx); P[j] = e; sum += e; }
+    sum = warp_sum(sum);
+    __syncwarp();
+    const float inv = 1.0f / sum;
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < NT; ++j) {
+      const float p = P[j];
+      o0 = fmaf(p, Vs[j * ASTR + lane], o0);
+      o1 = fmaf(p, Vs[j * ASTR + lane + 32], o1);
+    }
+    T* out = ctx.p[g] + ((int64_t)b * NT + i) * D + h * DH;
+    out[lane] = from_f<T>(o0 * inv);
+    out[lane + 32] = from_f<T>(o1 * inv);
+    if (lane == 0 && lse.p[g]) lse.p[g][((int64_t)b * NH + h) * NT + i] = mx + logf(sum);
+    __syncwarp();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) attn_bwd_simt_kernel(G4<const T*> qkv, G4<const T*> ctx,
+                                                            G4<const float*> lse, G4<const T*> dctx,
+                                                            G4<T*> dqkv) {
+  extern __shared__ float sm[];
+  float* Qs = sm;                     // [197][65]
+  float* Ks = Qs + NT * ASTR;
+  float* Vs = Ks + NT * ASTR;
+  float* dOs = Vs + NT * ASTR;
+  float* Ls = dOs + NT * ASTR;        // [197] lse
+  float* Ds = Ls + NT;                // [197] rowsum(dO * O)
+  float* Ps = Ds + NT;                // [8][200]
+  float* dSs = Ps + 8 * 200;          // [8][200]
+  const int h = blockIdx.x, b = blockIdx.y, g = blockIdx.z;
+  const T* base = qkv.p[g] + (int64_t)b * NT * 3 * D;
+  const T* ob = ctx.p[g] + (int64_t)b * NT * D + h * DH;
+  const T* dob = dctx.p[g] + (int64_t)b * NT * D + h * DH;
+  for (int i = threadIdx.x; i < NT * DH; i += blockDim.x) {
+    const int t = i / DH, d = i % DH;
+    Qs[t * ASTR + d] = to_f<T>(base[(int64_t)t * 3 * D + h * DH + d]);
+    Ks[t * ASTR + d] = to_f<T>(base[(int64_t)t * 3 * D + D + h * DH + d]);
+    Vs[t * ASTR + d] = to_f<T>(base[(int64_t)t * 3 * D + 2 * D + h * DH + d]);
+    dOs[t * ASTR + d] = to_f<T>(dob[(int64_t)t * D + d]);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = warp; t < NT; t += 8) {
+    float s = 0.f;
+    for (int d = lane; d < DH; d += 32) s += to_f<T>(ob[(int64_t)t * D + d]) * to_f<T>(dob[(int64_t)t * D + d]);
+    s = warp_sum(s);
+    if (lane == 0) { Ds[t] = s; Ls[t] = lse.p[g][((int64_t)b * NH + h) * NT + t]; }
+  }
+  __syncthreads();
+  float* P = Ps + warp * 200;
+  float* dS = dSs + warp * 200;
+  const float scale = 0.125f;
+  T* dq_base = dqkv.p[g] + (int64_t)b * NT * 3 * D;
+  // phase A: dQ_i = scale * sum_j dS_ij K_j
+  for (int i = warp; i < NT; i += 8) {
+    const float li = Ls[i], di = Ds[i];
+    for (int j = lane; j < NT; j += 32) {
+      float s = 0.f, dp = 0.f;
+#pragma unroll 16
+      for (int d = 0; d < DH; ++d) {
+        s = fmaf(Qs[i * ASTR + d], Ks[j * ASTR + d], s);
+        dp = fmaf(dOs[i * ASTR + d], Vs[j * ASTR + d], dp);
+      }
+      const float p = expf(s * scale - li);
+      dS[j] = p * (dp - di);
+    }
+    __syncwarp();
+    float a0 = 0.f, a1 = 0.f;
+    for (int j = 0; j < NT; ++j) {
+      const float w = dS[j];
+      a0 = fmaf(w, Ks[j * ASTR + lane], a0);
+      a1 = fmaf(w, Ks[j * ASTR + lane + 32], a1);
+    }
+    T* o = dq_base + (int64_t)i * 3 * D + h * DH;
+    o[lane] = from_f<T>(a0 * scale);
+    o[lane + 32] = from_f<T>(a1 * scale);
+    __syncwarp();
+  }
+  // phase B: dV_j = sum_i P_ij dO_i ; dK_j = scale * sum_i dS_ij Q_i
+  for (int j = warp; j < NT; j += 8) {
+    for (int i = lane; i < NT; i += 32) {
+      float s = 0.f, dp = 0.f;
+#pragma unroll 16
+      for (int d = 0; d < DH; ++d) {
+        s = fmaf(Qs[i * ASTR + d], Ks[j * ASTR + d], s);
+        dp = fmaf(dOs[i * ASTR + d], Vs[j * ASTR + d], dp);
+      }
+      const float p = expf(s * scale - Ls[i]);
+      P[i] = p;
+      dS[i] = p * (dp - Ds[i]);
+    }
+    __syncwarp();
+    float v0 = 0.f, v1 = 0.f, k0 = 0.f, k1 = 0.f;
+    for (int i = 0; i < NT; ++i) {
+      const float p = P[i], w = dS[i];
+      v0 = fmaf(p, dOs[i * ASTR + lane], v0);
+      v1 = fmaf(p, dOs[i * ASTR + lane + 32], v1);
+      k0 = fmaf(w, Qs[i * ASTR + lane], k0);
+      k1 = fmaf(w, Qs[i * ASTR + lane + 32], k1);
+    }
+    T* ok = dq_base + (int64_t)j * 3 * D + D + h * DH;
+    T* ov = dq_base + (int64_t)j * 3 * D + 2 * D + h * DH;
+    ok[lane] = from_f<T>(k0 * scale); ok[lane + 32] = from_f<T>(k1 * scale);
+    ov[lane] = from_f<T>(v0); ov[lane + 32] = from_f<T>(v1);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// loss = -mean_i cos(p_i, z_i) / accum   (torch CosineSimilarity: each norm clamped at 1e-8)
+// dp   = grad_scale * d loss / d p.  Single CTA (B rows x 128), deterministic reduction.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cosine_loss_kernel(const float* __restrict__ p,
+                                                          const float* __restrict__ z, float* loss,
+                                                          float* dp, int B, float inv_count,
+                                                          float grad_scale) {
+  __shared__ float part[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float eps = 1e-8f;
+  float acc = 0.f;
+  for (int i = warp; i < B; i += 8) {
+    const float4 pv = reinterpret_cast<const float4*>(p + (int64_t)i * V2S_PROJ_OUT)[lane];
+    const float4 zv = reinterpret_cast<const float4*>(z + (int64_t)i * V2S_PROJ_OUT)[lane];
+    float dot = pv.x * zv.x + pv.y * zv.y + pv.z * zv.z + pv.w * zv.w;
+    float pp = pv.x * pv.x + pv.y * pv.y + pv.z * pv.z + pv.w * pv.w;
+    float zz = zv.x * zv.x + zv.y * zv.y + zv.z * zv.z + zv.w * zv.w;
+    dot = warp_sum(dot); pp = warp_sum(pp); zz = warp_sum(zz);
+    const float pn = sqrtf(pp), zn = sqrtf(zz);
+    const float pc = fmaxf(pn, eps), zc = fmaxf(zn, eps);
+    const float cosv = dot / (pc * zc);
+    acc += cosv;
+    if (dp) {
+      // d cos / d p = z/(pc*zc) - [pn > eps] * cos * p / pn^2
+      const float a = 1.0f / (pc * zc);
+      const float c = (pn > eps) ? cosv / pp : 0.f;
+      const float s = -inv_count * grad_scale;
+      float4 o;
+      o.x = s * (zv.x * a - c * pv.x); o.y = s * (zv.y * a - c * pv.y);
+      o.z = s * (zv.z * a - c * pv.z); o.w = s * (zv.w * a - c * pv.w);
+      reinterpret_cast<float4*>(dp + (int64_t)i * V2S_PROJ_OUT)[lane] = o;
+    }
+  }
+  if (lane == 0) part[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    *loss = -t * inv_count;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam semantics) over up to 4 flat ranges; optional bf16 shadow refresh
+// ------------------------------------------------------------------------------------------
+struct AdamRanges {
+  v2s_range_t r[4];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) adam_kernel(AdamRanges rs, float step_size, float inv_bc2_sqrt,
+                                                   float b1, float b2, float eps, float wd,
+                                                   float grad_scale) {
+  const v2s_range_t r = rs.r[blockIdx.y];
+  const int64_t n4 = r.numel / 4;
+  float4* p4 = reinterpret_cast<float4*>(r.params);
+  const float4* g4 = reinterpret_cast<const float4*>(r.grads);
+  float4* m4 = reinterpret_cast<float4*>(r.exp_avg);
+  float4* v4 = reinterpret_cast<float4*>(r.exp_avg_sq);
+  bf16* lp = static_cast<bf16*>(r.params_lp);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 p = p4[i], g = g4[i], m = m4[i], v = v4[i];
+    float* pp = &p.x; float* gg = &g.x; float* mm = &m.x; float* vv = &v.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gr = gg[k] * grad_scale;
+      if (wd != 0.f) gr = fmaf(wd, pp[k], gr);
+      mm[k] = mm[k] + (gr - mm[k]) * (1.0f - b1);        // lerp, as torch
+      vv[k] = b2 * vv[k] + (1.0f - b2) * gr * gr;
+      const float denom = sqrtf(vv[k]) * inv_bc2_sqrt + eps;
+      pp[k] = pp[k] - step_size * (mm[k] / denom);
+    }
+    p4[i] = p; m4[i] = m; v4[i] = v;
+    if (lp) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(p.x, p.y), b = __floats2bfloat162_rn(p.z, p.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+      reinterpret_cast<uint2*>(lp)[i] = u;
+    }
+  }
+  // scalar tail (numel not a multiple of 4)
+  if (blockIdx.x == 0 && threadIdx.x < (r.numel & 3)) {
+    const int64_t i = n4 * 4 + threadIdx.x;
+    float gr = r.grads[i] * grad_scale;
+    if (wd != 0.f) gr = fmaf(wd, r.params[i], gr);
+    float m = r.exp_avg[i], v = r.exp_avg_sq[i];
+    m = m + (gr - m) * (1.0f - b1);
+    v = b2 * v + (1.0f - b2) * gr * gr;
+    const float denom = sqrtf(v) * inv_bc2_sqrt + eps;
+    const float pn = r.params[i] - step_size * (m / denom);
+    r.params[i] = pn; r.exp_avg[i] = m; r.exp_avg_sq[i] = v;
+    if (lp) lp[i] = __float2bfloat16_rn(pn);
+  }
+}
+
+struct EmaPairs {
+  float* t[4];
+  const float* o[4];
+  bf16* lp[4];
+};
+
+// target = m*target + (1-m)*online, rounded exactly as torch's two multiplies + add (ref:164)
+__global__ void __launch_bounds__(256) ema_kernel(EmaPairs pr, int64_t numel, float m, float om) {
+  float4* t4 = reinterpret_cast<float4*>(pr.t[blockIdx.y]);
+  const float4* o4 = reinterpret_cast<const float4*>(pr.o[blockIdx.y]);
+  bf16* lp = pr.lp[blockIdx.y];
+  const int64_t n4 = numel / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 t = t4[i];
+    const float4 o = o4[i];
+    t.x = __fadd_rn(__fmul_rn(m, t.x), __fmul_rn(om, o.x));
+    t.y = __fadd_rn(__fmul_rn(m, t.y), __fmul_rn(om, o.y));
+    t.z = __fadd_rn(__fmul_rn(m, t.z), __fmul_rn(om, o.z));
+    t.w = __fadd_rn(__fmul_rn(m, t.w), __fmul_rn(om, o.w));
+    t4[i] = t;
+    if (lp) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(t.x, t.y), b = __floats2bfloat162_rn(t.z, t.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+      reinterpret_cast<uint2*>(lp)[i] = u;
+    }
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n) {
+  const int64_t n4 = n / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(dst)[i] = u;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[n4 * 4 + threadIdx.x] = __float2bfloat16_rn(src[n4 * 4 + threadIdx.x]);
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void dropout_mask_kernel(float* mask, int64_t n, float p, float keep_scale, uint64_t seed,
+                                    uint64_t offset) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = splitmix64(splitmix64(seed) ^ (offset + (uint64_t)i));
+    const float u = (float)(r >> 40) * (1.0f / 16777216.0f);
+    mask[i] = (u >= p) ? keep_scale : 0.f;
+  }
+}
+
+// uint8 [B,1,28,28] → bilinear (align_corners=False) 224x224 → 3ch → ImageNet normalise
+__global__ void preprocess_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int B) {
+  const int64_t total = (int64_t)B * V2S_IMG * V2S_IMG;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int xo = idx % V2S_IMG, yo = (idx / V2S_IMG) % V2S_IMG, b = idx / (V2S_IMG * V2S_IMG);
+    const float sc = 28.0f / 224.0f;
+    float sx = fmaxf((xo + 0.5f) * sc - 0.5f, 0.f), sy = fmaxf((yo + 0.5f) * sc - 0.5f, 0.f);
+    const int x0 = (int)sx, y0 = (int)sy;
+    const int x1 = min(x0 + 1, 27), y1 = min(y0 + 1, 27);
+    const float lx = sx - x0, ly = sy - y0;
+    const uint8_t* s = src + (int64_t)b * 784;
+    const float k = 1.0f / 255.0f;
+    const float v00 = s[y0 * 28 + x0] * k, v01 = s[y0 * 28 + x1] * k, v10 = s[y1 * 28 + x0] * k, v11 = s[y1 * 28 + x1] * k;
+    const float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      dst[(((int64_t)b * 3 + c) * V2S_IMG + yo) * V2S_IMG + xo] = (v - mean[c]) / stdv[c];
+  }
+}
+
+inline int grid_for(int64_t n, int threads, int max_blocks = 148 * 8) {
+  int64_t b = (n + threads - 1) / threads;
+  if (b > max_blocks) b = max_blocks;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+int launch_im2col(const float* const* x, void* const* out, int groups, int B, int at, cudaStream_t s) {
+  dim3 grid(grid_for((int64_t)B * NP * (KPE / 4), 256, 148 * 16), groups);
+  if (at == 0) im2col_kernel<float><<<grid, 256, 0, s>>>(pack4<const float*>(x, groups), pack4<float*>(out, groups), B);
+  else im2col_kernel<bf16><<<grid, 256, 0, s>>>(pack4<const float*>(x, groups), pack4<bf16*>(out, groups), B);
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_cls_rows(const float* const* params, float* const* hidden, int groups, int B, cudaStream_t s) {
+  cls_rows_kernel<<<dim3(B, groups), D, 0, s>>>(pack4<const float*>(params, groups), pack4<float*>(hidden, groups));
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_ln_fwd(const float* const* x, const float* const* gamma, const float* const* beta, void* const* y,
+                  float* const* mean, float* const* rstd, int groups, int M, int at, cudaStream_t s) {
+  dim3 grid((M + 7) / 8, groups);
+  if (at == 0)
+    ln_fwd_kernel<float><<<grid, 256, 0, s>>>(pack4<const float*>(x, groups), pack4<const float*>(gamma, groups),
+                                              pack4<const float*>(beta, groups), pack4<float*>(y, groups),
+                                              pack4<float*>(mean, groups), pack4<float*>(rstd, groups), M);
+  else
+    ln_fwd_kernel<bf16><<<grid, 256, 0, s>>>(pack4<const float*>(x, groups), pack4<const float*>(gamma, groups),
+                                             pack4<const float*>(beta, groups), pack4<bf16*>(y, groups),
+                                             pack4<float*>(mean, groups), pack4<float*>(rstd, groups), M);
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_ln_bwd(const void* const* dy, const float* const* x, const float* const* mean, const float* const* rstd,
+                  const float* const* gamma, float* const* dres, void* const* dres_lp, float* const* dgamma,
+                  float* const* dbeta, int groups, int M, int at, cudaStream_t s) {
+  int bx = (M + 7) / 8;
+  if (bx > 148 * 4) bx = 148 * 4;
+  dim3 grid(bx, groups);
+  if (at == 0)
+    ln_bwd_kernel<float><<<grid, 256, 0, s>>>(pack4<const float*>(dy, groups), pack4<const float*>(x, groups),
+                                              pack4<const float*>(mean, groups), pack4<const float*>(rstd, groups),
+                                              pack4<const float*>(gamma, groups), pack4<float*>(dres, groups),
+                                              pack4<float*>(dres_lp, groups), pack4<float*>(dgamma, groups),
+                                              pack4<float*>(dbeta, groups), M);
+  else
+    ln_bwd_kernel<bf16><<<grid, 256, 0, s>>>(pack4<const bf16*>(dy, groups), pack4<const float*>(x, groups),
+                                             pack4<const float*>(mean, groups), pack4<const float*>(rstd, groups),
+                                             pack4<const float*>(gamma, groups), pack4<float*>(dres, groups),
+                                             pack4<bf16*>(dres_lp, groups), pack4<float*>(dgamma, groups),
+                                             pack4<float*>(dbeta, groups), M);
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_colsum(const void* const* dy, float* const* db, int groups, int M, int N, int t, cudaStream_t s) {
+  int splits = (M + 255) / 256;
+  if (splits > 128) splits = 128;
+  if (splits < 1) splits = 1;
+  const int rows_per_block = (M + splits - 1) / splits;
+  dim3 grid((N + 31) / 32, splits, groups), block(32, 8);
+  if (t == 0) colsum_kernel<float><<<grid, block, 0, s>>>(pack4<const float*>(dy, groups), pack4<float*>(db, groups), M, N, rows_per_block);
+  else colsum_kernel<bf16><<<grid, block, 0, s>>>(pack4<const bf16*>(dy, groups), pack4<float*>(db, groups), M, N, rows_per_block);
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_pool_fwd(const float* const* hidden, float* const* feat, const int64_t* feat_stride, int groups, int B,
+                    cudaStream_t s) {
+  G4<int64_t> st;
+  for (int i = 0; i < MAXG; ++i) st.p[i] = i < groups ? feat_stride[i] : 0;
+  pool_fwd_kernel<<<dim3(B, groups), D, 0, s>>>(pack4<const float*>(hidden, groups), pack4<float*>(feat, groups), st);
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_pool_bwd(const float* const* dfeat, const int64_t* dfeat_stride, const float* const* dhidden,
+                    float* const* dx, void* const* dx_lp, int groups, int B, int at, cudaStream_t s) {
+  G4<int64_t> st;
+  for (int i = 0; i < MAXG; ++i) st.p[i] = i < groups ? dfeat_stride[i] : 0;
+  dim3 grid(NT, B, groups);
+  if (at == 0)
+    pool_bwd_kernel<float><<<grid, D, 0, s>>>(pack4<const float*>(dfeat, groups), st, pack4<const float*>(dhidden, groups),
+                                              pack4<float*>(dx, groups), pack4<float*>(dx_lp, groups));
+  else
+    pool_bwd_kernel<bf16><<<grid, D, 0, s>>>(pack4<const float*>(dfeat, groups), st, pack4<const float*>(dhidden, groups),
+                                             pack4<float*>(dx, groups), pack4<bf16*>(dx_lp, groups));
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_embed_bwd(const float* const* dx, float* const* grads, int groups, int B, cudaStream_t s) {
+  embed_bwd_kernel<<<dim3(NT, groups), D, 0, s>>>(pack4<const float*>(dx, groups), pack4<float*>(grads, groups), B);
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_attn_fwd_simt(const void* const* qkv, void* const* ctx, float* const* lse, int groups, int B, int at,
+                         cudaStream_t s) {
+  const size_t smem = (size_t)(2 * NT * ASTR + 8 * 200 + 8 * DH) * sizeof(float);
+  dim3 grid(NH, B, groups);
+  if (at == 0) {
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_fwd_simt_kernel<float><<<grid, 256, smem, s>>>(pack4<const float*>(qkv, groups), pack4<float*>(ctx, groups),
+                                                        pack4<float*>(lse, groups));
+  } else {
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_fwd_simt_kernel<bf16><<<grid, 256, smem, s>>>(pack4<const bf16*>(qkv, groups), pack4<bf16*>(ctx, groups),
+                                                       pack4<float*>(lse, groups));
+  }
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_attn_bwd_simt(const void* const* qkv, const void* const* ctx, const float* const* lse,
+                         const void* const* dctx, void* const* dqkv, int groups, int B, int at, cudaStream_t s) {
+  const size_t smem = (size_t)(4 * NT * ASTR + 2 * NT + 16 * 200) * sizeof(float);
+  dim3 grid(NH, B, groups);
+  if (at == 0) {
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_bwd_simt_kernel<float><<<grid, 256, smem, s>>>(pack4<const float*>(qkv, groups), pack4<const float*>(ctx, groups),
+                                                        pack4<const float*>(lse, groups), pack4<const float*>(dctx, groups),
+                                                        pack4<float*>(dqkv, groups));
+  } else {
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_bwd_simt_kernel<bf16><<<grid, 256, smem, s>>>(pack4<const bf16*>(qkv, groups), pack4<const bf16*>(ctx, groups),
+                                                       pack4<const float*>(lse, groups), pack4<const bf16*>(dctx, groups),
+                                                       pack4<bf16*>(dqkv, groups));
+  }
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_cosine_loss(const float* p, const float* z, float* loss, float* dp, int B, int accum, float grad_scale,
+                       cudaStream_t s) {
+  const float inv_count = 1.0f / ((float)B * (float)accum);
+  cosine_loss_kernel<<<1, 256, 0, s>>>(p, z, loss, dp, B, inv_count, grad_scale);
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_adam(const v2s_range_t* ranges, int n, int64_t step, float lr, float b1, float b2, float eps, float wd,
+                float grad_scale, cudaStream_t s) {
+  if (n < 1 || n > 4) { set_error("adam: 1..4 ranges"); return 1; }
+  AdamRanges rs;
+  int64_t mx = 0;
+  for (int i = 0; i < 4; ++i) {
+    if (i < n) { rs.r[i] = ranges[i]; if (ranges[i].numel > mx) mx = ranges[i].numel; }
+    else memset(&rs.r[i], 0, sizeof(v2s_range_t));
+  }
+  rs.n = n;
+  const double bc1 = 1.0 - pow((double)b1, (double)step);
+  const double bc2 = 1.0 - pow((double)b2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  dim3 grid(grid_for(mx / 4 + 1, 256, 148 * 8), n);
+  adam_kernel<<<grid, 256, 0, s>>>(rs, step_size, inv_bc2_sqrt, b1, b2, eps, wd, grad_scale);
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_ema(float* const* tgt, const float* const* onl, void* const* tgt_lp, int n_pairs, int64_t numel,
+               float momentum, cudaStream_t s) {
+  if (n_pairs < 1 || n_pairs > 4) { set_error("ema: 1..4 pairs"); return 1; }
+  if (numel % 4) { set_error("ema: numel must be a multiple of 4"); return 1; }
+  EmaPairs pr;
+  for (int i = 0; i < 4; ++i) {
+    pr.t[i] = i < n_pairs ? tgt[i] : nullptr;
+    pr.o[i] = i < n_pairs ? onl[i] : nullptr;
+    pr.lp[i] = (i < n_pairs && tgt_lp) ? static_cast<bf16*>(tgt_lp[i]) : nullptr;
+  }
+  const float om = (float)(1.0 - (double)momentum);   // python: (1 - momentum) in double, then fp32
+  dim3 grid(grid_for(numel / 4, 256, 148 * 8), n_pairs);
+  ema_kernel<<<grid, 256, 0, s>>>(pr, numel, momentum, om);
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t s) {
+  cast_bf16_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, s>>>(src, static_cast<bf16*>(dst), n);
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_dropout_mask(float* mask, int64_t n, float p, uint64_t seed, uint64_t offset, cudaStream_t s) {
+  dropout_mask_kernel<<<grid_for(n, 256), 256, 0, s>>>(mask, n, p, 1.0f / (1.0f - p), seed, offset);
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_preprocess_u8(const uint8_t* src, float* dst, int B, cudaStream_t s) {
+  preprocess_u8_kernel<<<grid_for((int64_t)B * V2S_IMG * V2S_IMG, 256, 148 * 16), 256, 0, s>>>(src, dst, B);
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_zero(void* p, int64_t bytes, cudaStream_t s) {
+  V2S_CUDA_OK(cudaMemsetAsync(p, 0, (size_t)bytes, s));
+  return 0;
+}
+
+}  // namespace v2s

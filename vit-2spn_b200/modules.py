@@ -1,0 +1,657 @@
+"""Host-side mirror of the reference's model API on top of libvit2spn.so.
+
+Same class names, constructor/forward signatures, attribute names and ``state_dict`` keys as the
+reference (ref: = /root/reference):
+
+* ``ViTModel``            – stands in for ``transformers.ViTModel`` as the reference uses it
+                            (ref:ssp_vit2spn_tiny.py:112-116): HF parameter names, ``.hidden_states[-1]``.
+* ``ViTBackbone``         – ref:ssp_vit2spn_tiny.py:109-118
+* ``DualStreamNetwork``   – ref:ssp_vit2spn_tiny.py:121-166 (``forward(x1,x2) -> (pred, target_proj)``,
+                            ``update_target_network()``)
+* ``FineTunedModel``      – ref:octmnist_ft_vit2spn.py:73-87
+
+All arithmetic of the hot path runs in the CUDA library; parameters live in flat fp32 buffers
+(layout: include/vit2spn.h) of which the 200 HF-named ``nn.Parameter`` s are views, so
+``torch.optim.Adam(model.parameters())``, ``load_state_dict(strict=True)``, ``torch.save`` and the
+reference's own ``target_param.data = ...`` EMA loop keep working.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import warnings
+import weakref
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import Group, lib, check, ptr, stream_ptr
+
+momentum = 0.999            # ref:ssp_vit2spn_tiny.py:38 (module-level constant in the reference)
+
+_MODE_NAMES = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16}
+_default_mode = os.environ.get("V2S_MODE", "bf16")
+
+
+def set_compute_mode(mode: str) -> None:
+    """'bf16' (tcgen05 GEMMs, fp32 accumulate/residual/LN/softmax) or 'fp32' (check mode)."""
+    global _default_mode
+    if mode not in _MODE_NAMES:
+        raise ValueError(f"mode must be one of {list(_MODE_NAMES)}")
+    _default_mode = mode
+
+
+def get_compute_mode() -> str:
+    return _default_mode
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"vit2spn: {what} is on {t.device}; the hot path has no CPU fallback — move the model and "
+            "inputs to a CUDA (sm_100) device")
+    _lib.init_device(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+# ---------------------------------------------------------------------------------------------
+# flat parameter storage
+# ---------------------------------------------------------------------------------------------
+class FlatStore:
+    """One flat fp32 buffer whose slices back a list of ``nn.Parameter`` s (+ grads, bf16 shadow)."""
+
+    def __init__(self, params, offsets, numel, active_numel):
+        self.params = list(params)
+        self.offsets = list(offsets)
+        self.numel = int(numel)
+        self.active_numel = int(active_numel)
+        self.flat = None
+        self.flat_grad = None
+        self.flat_lp = None
+        self._grad_views = None
+        self.lp_fresh = False        # set by the fused Adam / EMA kernels that refresh the shadow
+        self.reflatten()
+        _STORES.add(self)
+
+    def _views(self, flat):
+        return [flat[o:o + p.numel()].view(p.shape) for p, o in zip(self.params, self.offsets)]
+
+    def reflatten(self):
+        """Copy the current parameter values into a fresh flat buffer and rebind ``.data`` to views."""
+        dev = self.params[0].device
+        flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, v in zip(self.params, self._views(flat)):
+                v.copy_(p.data.to(torch.float32))
+                p.data = v
+        self.flat = flat
+        self.flat_grad = None
+        self.flat_lp = None
+        self._grad_views = None
+        self.lp_fresh = False
+
+    def ensure(self):
+        """Re-flatten if anything rebound a parameter's storage (``.to()``, ``p.data = ...``: SURVEY D7)."""
+        base = self.flat.data_ptr()
+        dev = self.flat.device
+        for p, o in zip(self.params, self.offsets):
+            if p.data_ptr() != base + 4 * o or p.device != dev or p.dtype != torch.float32:
+                self.reflatten()
+                break
+        return self.flat
+
+    def lp(self, refresh=True):
+        """bf16 shadow copy of the flat buffer (same element offsets)."""
+        if self.flat_lp is None or self.flat_lp.device != self.flat.device:
+            self.flat_lp = torch.empty(self.numel, dtype=torch.bfloat16, device=self.flat.device)
+            self.lp_fresh = False
+        if refresh and not self.lp_fresh:
+            check(lib.v2s_cast_bf16(ptr(self.flat), ptr(self.flat_lp), self.numel, stream_ptr()), "cast_bf16")
+        return self.flat_lp
+
+    def grads(self):
+        """Flat gradient buffer; (re)attaches ``p.grad`` views.  After ``zero_grad(set_to_none=True)``
+        the buffer is zeroed once, like autograd's first accumulation into a fresh ``.grad``."""
+        if self.flat_grad is None or self.flat_grad.device != self.flat.device:
+            self.flat_grad = torch.zeros(self.numel, dtype=torch.float32, device=self.flat.device)
+            self._grad_views = self._views(self.flat_grad)
+        # tensors past active_numel (final LN, pooler) are never used: grad stays None
+        active = [(p, v) for p, v, o in zip(self.params, self._grad_views, self.offsets)
+                  if o < self.active_numel and p.requires_grad]
+        n_none = sum(1 for p, _ in active if p.grad is None)
+        if n_none == len(active):
+            self.flat_grad.zero_()
+            for p, v in active:
+                p.grad = v
+        else:
+            for p, v in active:
+                if p.grad is None:
+                    v.zero_()
+                    p.grad = v
+                elif p.grad.data_ptr() != v.data_ptr():
+                    v.copy_(p.grad)            # someone else accumulated a gradient: keep it
+                    p.grad = v
+        return self.flat_grad
+
+    def grads_attached(self):
+        """True if every trainable parameter's ``.grad`` is the matching view of the flat grad buffer."""
+        if self.flat_grad is None:
+            return False
+        for p, v, o in zip(self.params, self._grad_views, self.offsets):
+            if o < self.active_numel and p.requires_grad:
+                if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                    return False
+        return True
+
+
+_STORES = weakref.WeakSet()
+
+
+_workspaces = {}
+
+
+def _scratch_workspace(device, batch, mode, n_groups, n_saved):
+    """Persistent scratch for calls that keep nothing across calls (no-grad forwards)."""
+    key = (device, batch, mode, n_groups, n_saved)
+    ws = _workspaces.get(key)
+    if ws is None:
+        nbytes = lib.v2s_workspace_bytes(batch, mode, n_groups, n_saved)
+        if nbytes < 0:
+            raise RuntimeError("v2s_workspace_bytes: bad arguments")
+        ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _aligned(ws):
+    off = (-ws.data_ptr()) % 1024
+    return ws.data_ptr() + off, ws.numel() - off
+
+
+def _new_workspace(device, batch, mode, n_groups, n_saved):
+    nbytes = lib.v2s_workspace_bytes(batch, mode, n_groups, n_saved)
+    if nbytes < 0:
+        raise RuntimeError("v2s_workspace_bytes: bad arguments")
+    return torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+
+
+def _check_images(x):
+    if x.dim() != 4 or tuple(x.shape[1:]) != (3, 224, 224):
+        raise ValueError(f"expected pixel_values of shape [B,3,224,224], got {tuple(x.shape)}")
+    _require_cuda(x, "pixel_values")
+    return x.contiguous().to(torch.float32)
+
+
+def _run_forward(groups, batch, mode, ws):
+    arr = (Group * len(groups))(*groups)
+    base, nbytes = _aligned(ws)
+    check(lib.v2s_backbone_forward(arr, len(groups), batch, mode, C.c_void_p(base), nbytes, stream_ptr()),
+          "backbone_forward")
+
+
+def _run_backward(groups, batch, mode, ws):
+    arr = (Group * len(groups))(*groups)
+    base, nbytes = _aligned(ws)
+    check(lib.v2s_backbone_backward(arr, len(groups), batch, mode, C.c_void_p(base), nbytes, stream_ptr()),
+          "backbone_backward")
+
+
+def _group(store, mode, x, slot, grads=None, hidden=None, feat=None, feat_stride=0, dfeat=None,
+           dfeat_stride=0, dhidden=None):
+    g = Group()
+    g.params = store.flat.data_ptr()
+    g.params_lp = store.lp().data_ptr() if mode == _lib.MODE_BF16 else None
+    g.grads = grads.data_ptr() if grads is not None else None
+    g.x = x.data_ptr()
+    g.hidden = hidden.data_ptr() if hidden is not None else None
+    g.feat = feat.data_ptr() if feat is not None else None
+    g.feat_stride = feat_stride
+    g.dfeat = dfeat.data_ptr() if dfeat is not None else None
+    g.dfeat_stride = dfeat_stride
+    g.dhidden = dhidden.data_ptr() if dhidden is not None else None
+    g.slot = slot
+    return g
+
+
+# ---------------------------------------------------------------------------------------------
+# ViTModel (HF-compatible container + accelerated forward)
+# ---------------------------------------------------------------------------------------------
+class ViTConfig:
+    """The subset of ``transformers.ViTConfig`` the reference touches
+    (ref:ssp_ssl/ssl_vit2spn_scratch.py:100-108).  Only the ViT-Tiny/16@224 geometry is built."""
+
+    def __init__(self, hidden_size=192, num_hidden_layers=12, num_attention_heads=3, intermediate_size=768,
+                 patch_size=16, image_size=224, output_hidden_states=False, layer_norm_eps=1e-12,
+                 hidden_act="gelu", num_channels=3, qkv_bias=True, initializer_range=0.02, **kw):
+        self.hidden_size = hidden_size
+        self.num_hidden_layers = num_hidden_layers
+        self.num_attention_heads = num_attention_heads
+        self.intermediate_size = intermediate_size
+        self.patch_size = patch_size
+        self.image_size = image_size
+        self.output_hidden_states = output_hidden_states
+        self.layer_norm_eps = layer_norm_eps
+        self.hidden_act = hidden_act
+        self.num_channels = num_channels
+        self.qkv_bias = qkv_bias
+        self.initializer_range = initializer_range
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    def _check_supported(self):
+        geo = (self.hidden_size, self.num_hidden_layers, self.num_attention_heads, self.intermediate_size,
+               self.patch_size, self.image_size, self.num_channels)
+        if geo != (192, 12, 3, 768, 16, 224, 3) or self.hidden_act != "gelu" or not self.qkv_bias \
+                or abs(self.layer_norm_eps - 1e-12) > 0:
+            raise NotImplementedError(
+                "vit2spn implements exactly ViT-Tiny/16@224 (hidden 192, 12 layers, 3 heads, MLP 768, "
+                f"erf-GELU, LN eps 1e-12, qkv bias) — the reference's only backbone; got {geo}")
+
+
+class _Holder(nn.Module):
+    """Pure parameter container mirroring HF's sub-module names."""
+
+
+def _linear(i, o):
+    return nn.Linear(i, o)
+
+
+class _HiddenStates:
+    """``output.hidden_states``: the reference reads only ``[-1]`` (ref:ssp_vit2spn_tiny.py:116)."""
+
+    def __init__(self, last):
+        self._last = last
+
+    def __len__(self):
+        return 13
+
+    def __getitem__(self, i):
+        if i in (-1, 12):
+            return self._last
+        raise NotImplementedError("vit2spn keeps only hidden_states[-1] (the only one the reference reads)")
+
+
+class ViTModelOutput:
+    def __init__(self, model, last_hidden):
+        self._model = model
+        self.hidden_states = _HiddenStates(last_hidden)
+
+    @property
+    def last_hidden_state(self):
+        # HF: final LayerNorm of the last block output (modeling_vit.py:455); off the hot path, lazy torch op
+        m = self._model
+        return torch.nn.functional.layer_norm(self.hidden_states[-1], (192,), m.layernorm.weight,
+                                              m.layernorm.bias, 1e-12)
+
+    @property
+    def pooler_output(self):
+        m = self._model
+        return torch.tanh(torch.nn.functional.linear(self.last_hidden_state[:, 0], m.pooler.dense.weight,
+                                                     m.pooler.dense.bias))
+
+
+class _BackboneFn(torch.autograd.Function):
+    """x -> (hidden_states[-1] | mean-pooled features) for one backbone, autograd-compatible."""
+
+    @staticmethod
+    def forward(ctx, x, anchor, model, pooled):
+        store = model._store
+        store.ensure()
+        mode = model._mode()
+        B = x.shape[0]
+        need_grad = anchor.requires_grad and torch.is_grad_enabled()
+        dev = x.device
+        if pooled:
+            out = torch.empty(B, 192, dtype=torch.float32, device=dev)
+        else:
+            out = torch.empty(B, 197, 192, dtype=torch.float32, device=dev)
+        if need_grad:
+            ws = _new_workspace(dev, B, mode, 1, 1)
+        else:
+            ws = _scratch_workspace(dev, B, mode, 1, 0)
+        g = _group(store, mode, x, 0 if need_grad else -1,
+                   hidden=None if pooled else out, feat=out if pooled else None, feat_stride=192)
+        _run_forward([g], B, mode, ws)
+        ctx.model, ctx.pooled, ctx.mode, ctx.B = model, pooled, mode, B
+        ctx.ws = ws if need_grad else None
+        ctx.x = x
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        model, store = ctx.model, ctx.model._store
+        if ctx.ws is None:
+            raise RuntimeError("vit2spn: backward through a forward that saved no activations")
+        dout = dout.contiguous().to(torch.float32)
+        grads = store.grads()
+        g = _group(store, ctx.mode, ctx.x, 0, grads=grads,
+                   dfeat=dout if ctx.pooled else None, dfeat_stride=192,
+                   dhidden=None if ctx.pooled else dout)
+        _run_backward([g], ctx.B, ctx.mode, ctx.ws)
+        ctx.ws = None
+        return None, None, None, None
+
+
+class ViTModel(nn.Module):
+    """Drop-in for ``transformers.ViTModel`` as used by the reference (ViT-Tiny/16@224 only)."""
+
+    def __init__(self, config=None, add_pooling_layer=True, **kw):
+        super().__init__()
+        config = config or ViTConfig(**kw)
+        config._check_supported()
+        self.config = config
+        std = config.initializer_range
+        emb = _Holder()
+        emb.cls_token = nn.Parameter(torch.empty(1, 1, 192))
+        emb.position_embeddings = nn.Parameter(torch.empty(1, 197, 192))
+        emb.patch_embeddings = _Holder()
+        emb.patch_embeddings.projection = nn.Conv2d(3, 192, kernel_size=16, stride=16)
+        self.embeddings = emb
+        enc = _Holder()
+        layers = []
+        for _ in range(12):
+            layer = _Holder()
+            layer.attention = _Holder()
+            layer.attention.attention = _Holder()
+            layer.attention.attention.query = _linear(192, 192)
+            layer.attention.attention.key = _linear(192, 192)
+            layer.attention.attention.value = _linear(192, 192)
+            layer.attention.output = _Holder()
+            layer.attention.output.dense = _linear(192, 192)
+            layer.intermediate = _Holder()
+            layer.intermediate.dense = _linear(192, 768)
+            layer.output = _Holder()
+            layer.output.dense = _linear(768, 192)
+            layer.layernorm_before = nn.LayerNorm(192, eps=1e-12)
+            layer.layernorm_after = nn.LayerNorm(192, eps=1e-12)
+            layers.append(layer)
+        enc.layer = nn.ModuleList(layers)
+        self.encoder = enc
+        self.layernorm = nn.LayerNorm(192, eps=1e-12)
+        self.pooler = _Holder()
+        self.pooler.dense = _linear(192, 192)
+        # HF _init_weights (modeling_vit.py:384-398)
+        with torch.no_grad():
+            for m in self.modules():
+                if isinstance(m, (nn.Linear, nn.Conv2d)):
+                    nn.init.trunc_normal_(m.weight, mean=0.0, std=std)
+                    nn.init.zeros_(m.bias)
+                elif isinstance(m, nn.LayerNorm):
+                    nn.init.ones_(m.weight)
+                    nn.init.zeros_(m.bias)
+            nn.init.trunc_normal_(emb.cls_token, mean=0.0, std=std)
+            nn.init.trunc_normal_(emb.position_embeddings, mean=0.0, std=std)
+        params = list(self.parameters())
+        assert len(params) == 200
+        self._store = FlatStore(params, _lib.backbone_layout(), _lib.BACKBONE_NUMEL, _lib.BACKBONE_ACTIVE_NUMEL)
+        self.compute_mode = None        # None → package default (set_compute_mode)
+
+    @classmethod
+    def from_pretrained(cls, name, **kw):
+        """The reference loads ``WinKawaks/vit-tiny-patch16-224`` (ref:ssp_vit2spn_tiny.py:112).  A local
+        HF checkpoint directory / state-dict file is loaded if `name` is a path; otherwise (offline)
+        the same architecture is built with HF random init."""
+        cfg_kw = {k: v for k, v in kw.items() if k in ("output_hidden_states",)}
+        model = cls(ViTConfig(**cfg_kw))
+        path = name if os.path.exists(str(name)) else None
+        if path is not None:
+            f = os.path.join(path, "pytorch_model.bin") if os.path.isdir(path) else path
+            sd = torch.load(f, map_location="cpu")
+            sd = {k[4:] if k.startswith("vit.") else k: v for k, v in sd.items()}
+            model.load_state_dict(sd, strict=False)
+        else:
+            warnings.warn(f"vit2spn.ViTModel.from_pretrained({name!r}): no local checkpoint (offline); "
+                          "using HF random initialisation of ViT-Tiny/16")
+        return model
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        if getattr(self, "_store", None) is not None:
+            self._store.reflatten()
+        return r
+
+    def _mode(self):
+        return _MODE_NAMES[self.compute_mode or _default_mode]
+
+    def features(self, pixel_values):
+        """Mean over the 197 tokens of ``hidden_states[-1]`` (fused pooling)."""
+        x = _check_images(pixel_values)
+        return _BackboneFn.apply(x, self.embeddings.cls_token, self, True)
+
+    def forward(self, pixel_values, **kw):
+        x = _check_images(pixel_values)
+        last = _BackboneFn.apply(x, self.embeddings.cls_token, self, False)
+        return ViTModelOutput(self, last)
+
+
+class ViTBackbone(nn.Module):
+    """ref:ssp_vit2spn_tiny.py:109-118 — ``ViTModel(x).hidden_states[-1].mean(dim=1)``."""
+
+    def __init__(self):
+        super().__init__()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            self.vit = ViTModel.from_pretrained("WinKawaks/vit-tiny-patch16-224", output_hidden_states=True)
+
+    def forward(self, x):
+        return self.vit.features(x)
+
+
+# ---------------------------------------------------------------------------------------------
+# DualStreamNetwork
+# ---------------------------------------------------------------------------------------------
+class _DualStreamFn(torch.autograd.Function):
+    """(x1, x2) -> (online_pred, target_proj): 4 grouped backbones + heads in the CUDA library."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, anchor, model):
+        st = model._stores()
+        for s in st:
+            s.ensure()
+        hs = model._head_store
+        hs.ensure()
+        mode = model._mode()
+        B, dev = x1.shape[0], x1.device
+        need_grad = anchor.requires_grad and torch.is_grad_enabled()
+        ws = model._take_workspace(dev, B, mode)
+        feat_o = torch.empty(B, 384, dtype=torch.float32, device=dev)
+        feat_t = torch.empty(B, 384, dtype=torch.float32, device=dev)
+        groups = [
+            _group(st[0], mode, x1, 0 if need_grad else -1, feat=feat_o, feat_stride=384),
+            _group(st[1], mode, x2, 1 if need_grad else -1, feat=feat_o[:, 192:], feat_stride=384),
+            _group(st[2], mode, x1, -1, feat=feat_t, feat_stride=384),
+            _group(st[3], mode, x2, -1, feat=feat_t[:, 192:], feat_stride=384),
+        ]
+        _run_forward(groups, B, mode, ws)
+        mask_o, mask_t = model._dropout_masks(B, dev)
+        pred = torch.empty(B, 128, dtype=torch.float32, device=dev)
+        tgt = torch.empty(B, 128, dtype=torch.float32, device=dev)
+        base, nbytes = _aligned(ws)
+        check(lib.v2s_heads_forward(ptr(hs.flat), ptr(feat_o), ptr(feat_t), ptr(mask_o), ptr(mask_t), ptr(pred),
+                                    ptr(tgt), B, C.c_void_p(base), nbytes, stream_ptr()), "heads_forward")
+        ctx.model, ctx.mode, ctx.B = model, mode, B
+        ctx.ws = ws if need_grad else None
+        if not need_grad:
+            model._release_workspace(ws)
+        ctx.keep = (x1, x2, feat_o, mask_o)
+        ctx.mark_non_differentiable(tgt)
+        return pred, tgt
+
+    @staticmethod
+    def backward(ctx, dpred, _dtgt):
+        model = ctx.model
+        if ctx.ws is None:
+            raise RuntimeError("vit2spn: backward through a forward that saved no activations")
+        x1, x2, feat_o, mask_o = ctx.keep
+        st, hs = model._stores(), model._head_store
+        B, mode, ws = ctx.B, ctx.mode, ctx.ws
+        dpred = dpred.contiguous().to(torch.float32)
+        dfeat = torch.empty(B, 384, dtype=torch.float32, device=dpred.device)
+        base, nbytes = _aligned(ws)
+        check(lib.v2s_heads_backward(ptr(hs.flat), ptr(hs.grads()), ptr(feat_o), ptr(mask_o), ptr(dpred), ptr(dfeat),
+                                     B, C.c_void_p(base), nbytes, stream_ptr()), "heads_backward")
+        groups = [
+            _group(st[0], mode, x1, 0, grads=st[0].grads(), dfeat=dfeat, dfeat_stride=384),
+            _group(st[1], mode, x2, 1, grads=st[1].grads(), dfeat=dfeat[:, 192:], dfeat_stride=384),
+        ]
+        _run_backward(groups, B, mode, ws)
+        model._release_workspace(ws)
+        ctx.ws = None
+        return None, None, None, None
+
+
+class DualStreamNetwork(nn.Module):
+    """ref:ssp_vit2spn_tiny.py:121-166.  Same attributes, ``state_dict`` keys and parameter order."""
+
+    def __init__(self):
+        super().__init__()
+        self.online_network_1 = ViTBackbone()
+        self.online_network_2 = ViTBackbone()
+        self.target_network_1 = ViTBackbone()
+        self.target_network_2 = ViTBackbone()
+        for param in self.target_network_1.parameters():
+            param.requires_grad = False
+        for param in self.target_network_2.parameters():
+            param.requires_grad = False
+        self.projection_head = nn.Sequential(
+            nn.Linear(192 * 2, 1024),
+            nn.ReLU(),
+            nn.Dropout(0.3),
+            nn.Linear(1024, 128),
+        )
+        self.prediction_head = nn.Sequential(
+            nn.Linear(128, 128),
+            nn.ReLU(),
+            nn.Linear(128, 128),
+        )
+        head_params = list(self.projection_head.parameters()) + list(self.prediction_head.parameters())
+        self._head_store = FlatStore(head_params, _lib.heads_layout(), _lib.HEADS_NUMEL, _lib.HEADS_NUMEL)
+        self.compute_mode = None
+        self.momentum = momentum
+        self._ws = {}
+        self._ws_busy = set()
+        self._fixed_masks = None       # tests: (mask_online, mask_target) consumed instead of the RNG
+
+    # -- plumbing --------------------------------------------------------------------------
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        if getattr(self, "_head_store", None) is not None:
+            self._head_store.reflatten()
+            self._ws.clear()
+            self._ws_busy.clear()
+        return r
+
+    def _mode(self):
+        return _MODE_NAMES[self.compute_mode or _default_mode]
+
+    def _stores(self):
+        return [self.online_network_1.vit._store, self.online_network_2.vit._store,
+                self.target_network_1.vit._store, self.target_network_2.vit._store]
+
+    def _take_workspace(self, dev, B, mode):
+        key = (dev, B, mode)
+        ws = self._ws.get(key)
+        if ws is None:
+            ws = _new_workspace(dev, B, mode, 4, 2)
+            self._ws[key] = ws
+        if ws.data_ptr() in self._ws_busy:      # a previous forward still waits for its backward
+            return _new_workspace(dev, B, mode, 4, 2)
+        self._ws_busy.add(ws.data_ptr())
+        return ws
+
+    def _release_workspace(self, ws):
+        self._ws_busy.discard(ws.data_ptr())
+
+    def _dropout_masks(self, B, dev):
+        if self._fixed_masks is not None:
+            return self._fixed_masks
+        drop = self.projection_head[2]
+        if not (self.training and drop.training) or drop.p <= 0.0:
+            return None, None
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())        # CPU generator: no device sync
+        masks = torch.empty(2, B, 1024, dtype=torch.float32, device=dev)
+        check(lib.v2s_dropout_mask(ptr(masks), masks.numel(), float(drop.p), seed, 0, stream_ptr()), "dropout_mask")
+        return masks[0], masks[1]       # two independent draws, as the reference
+
+    # -- reference API ---------------------------------------------------------------------
+    def forward(self, x1, x2):
+        x1, x2 = _check_images(x1), _check_images(x2)
+        if x1.shape != x2.shape:
+            raise ValueError("x1 and x2 must have the same shape")
+        anchor = self.online_network_1.vit.embeddings.cls_token
+        return _DualStreamFn.apply(x1, x2, anchor, self)
+
+    def update_target_network(self):
+        """ref:ssp_vit2spn_tiny.py:162-166 as one flat-buffer kernel over both (online, target) pairs."""
+        st = self._stores()
+        for s in st:
+            s.ensure()
+        _require_cuda(st[0].flat, "model parameters")
+        n = st[0].numel
+        tg = (C.c_void_p * 2)(st[2].flat.data_ptr(), st[3].flat.data_ptr())
+        on = (C.c_void_p * 2)(st[0].flat.data_ptr(), st[1].flat.data_ptr())
+        lp = (C.c_void_p * 2)(st[2].lp(refresh=False).data_ptr(), st[3].lp(refresh=False).data_ptr())
+        m = globals().get("momentum", 0.999) if self.momentum is None else self.momentum
+        check(lib.v2s_ema_update(tg, on, lp, 2, n, float(m), stream_ptr()), "ema_update")
+
+    # -- fused native step (no autograd graph): fwd + loss + bwd in the library --------------
+    def ssp_step(self, x1, x2, accumulation_steps=1, grad_scale=1.0, with_backward=True):
+        """One micro-step of ref:ssp_vit2spn_tiny.py:209-213 — returns the loss tensor (already divided
+        by ``accumulation_steps``); gradients are accumulated into ``.grad`` of the parameters."""
+        x1, x2 = _check_images(x1), _check_images(x2)
+        st, hs = self._stores(), self._head_store
+        for s in st:
+            s.ensure()
+        hs.ensure()
+        mode, B, dev = self._mode(), x1.shape[0], x1.device
+        ws = self._take_workspace(dev, B, mode)
+        try:
+            feat = torch.empty(2, B, 384, dtype=torch.float32, device=dev)
+            feat_o, feat_t = feat[0], feat[1]
+            sl = (0, 1) if with_backward else (-1, -1)
+            groups = [
+                _group(st[0], mode, x1, sl[0], feat=feat_o, feat_stride=384),
+                _group(st[1], mode, x2, sl[1], feat=feat_o[:, 192:], feat_stride=384),
+                _group(st[2], mode, x1, -1, feat=feat_t, feat_stride=384),
+                _group(st[3], mode, x2, -1, feat=feat_t[:, 192:], feat_stride=384),
+            ]
+            _run_forward(groups, B, mode, ws)
+            mask_o, mask_t = self._dropout_masks(B, dev)
+            out = torch.empty(1 + B * 384, dtype=torch.float32, device=dev)
+            loss, dfeat = out[:1], out[1:].view(B, 384)
+            base, nbytes = _aligned(ws)
+            hg = hs.grads() if with_backward else None
+            check(lib.v2s_heads_loss_fwd_bwd(ptr(hs.flat), ptr(hg), ptr(feat_o), ptr(feat_t), ptr(mask_o), ptr(mask_t),
+                                             ptr(dfeat), None, None, ptr(loss), B, int(accumulation_steps),
+                                             float(grad_scale), 1 if with_backward else 0, C.c_void_p(base), nbytes,
+                                             stream_ptr()), "heads_loss_fwd_bwd")
+            if with_backward:
+                bw = [
+                    _group(st[0], mode, x1, 0, grads=st[0].grads(), dfeat=dfeat, dfeat_stride=384),
+                    _group(st[1], mode, x2, 1, grads=st[1].grads(), dfeat=dfeat[:, 192:], dfeat_stride=384),
+                ]
+                _run_backward(bw, B, mode, ws)
+        finally:
+            self._release_workspace(ws)
+        return loss[0]
+
+
+class FineTunedModel(nn.Module):
+    """ref:octmnist_ft_vit2spn.py:73-87 — accelerated backbone + the reference's small fc head
+    (BatchNorm1d/Dropout head: <0.1 % of the FLOPs, left to torch)."""
+
+    def __init__(self, num_classes):
+        super().__init__()
+        self.backbone = ViTBackbone()
+        self.fc = nn.Sequential(
+            nn.Linear(192, 128),
+            nn.BatchNorm1d(128),
+            nn.ReLU(),
+            nn.Dropout(0.5),
+            nn.Linear(128, num_classes),
+        )
+
+    def forward(self, x):
+        features = self.backbone(x)
+        return self.fc(features)
