@@ -132,6 +132,7 @@ int v2s_dropout_mask(float* mask, int64_t n, float p, uint64_t seed, uint64_t of
 
 /* torch.optim.Adam.step (ref:173,216) over up to 4 flat ranges: defaults betas (0.9,0.999),
  * eps 1e-8, no weight decay unless weight_decay != 0 (L2, as the fine-tune scripts use).
+ * Hyper-parameters are doubles, converted exactly as torch converts its Python floats.
  * `step` is the 1-based step count; grads are multiplied by grad_scale first (1/world, 1/scale).
  * If params_lp != NULL the bf16 shadow copy is refreshed in the same pass. */
 typedef struct v2s_range {
@@ -142,12 +143,12 @@ typedef struct v2s_range {
   void* params_lp;
   int64_t numel;
 } v2s_range_t;
-int v2s_adam_step(const v2s_range_t* host_ranges, int n_ranges, int64_t step, float lr, float beta1,
-                  float beta2, float eps, float weight_decay, float grad_scale, void* stream);
+int v2s_adam_step(const v2s_range_t* host_ranges, int n_ranges, int64_t step, double lr, double beta1,
+                  double beta2, double eps, double weight_decay, double grad_scale, void* stream);
 
 /* update_target_network (ref:162-166): target = m*target + (1-m)*online over flat buffers */
 int v2s_ema_update(float* const* host_targets, const float* const* host_onlines,
-                   void* const* host_targets_lp, int n_pairs, int64_t numel, float momentum,
+                   void* const* host_targets_lp, int n_pairs, int64_t numel, double momentum,
                    void* stream);
 
 /* fp32 → bf16 shadow copy of a flat buffer */

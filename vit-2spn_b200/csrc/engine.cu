@@ -697,8 +697,8 @@ int v2s_dropout_mask(float* mask, int64_t n, float p, uint64_t seed, uint64_t of
   return launch_dropout_mask(mask, n, p, seed, offset, (cudaStream_t)stream);
 }
 
-int v2s_adam_step(const v2s_range_t* ranges, int n_ranges, int64_t step, float lr, float beta1, float beta2,
-                  float eps, float weight_decay, float grad_scale, void* stream) {
+int v2s_adam_step(const v2s_range_t* ranges, int n_ranges, int64_t step, double lr, double beta1, double beta2,
+                  double eps, double weight_decay, double grad_scale, void* stream) {
   if (!ranges || step < 1) { set_error("adam: bad argument"); return 1; }
   for (int i = 0; i < n_ranges; ++i)
     if ((reinterpret_cast<uintptr_t>(ranges[i].params) | reinterpret_cast<uintptr_t>(ranges[i].grads) |
@@ -710,7 +710,7 @@ int v2s_adam_step(const v2s_range_t* ranges, int n_ranges, int64_t step, float l
 }
 
 int v2s_ema_update(float* const* targets, const float* const* onlines, void* const* targets_lp, int n_pairs,
-                   int64_t numel, float momentum, void* stream) {
+                   int64_t numel, double momentum, void* stream) {
   if (!targets || !onlines) { set_error("ema: null"); return 1; }
   return launch_ema(targets, onlines, targets_lp, n_pairs, numel, momentum, (cudaStream_t)stream);
 }

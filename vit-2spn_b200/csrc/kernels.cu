@@ -395,8 +395,8 @@ struct AdamRanges {
   int n;
 };
 
-__global__ void __launch_bounds__(256) adam_kernel(AdamRanges rs, float step_size, float inv_bc2_sqrt,
-                                                   float b1, float b2, float eps, float wd,
+__global__ void __launch_bounds__(256) adam_kernel(AdamRanges rs, float step_size, float bc2_sqrt,
+                                                   float om_b1, float b2, float om_b2, float eps, float wd,
                                                    float grad_scale) {
   const v2s_range_t r = rs.r[blockIdx.y];
   const int64_t n4 = r.numel / 4;
@@ -412,9 +412,9 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamRanges rs, float step_siz
     for (int k = 0; k < 4; ++k) {
       float gr = gg[k] * grad_scale;
       if (wd != 0.f) gr = fmaf(wd, pp[k], gr);
-      mm[k] = mm[k] + (gr - mm[k]) * (1.0f - b1);        // lerp, as torch
-      vv[k] = b2 * vv[k] + (1.0f - b2) * gr * gr;
-      const float denom = sqrtf(vv[k]) * inv_bc2_sqrt + eps;
+      mm[k] = mm[k] + (gr - mm[k]) * om_b1;              // exp_avg.lerp_(grad, 1-beta1), as torch
+      vv[k] = b2 * vv[k] + om_b2 * gr * gr;             // mul_(beta2).addcmul_(g, g, 1-beta2)
+      const float denom = sqrtf(vv[k]) / bc2_sqrt + eps;
       pp[k] = pp[k] - step_size * (mm[k] / denom);
     }
     p4[i] = p; m4[i] = m; v4[i] = v;
@@ -431,9 +431,9 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamRanges rs, float step_siz
     float gr = r.grads[i] * grad_scale;
     if (wd != 0.f) gr = fmaf(wd, r.params[i], gr);
     float m = r.exp_avg[i], v = r.exp_avg_sq[i];
-    m = m + (gr - m) * (1.0f - b1);
-    v = b2 * v + (1.0f - b2) * gr * gr;
-    const float denom = sqrtf(v) * inv_bc2_sqrt + eps;
+    m = m + (gr - m) * om_b1;
+    v = b2 * v + om_b2 * gr * gr;
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
     const float pn = r.params[i] - step_size * (m / denom);
     r.params[i] = pn; r.exp_avg[i] = m; r.exp_avg_sq[i] = v;
     if (lp) lp[i] = __float2bfloat16_rn(pn);
@@ -667,8 +667,8 @@ int launch_cosine_loss(const float* p, const float* z, float* loss, float* dp, i
   return 0;
 }
 
-int launch_adam(const v2s_range_t* ranges, int n, int64_t step, float lr, float b1, float b2, float eps, float wd,
-                float grad_scale, cudaStream_t s) {
+int launch_adam(const v2s_range_t* ranges, int n, int64_t step, double lr, double b1, double b2, double eps, double wd,
+                double grad_scale, cudaStream_t s) {
   if (n < 1 || n > 4) { set_error("adam: 1..4 ranges"); return 1; }
   AdamRanges rs;
   int64_t mx = 0;
@@ -677,18 +677,19 @@ int launch_adam(const v2s_range_t* ranges, int n, int64_t step, float lr, float 
     else memset(&rs.r[i], 0, sizeof(v2s_range_t));
   }
   rs.n = n;
-  const double bc1 = 1.0 - pow((double)b1, (double)step);
-  const double bc2 = 1.0 - pow((double)b2, (double)step);
-  const float step_size = (float)((double)lr / bc1);
-  const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  const double bc1 = 1.0 - pow(b1, (double)step);
+  const double bc2 = 1.0 - pow(b2, (double)step);
+  const float step_size = (float)(lr / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
   dim3 grid(grid_for(mx / 4 + 1, 256, 148 * 8), n);
-  adam_kernel<<<grid, 256, 0, s>>>(rs, step_size, inv_bc2_sqrt, b1, b2, eps, wd, grad_scale);
+  adam_kernel<<<grid, 256, 0, s>>>(rs, step_size, bc2_sqrt, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2),
+                                   (float)eps, (float)wd, (float)grad_scale);
   V2S_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_ema(float* const* tgt, const float* const* onl, void* const* tgt_lp, int n_pairs, int64_t numel,
-               float momentum, cudaStream_t s) {
+               double momentum, cudaStream_t s) {
   if (n_pairs < 1 || n_pairs > 4) { set_error("ema: 1..4 pairs"); return 1; }
   if (numel % 4) { set_error("ema: numel must be a multiple of 4"); return 1; }
   EmaPairs pr;
@@ -697,9 +698,9 @@ int launch_ema(float* const* tgt, const float* const* onl, void* const* tgt_lp, 
     pr.o[i] = i < n_pairs ? onl[i] : nullptr;
     pr.lp[i] = (i < n_pairs && tgt_lp) ? static_cast<bf16*>(tgt_lp[i]) : nullptr;
   }
-  const float om = (float)(1.0 - (double)momentum);   // python: (1 - momentum) in double, then fp32
+  const float om = (float)(1.0 - momentum);   // python: (1 - momentum) in double, then fp32
   dim3 grid(grid_for(numel / 4, 256, 148 * 8), n_pairs);
-  ema_kernel<<<grid, 256, 0, s>>>(pr, numel, momentum, om);
+  ema_kernel<<<grid, 256, 0, s>>>(pr, numel, (float)momentum, om);
   V2S_LAUNCH_CHECK();
   return 0;
 }

@@ -33,10 +33,10 @@ int launch_attn_bwd_simt(const void* const* qkv, const void* const* ctx, const f
 
 int launch_cosine_loss(const float* p, const float* z, float* loss, float* dp, int B, int accum,
                        float grad_scale, cudaStream_t s);
-int launch_adam(const v2s_range_t* ranges, int n, int64_t step, float lr, float b1, float b2, float eps,
-                float wd, float grad_scale, cudaStream_t s);
+int launch_adam(const v2s_range_t* ranges, int n, int64_t step, double lr, double b1, double b2, double eps,
+                double wd, double grad_scale, cudaStream_t s);
 int launch_ema(float* const* tgt, const float* const* onl, void* const* tgt_lp, int n_pairs,
-               int64_t numel, float momentum, cudaStream_t s);
+               int64_t numel, double momentum, cudaStream_t s);
 int launch_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t s);
 int launch_dropout_mask(float* mask, int64_t n, float p, uint64_t seed, uint64_t offset, cudaStream_t s);
 int launch_preprocess_u8(const uint8_t* src, float* dst, int B, cudaStream_t s);

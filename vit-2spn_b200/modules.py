@@ -295,12 +295,11 @@ class _BackboneFn(torch.autograd.Function):
     """x -> (hidden_states[-1] | mean-pooled features) for one backbone, autograd-compatible."""
 
     @staticmethod
-    def forward(ctx, x, anchor, model, pooled):
+    def forward(ctx, x, anchor, model, pooled, need_grad):
         store = model._store
         store.ensure()
         mode = model._mode()
         B = x.shape[0]
-        need_grad = anchor.requires_grad and torch.is_grad_enabled()
         dev = x.device
         if pooled:
             out = torch.empty(B, 192, dtype=torch.float32, device=dev)
@@ -330,7 +329,7 @@ class _BackboneFn(torch.autograd.Function):
                    dhidden=None if ctx.pooled else dout)
         _run_backward([g], ctx.B, ctx.mode, ctx.ws)
         ctx.ws = None
-        return None, None, None, None
+        return None, None, None, None, None
 
 
 class ViTModel(nn.Module):
@@ -417,11 +416,13 @@ class ViTModel(nn.Module):
     def features(self, pixel_values):
         """Mean over the 197 tokens of ``hidden_states[-1]`` (fused pooling)."""
         x = _check_images(pixel_values)
-        return _BackboneFn.apply(x, self.embeddings.cls_token, self, True)
+        a = self.embeddings.cls_token
+        return _BackboneFn.apply(x, a, self, True, a.requires_grad and torch.is_grad_enabled())
 
     def forward(self, pixel_values, **kw):
         x = _check_images(pixel_values)
-        last = _BackboneFn.apply(x, self.embeddings.cls_token, self, False)
+        a = self.embeddings.cls_token
+        last = _BackboneFn.apply(x, a, self, False, a.requires_grad and torch.is_grad_enabled())
         return ViTModelOutput(self, last)
 
 
@@ -445,7 +446,7 @@ class _DualStreamFn(torch.autograd.Function):
     """(x1, x2) -> (online_pred, target_proj): 4 grouped backbones + heads in the CUDA library."""
 
     @staticmethod
-    def forward(ctx, x1, x2, anchor, model):
+    def forward(ctx, x1, x2, anchor, model, need_grad):
         st = model._stores()
         for s in st:
             s.ensure()
@@ -453,7 +454,6 @@ class _DualStreamFn(torch.autograd.Function):
         hs.ensure()
         mode = model._mode()
         B, dev = x1.shape[0], x1.device
-        need_grad = anchor.requires_grad and torch.is_grad_enabled()
         ws = model._take_workspace(dev, B, mode)
         feat_o = torch.empty(B, 384, dtype=torch.float32, device=dev)
         feat_t = torch.empty(B, 384, dtype=torch.float32, device=dev)
@@ -498,7 +498,7 @@ class _DualStreamFn(torch.autograd.Function):
         _run_backward(groups, B, mode, ws)
         model._release_workspace(ws)
         ctx.ws = None
-        return None, None, None, None
+        return None, None, None, None, None
 
 
 class DualStreamNetwork(nn.Module):
@@ -580,7 +580,7 @@ class DualStreamNetwork(nn.Module):
         if x1.shape != x2.shape:
             raise ValueError("x1 and x2 must have the same shape")
         anchor = self.online_network_1.vit.embeddings.cls_token
-        return _DualStreamFn.apply(x1, x2, anchor, self)
+        return _DualStreamFn.apply(x1, x2, anchor, self, anchor.requires_grad and torch.is_grad_enabled())
 
     def update_target_network(self):
         """ref:ssp_vit2spn_tiny.py:162-166 as one flat-buffer kernel over both (online, target) pairs."""
