@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py — dual-view SSP pairs/sec, ViT-Tiny, batch 128 per GPU (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+A "step" is one full SSP step of the reference recipe with accumulation_steps=1:
+zero_grad → 4 backbones forward (2 online with grad, 2 EMA targets) → heads → -mean(cos)/1 →
+backward → [gradient all-reduce if N>1] → Adam(lr 1e-4) → EMA(0.999), on one batch of 128 synthetic
+OCTMNIST-shaped pairs per GPU (uint8 28x28 → bilinear 224 → 3ch → ImageNet-normalised fp32).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_PAIR = 19.945e9          # algorithmic FLOPs of one pair per micro-step
+METRIC = "dual-view SSP pairs/sec, ViT-Tiny b128/GPU"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=128, help="pairs per GPU")
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-batch", type=int, default=8, help="bounded CPU sample (pairs per CPU step)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # median over the samples under load (upper half: idle samples at the edges pull it down)
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_step_fn(batch):
+    """The reference algorithm on host cores: oracle port of ref:ssp_vit2spn_tiny.py:205-219
+    (fp32, accumulation_steps=1: fwd → loss → bwd → Adam → EMA).  /root/reference itself does not
+    exist on the GPU box, so kind = "port"."""
+    import torch
+    from oracle import vit2spn_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    state = orc.init_state(42, 0.0)
+    x1, x2 = orc.synthetic_views(batch, seed=0)
+    opt = {}
+
+    def step():
+        nonlocal state, opt
+        loss, _, state, opt = orc.ssp_step(state, opt, x1, x2, lr=1e-4, momentum=0.999)
+        return float(loss)
+    return step, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step, cores = cpu_reference_step_fn(args.cpu_batch)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = args.cpu_batch * args.steps / dt
+    sample = (f"{args.steps} full SSP steps (fwd+bwd+Adam+EMA, fp32) of {args.cpu_batch} pairs each on "
+              f"{cores} host threads; oracle port of the reference algorithm")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ViT-Tiny dual-stream SSP full step, accumulation 1 (BASELINE config 2 recipe), "
+                               f"bounded CPU sample of {args.cpu_batch} pairs/step"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import vit2spn
+    from vit2spn import _lib
+    from oracle import vit2spn_oracle as orc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    vit2spn.set_compute_mode(args.mode)
+
+    # ---- model, optimizer, synthetic device-resident data -------------------------------------
+    torch.manual_seed(42)
+    model = vit2spn.DualStreamNetwork().to(dev).train()
+    if world > 1:                                    # identical replicas
+        for s in model._stores() + [model._head_store]:
+            dist.broadcast(s.flat, 0)
+    opt = vit2spn.FusedAdam(model.parameters(), lr=1e-4)
+    opt.grad_scale = 1.0 / world
+    u8 = torch.from_numpy(orc.synthetic_octmnist_u8(2 * B, seed=1000 + rank)).to(dev)
+    views = torch.empty(2, B, 3, 224, 224, device=dev)
+    _lib.init_device(local)
+    _lib.check(_lib.lib.v2s_preprocess_u8(_lib.ptr(u8), _lib.ptr(views), 2 * B, _lib.stream_ptr()))
+    x1, x2 = views[0], views[1]
+
+    def grads_allreduce():
+        if world > 1:
+            for s in model._stores()[:2]:
+                dist.all_reduce(s.flat_grad[:s.active_numel])
+            dist.all_reduce(model._head_store.flat_grad)
+
+    def step(a, b):
+        loss = model.ssp_step(a, b, accumulation_steps=1)
+        grads_allreduce()
+        opt.step()
+        opt.zero_grad()
+        model.update_target_network()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    opt.zero_grad()
+    for _ in range(max(args.warmup, 3)):
+        step(x1, x2)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.lib.v2s_launch_count()
+    ms_total = timed(lambda: step(x1, x2), args.steps)
+    launches = int(_lib.lib.v2s_launch_count() - l0)
+    clocks = sampler.stop() if rank == 0 else None
+    flag = _lib.lib.v2s_debug_flag()
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end: host fp32 views (the reference's DataLoader contract, ref:206-207) → pinned H2D
+    #      every step (double-buffered on a copy stream) + loss.item() D2H every step ---------------
+    e2e = None
+    if not args.no_e2e:
+        host = [views[i].cpu().pin_memory() for i in range(2)]
+        bufs = [torch.empty_like(views) for _ in range(2)]
+        copy_stream = torch.cuda.Stream()
+        ready = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+
+        def upload(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done[i])
+                bufs[i][0].copy_(host[0], non_blocking=True)
+                bufs[i][1].copy_(host[1], non_blocking=True)
+                ready[i].record(copy_stream)
+
+        state = {"i": 0}
+        for d in done:
+            d.record()
+
+        def e2e_step():
+            i = state["i"]
+            torch.cuda.current_stream().wait_event(ready[i])
+            loss = step(bufs[i][0], bufs[i][1])
+            done[i].record()
+            upload(i)                      # refill this buffer for step i+2 while step i+1 computes
+            state["i"] = i ^ 1
+            return loss.item()             # D2H read of the step's result, every step (ref:220)
+
+        upload(0); upload(1)
+        for _ in range(3):
+            e2e_step()
+        ms_e2e = timed(e2e_step, args.steps)
+        e2e = {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s",
+               "h2d_bytes_per_step": int(2 * B * 3 * 224 * 224 * 4), "d2h_bytes_per_step": 4,
+               "ms_per_step": ms_e2e / args.steps,
+               "input": "fp32 views [2,B,3,224,224] in pinned host memory, double-buffered H2D on a copy stream"}
+
+    # ---- per-kernel-class device timing (CUDA events on the launching stream) → roofline ---------
+    pk, pk_src = peaks()
+    _lib.prof_enable(True)
+    nprof = 3
+    for _ in range(nprof):
+        step(x1, x2)
+    rep = _lib.prof_report()
+    _lib.prof_enable(False)
+    classes = {k: {"launches": n // nprof, "ms_per_step": ms / nprof,
+                   "work_per_step": w / nprof} for k, (n, ms, w) in rep.items()}
+    tensor_classes = [k for k in classes if k.startswith("gemm") or k.startswith("attn")]
+    roofline = None
+    if tensor_classes:
+        dom = max(tensor_classes, key=lambda k: classes[k]["ms_per_step"])
+        c = classes[dom]
+        ach = c["work_per_step"] / (c["ms_per_step"] * 1e-3) / 1e12
+        peak = pk["bf16_tflops_sustained"]
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": f"bf16_tflops_sustained ({pk_src})",
+                    "launches_per_step": c["launches"], "ms_per_step": c["ms_per_step"],
+                    "share_of_step": c["ms_per_step"] / ms_per_step}
+    step_tflops = value / world * FLOP_PER_PAIR / 1e12
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cstep, cores = cpu_reference_step_fn(args.cpu_batch)
+        cstep()
+        n = 0
+        t0 = time.perf_counter()
+        while n < 3 or (time.perf_counter() - t0 < 12 and n < 30):
+            cstep(); n += 1
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": args.cpu_batch * n / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+                        "sample": f"{n} full SSP steps (fwd+bwd+Adam+EMA, fp32) of {args.cpu_batch} pairs each; "
+                                  "oracle port of the reference algorithm (the reference's CPU path is torch fp32)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.mode, "data": "synthetic",
+            "config": {"workload": "ViT-Tiny dual-stream SSP full step (4 backbones fwd, 2 bwd, heads, cosine loss, "
+                                   "Adam lr 1e-4, EMA 0.999), accumulation 1, batch 128/GPU (BASELINE config 2)",
+                       "batch_per_gpu": B, "parallelism": f"dp{world}",
+                       "l2": "inputs (154 MB/step) and activations (>2 GB/step) exceed the 126 MB L2; no explicit flush"},
+            "step_tflops_per_gpu": step_tflops,
+            "step_frac_of_bf16_peak": step_tflops / pk["bf16_tflops_sustained"],
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks, "kernel_classes": classes, "debug_flag": flag,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -758,6 +758,8 @@ int v2s_prof_report(char* host_buf, int64_t buf_bytes) {
   return 0;
 }
 
+int v2s_debug_flag(void) { return gemm_tc_error_flag(); }
+
 int v2s_test_gemm(int which, const void* a, const void* b, void* c, int m, int n, int k, int variant, void* stream) {
   return gemm_tc_test(which, a, b, c, m, n, k, variant, (cudaStream_t)stream);
 }

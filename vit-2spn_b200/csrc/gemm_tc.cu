@@ -1,18 +1,511 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a: persistent, warp-specialised, grouped (up to 4 backbones
+// per launch), bf16 operands with fp32 accumulation in tensor memory, fused epilogues staged through
+// shared memory and written with TMA (plain store or reduce-add).
+//
+//   C[M,N] (+)= A[M,K] * B[N,K]^T        A, B: K-major or MN-major (UMMA descriptor major bits)
+//
+// CTA = 384 threads: warp 0 TMA producer, warp 1 MMA issuer (single thread), warp 2 TMEM allocator,
+// warps 4..11 epilogue (two groups of four warps; a warp reads TMEM lane quarter warp%4, the two
+// groups take alternate 32-column chunks of the 128x192 accumulator).
+// Tile = 128 x 192 x 64; 3-stage smem ring (A 16 KB + B 24 KB per stage); 2 accumulator stages in
+// TMEM (2 x 192 of 512 columns) so that the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <string.h>
+
+#include <unordered_map>
+
 #include "gemm_tc.cuh"
+#include "ptx.cuh"
 
 namespace v2s {
 
-int gemm_tc_init() { return 0; }
+namespace {
 
-int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t stream, int* handled) {
-  *handled = 0;
+constexpr int BM = 128, BN = 192, BK = 64;
+constexpr int STAGES = 3;
+constexpr int A_STAGE_BYTES = BM * BK * 2;        // 16384
+constexpr int B_STAGE_BYTES = BN * BK * 2;        // 24576
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int CHUNK = 32;                         // epilogue column chunk
+constexpr int N_CHUNKS = BN / CHUNK;              // 6
+constexpr int STG_BYTES = BM * CHUNK * 4;         // 16384: one fp32 chunk (bf16 chunks use half)
+constexpr int SMEM_STAGING_OFF = STAGES * STAGE_BYTES;                 // 122880
+constexpr int SMEM_BAR_OFF = SMEM_STAGING_OFF + 4 * STG_BYTES;         // 188416
+constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 256 + 1024;                  // + alignment slack
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;                   // TMEM column stride between accumulator stages
+constexpr int N_THREADS = 384;
+
+enum TcEpi : int {
+  T_STORE = 0,   // out = acc (+bias)            OutT = bf16 | fp32
+  T_RESID = 1,   // out(fp32) = acc + bias + aux(fp32)
+  T_GELU = 2,    // u = acc + bias -> out2 (optional), gelu(u) -> out   (bf16)
+  T_DGELU = 3,   // out(bf16) = acc * gelu'(aux(bf16))
+  T_ACCUM = 4,   // global(fp32) += acc          (TMA reduce-add; split-K)
+};
+
+struct alignas(64) TcParams {
+  CUtensorMap tmA[MAXG], tmB[MAXG], tmOut[MAXG], tmOut2[MAXG], tmAux[MAXG];
+  const float* bias[MAXG];
+  int M, N, K;
+  int tiles_m, tiles_n, splits, kb_total, kb_per_split, groups, total_tiles;
+  int a_mn, b_mn;
+  int out2_mask;      // bit g: group g writes the secondary output (pre-GELU u)
+  int* err_flag;
+};
+
+// fast erf-GELU for the bf16 path: Abramowitz-Stegun 7.1.26, |erf error| < 1.5e-7 (far below bf16
+// resolution); shares exp(-x^2/2) between gelu and gelu'.
+__device__ __forceinline__ void gelu_core(float x, float& cdf, float& pdf_e) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float e = exp2f(-0.72134752044448170f * x * x);   // exp(-x^2/2)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * e;
+  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  pdf_e = e;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float cdf, e;
+  gelu_core(x, cdf, e);
+  return x * cdf;
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  float cdf, e;
+  gelu_core(x, cdf, e);
+  return fmaf(x * 0.39894228040143268f, e, cdf);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int EPI, bool OUT_BF16>
+__global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;      // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;          // [2] accumulator drained
+  uint64_t* aux_bar = tempty_bar + 2;            // [2] per epilogue group: aux chunk landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aux_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int g = 0; g < p.groups; ++g) {
+      ptx::prefetch_tmap(&p.tmA[g]);
+      ptx::prefetch_tmap(&p.tmB[g]);
+      ptx::prefetch_tmap(&p.tmOut[g]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], 8); ptx::mbar_init(&aux_bar[s], 1); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int tiles_per_group = p.tiles_m * p.splits * p.tiles_n;
+  auto decode = [&](int t, int& g, int& m_tile, int& split, int& n_tile) {
+    g = t / tiles_per_group;
+    int r = t - g * tiles_per_group;
+    n_tile = r % p.tiles_n; r /= p.tiles_n;
+    split = r % p.splits;
+    m_tile = r / p.splits;
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ================= TMA producer =================
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      int g, m_tile, split, n_tile;
+      decode(t, g, m_tile, split, n_tile);
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
+        uint8_t* sa = smem + stage * STAGE_BYTES;
+        uint8_t* sb = sa + A_STAGE_BYTES;
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+        if (!p.a_mn) {
+          ptx::tma_load_2d(sa, &p.tmA[g], &full_bar[stage], kb * BK, m_tile * BM);
+        } else {
+          ptx::tma_load_2d(sa, &p.tmA[g], &full_bar[stage], m_tile * BM, kb * BK);
+          ptx::tma_load_2d(sa + 8192, &p.tmA[g], &full_bar[stage], m_tile * BM + 64, kb * BK);
+        }
+        if (!p.b_mn) {
+          ptx::tma_load_2d(sb, &p.tmB[g], &full_bar[stage], kb * BK, n_tile * BN);
+        } else {
+          ptx::tma_load_2d(sb, &p.tmB[g], &full_bar[stage], n_tile * BN, kb * BK);
+          ptx::tma_load_2d(sb + 8192, &p.tmB[g], &full_bar[stage], n_tile * BN + 64, kb * BK);
+          ptx::tma_load_2d(sb + 16384, &p.tmB[g], &full_bar[stage], n_tile * BN + 128, kb * BK);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = ptx::make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      int g, m_tile, split, n_tile;
+      decode(t, g, m_tile, split, n_tile);
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 2);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // K-major: 16 elements = 32 B along the swizzled row; MN-major: 16 k-rows = 2048 B
+          const uint64_t da = p.a_mn ? ptx::make_smem_desc(sa + k * 2048, 8192, 1024)
+                                     : ptx::make_smem_desc(sa + k * 32, 16, 1024);
+          const uint64_t db = p.b_mn ? ptx::make_smem_desc(sb + k * 2048, 8192, 1024)
+                                     : ptx::make_smem_desc(sb + k * 32, 16, 1024);
+          ptx::umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty_bar[stage]);       // frees the smem stage when these MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      ptx::umma_commit(&tfull_bar[acc]);           // accumulator complete → epilogue
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int ge = (warp - 4) >> 2;                 // epilogue group 0/1
+    const int q = warp & 3;                         // TMEM lane quarter
+    const int row = q * 32 + lane;                  // row within the 128-row tile
+    const bool issuer = (warp == 4 + 4 * ge) && lane == 0;
+    uint8_t* stg_out = smem + SMEM_STAGING_OFF + ge * 2 * STG_BYTES;
+    uint8_t* stg_aux = stg_out + STG_BYTES;
+    const int bar_id = 1 + ge;
+    int acc = 0; uint32_t acc_phase = 0;
+    uint32_t aux_phase = 0;
+    constexpr bool HAS_AUX = (EPI == T_RESID || EPI == T_DGELU);
+    constexpr int AUX_BYTES = (EPI == T_RESID) ? BM * CHUNK * 4 : BM * CHUNK * 2;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      int g, m_tile, split, n_tile;
+      decode(t, g, m_tile, split, n_tile);
+      const int m0 = m_tile * BM, n0 = n_tile * BN;
+      if (HAS_AUX && issuer) {
+        ptx::mbar_arrive_expect_tx(&aux_bar[ge], AUX_BYTES);
+        ptx::tma_load_2d(stg_aux, &p.tmAux[g], &aux_bar[ge], n0 + ge * CHUNK, m0);
+      }
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 4);
+      ptx::tc_fence_after();
+      const bool write_u = (EPI == T_GELU) && ((p.out2_mask >> g) & 1);
+      for (int c = ge; c < N_CHUNKS; c += 2) {
+        const int col0 = n0 + c * CHUNK;
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE + c * CHUNK, r);
+        ptx::tmem_ld_wait();
+        if (c + 2 >= N_CHUNKS) {                    // last TMEM read of this warp for this tile
+          ptx::tc_fence_before();
+          if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+        }
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (EPI != T_ACCUM && EPI != T_DGELU && p.bias[g] != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias[g] + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col0 + 4 * i < p.N) b = __ldg(b4 + i);
+            v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+          }
+        }
+        if (HAS_AUX) {
+          ptx::mbar_wait(&aux_bar[ge], aux_phase, p.err_flag, 5);
+          aux_phase ^= 1;
+          if (EPI == T_RESID) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 a = *reinterpret_cast<const float4*>(stg_aux + row * 128 + ((j ^ (row & 7)) << 4));
+              v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 a = *reinterpret_cast<const uint4*>(stg_aux + row * 64 + ((j ^ ((row >> 1) & 3)) << 4));
+              const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 u2 = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+                v[8 * j + 2 * e] *= gelu_grad_fast(__low2float(u2));
+                v[8 * j + 2 * e + 1] *= gelu_grad_fast(__high2float(u2));
+              }
+            }
+          }
+        }
+        // the previous TMA store out of this group's staging buffers must have finished reading them
+        if (issuer) ptx::tma_wait_group_read<0>();
+        ptx::bar_sync(bar_id, 128);
+        if (OUT_BF16) {
+          if (EPI == T_GELU) {
+            if (write_u) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                o.x = pack_bf16(v[8 * j], v[8 * j + 1]); o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+                o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                *reinterpret_cast<uint4*>(stg_aux + row * 64 + ((j ^ ((row >> 1) & 3)) << 4)) = o;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16(v[8 * j], v[8 * j + 1]); o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+            o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+            *reinterpret_cast<uint4*>(stg_out + row * 64 + ((j ^ ((row >> 1) & 3)) << 4)) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(stg_out + row * 128 + ((j ^ (row & 7)) << 4)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        ptx::fence_proxy_async();
+        ptx::bar_sync(bar_id, 128);
+        if (issuer) {
+          if (col0 < p.N) {
+            if (EPI == T_ACCUM) ptx::tma_reduce_add_2d(&p.tmOut[g], stg_out, col0, m0);
+            else ptx::tma_store_2d(&p.tmOut[g], stg_out, col0, m0);
+            if (write_u) ptx::tma_store_2d(&p.tmOut2[g], stg_aux, col0, m0);
+          }
+          ptx::tma_commit_group();
+          if (HAS_AUX && c + 2 < N_CHUNKS) {        // aux buffer is free (all reads precede the barrier)
+            ptx::mbar_arrive_expect_tx(&aux_bar[ge], AUX_BYTES);
+            ptx::tma_load_2d(stg_aux, &p.tmAux[g], &aux_bar[ge], n0 + (c + 2) * CHUNK, m0);
+          }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (issuer) ptx::tma_wait_group<0>();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor-map cache + dispatch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int* g_err_flag = nullptr;      // device int, allocated once at init (4 bytes; the only allocation)
+int g_num_sms = 148;
+bool g_disabled = false;
+
+struct MapKey {
+  const void* ptr; uint64_t d0, d1, stride1; uint32_t b0, b1, dtype, swz;
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(MapKey) / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// 2-D row-major tensor [d1 rows, d0 cols] of `dtype`, row stride `stride1` elements, box b0 x b1
+int get_map(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t stride1_elems, uint32_t b0,
+            uint32_t b1, bool is_bf16, CUtensorMapSwizzle swz) {
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.d0 = d0; key.d1 = d1; key.stride1 = stride1_elems; key.b0 = b0; key.b1 = b1;
+  key.dtype = is_bf16 ? 1 : 0; key.swz = (uint32_t)swz;
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = it->second; return 0; }
+  const uint64_t es = is_bf16 ? 2 : 4;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((stride1_elems * es) & 15)) {
+    set_error("gemm_tc: tensor %p (row stride %llu B) is not 16-byte aligned for TMA", ptr,
+              (unsigned long long)(stride1_elems * es));
+    return 1;
+  }
+  cuuint64_t gdim[2] = {d0, d1};
+  cuuint64_t gstride[1] = {stride1_elems * es};
+  cuuint32_t box[2] = {b0, b1};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = g_encode(&m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for tensor %p dims %llu x %llu box %u x %u", (int)r, ptr,
+              (unsigned long long)d0, (unsigned long long)d1, b0, b1);
+    return 1;
+  }
+  if (g_maps.size() > 8192) g_maps.clear();
+  g_maps.emplace(key, m);
+  *out = m;
   return 0;
 }
 
+template <int EPI, bool OUT_BF16>
+int launch_kernel(const TcParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    V2S_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI, OUT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    attr_set = true;
+  }
+  const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+  gemm_tc_kernel<EPI, OUT_BF16><<<grid, N_THREADS, SMEM_TOTAL, stream>>>(p);
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+int gemm_tc_init() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  int dev = 0;
+  V2S_CUDA_OK(cudaGetDevice(&dev));
+  V2S_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  V2S_CUDA_OK(cudaMalloc(&g_err_flag, sizeof(int)));
+  V2S_CUDA_OK(cudaMemset(g_err_flag, 0, sizeof(int)));
+  const char* env = getenv("V2S_GEMM");
+  g_disabled = env && strcmp(env, "simt") == 0;   // debugging: route every GEMM through the SIMT kernel
+  return 0;
+}
+
+int gemm_tc_error_flag() {
+  if (!g_err_flag) return 0;
+  int v = 0;
+  cudaMemcpy(&v, g_err_flag, sizeof(int), cudaMemcpyDeviceToHost);
+  if (v) cudaMemset(g_err_flag, 0, sizeof(int));
+  return v;
+}
+
+int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t stream, int* handled) {
+  *handled = 0;
+  if (g_disabled || !g_encode) return 0;
+  if (ta != 1 || tb != 1) return 0;                       // fp32 check mode stays on the SIMT kernel
+  if (d.a_remap || d.b_remap) return 0;
+  int epi;
+  switch (d.epi) {
+    case EPI_STORE: epi = T_STORE; break;
+    case EPI_BIAS_RESID: epi = T_RESID; break;
+    case EPI_BIAS_GELU: epi = T_GELU; break;
+    case EPI_DGELU: epi = T_DGELU; break;
+    case EPI_ACCUM: epi = T_ACCUM; break;
+    default: return 0;
+  }
+  if (d.alpha != 1.0f) return 0;
+  const bool out_bf16 = (to == 1);
+  if ((epi == T_RESID || epi == T_ACCUM) && out_bf16) return 0;
+  if ((epi == T_GELU || epi == T_DGELU) && !out_bf16) return 0;
+  int a_mn, b_mn;
+  int64_t a_ld, b_ld;
+  if (d.a_cs == 1) { a_mn = 0; a_ld = d.a_rs; } else if (d.a_rs == 1) { a_mn = 1; a_ld = d.a_cs; } else return 0;
+  if (d.b_rs == 1) { b_mn = 0; b_ld = d.b_cs; } else if (d.b_cs == 1) { b_mn = 1; b_ld = d.b_rs; } else return 0;
+  if ((a_ld % 8) || (b_ld % 8) || (d.ldc % 8) || (d.N % 8)) return 0;
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = d.M; p.N = d.N; p.K = d.K; p.groups = d.groups;
+  p.tiles_m = (d.M + BM - 1) / BM;
+  p.tiles_n = (d.N + BN - 1) / BN;
+  p.kb_total = (d.K + BK - 1) / BK;
+  p.splits = 1;
+  if (epi == T_ACCUM) {
+    const int base = d.groups * p.tiles_m * p.tiles_n;
+    int s = (g_num_sms + base - 1) / base;
+    const int max_s = p.kb_total / 4 > 0 ? p.kb_total / 4 : 1;
+    if (s > max_s) s = max_s;
+    if (s < 1) s = 1;
+    p.splits = s;
+  }
+  p.kb_per_split = (p.kb_total + p.splits - 1) / p.splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
+  p.total_tiles = d.groups * p.tiles_m * p.tiles_n * p.splits;
+  p.a_mn = a_mn; p.b_mn = b_mn;
+  p.err_flag = g_err_flag;
+  const CUtensorMapSwizzle out_swz = out_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  for (int g = 0; g < d.groups; ++g) {
+    if (!a_mn) V2S_TRY(get_map(&p.tmA[g], d.A[g], d.K, d.M, a_ld, BK, BM, true, CU_TENSOR_MAP_SWIZZLE_128B));
+    else V2S_TRY(get_map(&p.tmA[g], d.A[g], d.M, d.K, a_ld, 64, BK, true, CU_TENSOR_MAP_SWIZZLE_128B));
+    if (!b_mn) V2S_TRY(get_map(&p.tmB[g], d.B[g], d.K, d.N, b_ld, BK, BN, true, CU_TENSOR_MAP_SWIZZLE_128B));
+    else V2S_TRY(get_map(&p.tmB[g], d.B[g], d.N, d.K, b_ld, 64, BK, true, CU_TENSOR_MAP_SWIZZLE_128B));
+    void* outp = (epi == T_GELU) ? d.out2[g] : d.out[g];      // GELU: primary = h (GemmDesc.out2), secondary = u
+    V2S_TRY(get_map(&p.tmOut[g], outp, d.N, d.M, d.ldc, CHUNK, BM, out_bf16, out_swz));
+    if (epi == T_GELU && d.out[g]) {
+      V2S_TRY(get_map(&p.tmOut2[g], d.out[g], d.N, d.M, d.ldc, CHUNK, BM, true, CU_TENSOR_MAP_SWIZZLE_64B));
+      p.out2_mask |= 1 << g;
+    }
+    if (epi == T_RESID) V2S_TRY(get_map(&p.tmAux[g], d.resid[g], d.N, d.M, d.ldc, CHUNK, BM, false, CU_TENSOR_MAP_SWIZZLE_128B));
+    if (epi == T_DGELU) V2S_TRY(get_map(&p.tmAux[g], d.aux[g], d.N, d.M, d.ldc, CHUNK, BM, true, CU_TENSOR_MAP_SWIZZLE_64B));
+    p.bias[g] = (epi == T_ACCUM || epi == T_DGELU) ? nullptr : d.bias[g];
+  }
+  int rc;
+  switch (epi) {
+    case T_STORE: rc = out_bf16 ? launch_kernel<T_STORE, true>(p, stream) : launch_kernel<T_STORE, false>(p, stream); break;
+    case T_RESID: rc = launch_kernel<T_RESID, false>(p, stream); break;
+    case T_GELU: rc = launch_kernel<T_GELU, true>(p, stream); break;
+    case T_DGELU: rc = launch_kernel<T_DGELU, true>(p, stream); break;
+    default: rc = launch_kernel<T_ACCUM, false>(p, stream); break;
+  }
+  if (rc) return rc;
+  *handled = 1;
+  return 0;
+}
+
+// test hook (v2s_test_gemm): which = 0 NT (A[M,K], B[N,K]), 1 NN/dgrad (A[M,K], B[K,N]),
+// 2 TN/wgrad (A[K,M], B[K,N], out fp32 +=); variant: 0 = tensor-core path, 1 = SIMT reference.
+// bf16 operands; out bf16 for which 0/1, fp32 accumulate-into for which 2.
 int gemm_tc_test(int which, const void* a, const void* b, void* c, int m, int n, int k, int variant,
                  cudaStream_t stream) {
-  set_error("gemm_tc_test: not built yet");
-  return 1;
+  GemmDesc d = make_gemm_desc();
+  d.M = m; d.N = n; d.K = k; d.groups = 1; d.A[0] = a; d.B[0] = b; d.out[0] = c; d.ldc = n;
+  int to = 1;
+  if (which == 0) { d.a_rs = k; d.a_cs = 1; d.b_rs = 1; d.b_cs = k; d.epi = EPI_STORE; }
+  else if (which == 1) { d.a_rs = k; d.a_cs = 1; d.b_rs = n; d.b_cs = 1; d.epi = EPI_STORE; }
+  else if (which == 2) { d.a_rs = 1; d.a_cs = m; d.b_rs = n; d.b_cs = 1; d.epi = EPI_ACCUM; to = 0; d.split_k = 1; }
+  else { set_error("gemm_tc_test: which must be 0..2"); return 1; }
+  if (variant == 1) return launch_gemm_simt(d, 1, 1, to, stream);
+  int handled = 0;
+  V2S_TRY(launch_gemm_tc(d, 1, 1, to, stream, &handled));
+  if (!handled) { set_error("gemm_tc_test: shape not handled by the tensor-core path"); return 1; }
+  return 0;
 }
 
 }  // namespace v2s

@@ -10,6 +10,8 @@ int gemm_tc_init();
 // tries to run `d` on the tensor-core path; *handled = 1 if it did (0: caller falls back to SIMT,
 // only ever taken for shapes/types the tcgen05 kernels do not cover, e.g. fp32 check mode)
 int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t stream, int* handled);
+// reads and clears the device-side protocol error flag (0 = none); synchronises
+int gemm_tc_error_flag();
 // test hook behind v2s_test_gemm
 int gemm_tc_test(int which, const void* a, const void* b, void* c, int m, int n, int k, int variant,
                  cudaStream_t stream);
