@@ -161,6 +161,8 @@ int v2s_preprocess_u8(const uint8_t* src, float* dst, int batch, void* stream);
 /* test hooks: individual operators, used by tests/ to localise a parity failure */
 int v2s_test_gemm(int which, const void* a, const void* b, void* c, int m, int n, int k,
                   int variant, void* stream);
+int v2s_test_attention(int which, const void* qkv, void* ctx, float* lse, const void* dctx, void* dqkv,
+                       int batch, int variant, void* stream);
 /* reads and clears the device-side pipeline-protocol error flag of the tcgen05 kernels (0 = ok) */
 int v2s_debug_flag(void);
 int64_t v2s_launch_count(void); /* kernels launched by this library since load (bench: gpu_launches) */

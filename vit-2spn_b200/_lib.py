@@ -63,6 +63,7 @@ _SIGS = {
     "v2s_cast_bf16": (C.c_int, [_vp, _vp, _i64, _vp]),
     "v2s_preprocess_u8": (C.c_int, [_vp, _vp, _i, _vp]),
     "v2s_test_gemm": (C.c_int, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "v2s_test_attention": (C.c_int, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "v2s_launch_count": (_i64, []),
     "v2s_debug_flag": (C.c_int, []),
     "v2s_prof_enable": (C.c_int, [_i]),

@@ -1,0 +1,574 @@
+// tcgen05 attention for the 197-token ViT-Tiny blocks (3 heads x 64): one CTA per (head, image,
+// backbone).  All 197 keys fit one tile (padded to 208), so the softmax is a plain two-pass row
+// softmax over a 128 x 208 fp32 score tile held in tensor memory - no online rescaling.
+//
+//   forward:  S = Q K^T (UMMA 128x208x64, both K-major)  ->  P = softmax(S/8) (thread per row,
+//             TMEM -> registers -> bf16 P in swizzled smem)  ->  O = P V (UMMA 128x64x208, V MN-major)
+//             -> O / rowsum -> bf16 -> TMA store; log-sum-exp saved for the backward.
+//   backward: see attn_bwd_tc_kernel.
+#include <string.h>
+
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace v2s {
+
+namespace {
+
+constexpr int KPAD = 208;                      // keys padded to a multiple of 16
+constexpr int QT = 128;                        // query rows per tile (2 tiles cover 197)
+constexpr int Q_TILE_BYTES = QT * DH * 2;      // 16384
+constexpr int KV_TILE_BYTES = KPAD * DH * 2;   // 26624
+constexpr int P_TILE_BYTES = 4 * QT * 128;     // 65536: four 64-key column blocks of 128 rows x 128 B
+constexpr float SCALE = 0.125f;                // 64^-0.5
+constexpr float SCALE_LOG2E = 0.125f * 1.4426950408889634f;
+
+// ---- forward --------------------------------------------------------------------------------
+constexpr int F_OFF_Q = 0;                                  // 2 tiles
+constexpr int F_OFF_K = 2 * Q_TILE_BYTES;                   // 32768
+constexpr int F_OFF_V = F_OFF_K + KV_TILE_BYTES;            // 59392
+constexpr int F_OFF_P = F_OFF_V + KV_TILE_BYTES;            // 86016 (2 tiles)
+constexpr int F_OFF_BAR = F_OFF_P + 2 * P_TILE_BYTES;       // 217088
+constexpr int F_SMEM = F_OFF_BAR + 128 + 1024;
+constexpr int F_THREADS = 288;                              // warp 0 control, warps 1..8 softmax
+
+struct alignas(64) AttnFwdParams {
+  CUtensorMap tmQ[MAXG], tmKV[MAXG], tmCtx[MAXG];
+  float* lse[MAXG];
+  int* err_flag;
+};
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// writes 8 consecutive bf16 (one 16-byte chunk) of row r, key group c8 (keys 8*c8..8*c8+7) into a
+// K-major SWIZZLE_128B operand tile made of 64-key column blocks of [128 rows x 128 B]
+__device__ __forceinline__ void store_p_chunk(uint8_t* tile, int r, int c8, uint4 v) {
+  const int block = c8 >> 3, chunk = c8 & 7;
+  *reinterpret_cast<uint4*>(tile + block * (QT * 128) + r * 128 + ((chunk ^ (r & 7)) << 4)) = v;
+}
+
+__global__ void __launch_bounds__(F_THREADS, 1) attn_fwd_tc_kernel(const __grid_constant__ AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + F_OFF_BAR);
+  uint64_t* bar_s = bar_load + 1;     // [2]
+  uint64_t* bar_p = bar_s + 2;        // [2]
+  uint64_t* bar_o = bar_p + 2;        // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_o + 2);
+  const int h = blockIdx.x, b = blockIdx.y, g = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_init(bar_load, 1);
+      for (int t = 0; t < 2; ++t) { ptx::mbar_init(&bar_s[t], 1); ptx::mbar_init(&bar_p[t], 128); ptx::mbar_init(&bar_o[t], 1); }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_ptr, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(bar_load, 2 * Q_TILE_BYTES + 2 * KV_TILE_BYTES);
+      ptx::tma_load_3d(smem + F_OFF_Q, &p.tmQ[g], bar_load, h * DH, 0, b);
+      ptx::tma_load_3d(smem + F_OFF_Q + Q_TILE_BYTES, &p.tmQ[g], bar_load, h * DH, QT, b);
+      ptx::tma_load_3d(smem + F_OFF_K, &p.tmKV[g], bar_load, D + h * DH, 0, b);
+      ptx::tma_load_3d(smem + F_OFF_V, &p.tmKV[g], bar_load, 2 * D + h * DH, 0, b);
+      ptx::mbar_wait(bar_load, 0, p.err_flag, 11);
+      ptx::tc_fence_after();
+      const uint32_t idesc_s = ptx::make_idesc_bf16(QT, KPAD, 0, 0);
+      const uint32_t sk = ptx::smem_u32(smem + F_OFF_K);
+      for (int t = 0; t < 2; ++t) {
+        const uint32_t sq = ptx::smem_u32(smem + F_OFF_Q + t * Q_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          ptx::umma_bf16(tmem_base + t * 256, ptx::make_smem_desc(sq + k * 32, 16, 1024),
+                         ptx::make_smem_desc(sk + k * 32, 16, 1024), idesc_s, k > 0);
+        ptx::umma_commit(&bar_s[t]);
+      }
+      const uint32_t idesc_o = ptx::make_idesc_bf16(QT, DH, 0, 1);
+      const uint32_t sv = ptx::smem_u32(smem + F_OFF_V);
+      for (int t = 0; t < 2; ++t) {
+        ptx::mbar_wait(&bar_p[t], 0, p.err_flag, 12);
+        ptx::tc_fence_after();
+        const uint32_t sp = ptx::smem_u32(smem + F_OFF_P + t * P_TILE_BYTES);
+#pragma unroll
+        for (int j = 0; j < KPAD / 16; ++j)
+          ptx::umma_bf16(tmem_base + t * 256,
+                         ptx::make_smem_desc(sp + (j >> 2) * (QT * 128) + (j & 3) * 32, 16, 1024),
+                         ptx::make_smem_desc(sv + j * 2048, 8192, 1024), idesc_o, j > 0);
+        ptx::umma_commit(&bar_o[t]);
+      }
+    }
+  } else {
+    const int t = (warp - 1) >> 2;              // query tile
+    const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int qrow = t * QT + row;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + t * 256;
+    uint8_t* ptile = smem + F_OFF_P + t * P_TILE_BYTES;
+    ptx::mbar_wait(&bar_s[t], 0, p.err_flag, 13);
+    ptx::tc_fence_after();
+    // pass 1: row maximum over the 197 real keys
+    float mx = -INFINITY;
+    uint32_t r[32];
+#pragma unroll 1
+    for (int c = 0; c < 6; ++c) {
+      ptx::tmem_ld_32x32(taddr + c * 32, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+    }
+    ptx::tmem_ld_32x16(taddr + 192, r);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < NT - 192; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+    // pass 2: p = exp2((s - max) * scale * log2e), row sum, bf16 P into the swizzled operand tile
+    const float moff = mx * SCALE_LOG2E;
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 6; ++c) {
+      ptx::tmem_ld_32x32(taddr + c * 32, r);
+      ptx::tmem_ld_wait();
+      float e[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { e[i] = ptx::ex2_approx(fmaf(__uint_as_float(r[i]), SCALE_LOG2E, -moff)); sum += e[i]; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 v;
+        v.x = pack2(e[8 * j], e[8 * j + 1]); v.y = pack2(e[8 * j + 2], e[8 * j + 3]);
+        v.z = pack2(e[8 * j + 4], e[8 * j + 5]); v.w = pack2(e[8 * j + 6], e[8 * j + 7]);
+        store_p_chunk(ptile, row, c * 4 + j, v);
+      }
+    }
+    {
+      ptx::tmem_ld_32x16(taddr + 192, r);
+      ptx::tmem_ld_wait();
+      float e[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        e[i] = (192 + i < NT) ? ptx::ex2_approx(fmaf(__uint_as_float(r[i]), SCALE_LOG2E, -moff)) : 0.f;
+        sum += e[i];
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        uint4 v;
+        v.x = pack2(e[8 * j], e[8 * j + 1]); v.y = pack2(e[8 * j + 2], e[8 * j + 3]);
+        v.z = pack2(e[8 * j + 4], e[8 * j + 5]); v.w = pack2(e[8 * j + 6], e[8 * j + 7]);
+        store_p_chunk(ptile, row, 24 + j, v);
+      }
+    }
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    ptx::mbar_arrive(&bar_p[t]);
+    if (qrow < NT && p.lse[g]) p.lse[g][((int64_t)b * NH + h) * NT + qrow] = mx * SCALE + __logf(sum);
+    const float inv = 1.0f / sum;
+    ptx::mbar_wait(&bar_o[t], 0, p.err_flag, 14);
+    ptx::tc_fence_after();
+    uint8_t* stg = smem + F_OFF_Q + t * Q_TILE_BYTES;       // Q tile is dead once S is complete
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      ptx::tmem_ld_32x32(taddr + c * 32, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 v;
+        v.x = pack2(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+        v.y = pack2(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+        v.z = pack2(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+        v.w = pack2(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+        *reinterpret_cast<uint4*>(stg + row * 128 + (((c * 4 + j) ^ (row & 7)) << 4)) = v;
+      }
+    }
+    ptx::fence_proxy_async();
+    ptx::bar_sync(1 + t, 128);
+    if (row == 0) {
+      ptx::tma_store_3d(&p.tmCtx[g], stg, h * DH, t * QT, b);   // rows >= 197 are clipped by TMA
+      ptx::tma_commit_group();
+      ptx::tma_wait_group<0>();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- backward ---------------------------------------------------------------------------------
+// One CTA per (head, image, backbone); the two 128-row query tiles are processed one after the
+// other while dK / dV accumulate in tensor memory across both.
+//   S  = Q_t K^T                      (UMMA 128x208x64)         -> P = exp2(S*c - lse*log2e)  (bf16, smem)
+//   dP = dO_t V^T                     (UMMA 128x208x64)         -> dS = P * (dP - D) / 8      (bf16, smem)
+//   dV += P^T dO_t,  dK += dS^T Q_t   (UMMA 128x64x128, A MN-major = the same smem tiles read transposed)
+//   dQ_t = dS K                       (UMMA 128x64x208, K MN-major)
+// TMEM columns: [0,208) S then dP then dQ_t | [256,384) dK (two 128-key tiles) | [384,512) dV.
+constexpr int B_OFF_Q = 0;
+constexpr int B_OFF_DO = Q_TILE_BYTES;
+constexpr int B_OFF_K = 2 * Q_TILE_BYTES;
+constexpr int B_OFF_V = B_OFF_K + KV_TILE_BYTES;
+constexpr int B_OFF_P = B_OFF_V + KV_TILE_BYTES;
+constexpr int B_OFF_DS = B_OFF_P + P_TILE_BYTES;
+constexpr int B_OFF_BAR = B_OFF_DS + P_TILE_BYTES;       // 217088
+constexpr int B_SMEM = B_OFF_BAR + 256 + 1024;
+constexpr int B_THREADS = 288;
+constexpr int TM_DK = 256, TM_DV = 384;
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct alignas(64) AttnBwdParams {
+  CUtensorMap tmQ[MAXG], tmKV[MAXG], tmDO[MAXG], tmDQKV[MAXG];
+  const bf16* ctx[MAXG];
+  const float* lse[MAXG];
+  int* err_flag;
+};
+
+__device__ __forceinline__ uint4 load_p_chunk(const uint8_t* tile, int r, int c8) {
+  const int block = c8 >> 3, chunk = c8 & 7;
+  return *reinterpret_cast<const uint4*>(tile + block * (QT * 128) + r * 128 + ((chunk ^ (r & 7)) << 4));
+}
+
+__global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + B_OFF_BAR);   // [2]
+  uint64_t* bar_s = bar_load + 2;     // [2]
+  uint64_t* bar_p = bar_s + 2;        // [2] count 256
+  uint64_t* bar_dp = bar_p + 2;       // [2]
+  uint64_t* bar_ds = bar_dp + 2;      // [2] count 256
+  uint64_t* bar_dq = bar_ds + 2;      // [2]
+  uint64_t* bar_kv = bar_dq + 2;      // [2] all MMAs of the tile retired
+  uint64_t* bar_free = bar_kv + 2;    // [1] count 256: tile-0 buffers and TMEM[0,208) reusable
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_free + 1);
+  const int h = blockIdx.x, b = blockIdx.y, g = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int t = 0; t < 2; ++t) {
+        ptx::mbar_init(&bar_load[t], 1); ptx::mbar_init(&bar_s[t], 1); ptx::mbar_init(&bar_p[t], 256);
+        ptx::mbar_init(&bar_dp[t], 1); ptx::mbar_init(&bar_ds[t], 256); ptx::mbar_init(&bar_dq[t], 1);
+        ptx::mbar_init(&bar_kv[t], 1);
+      }
+      ptx::mbar_init(bar_free, 256);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_ptr, 512);
+    ptx::tmem_relinquish();
+  } else {
+    // zero the never-written part of the 4th key block (keys 208..255) of P and dS: it is read as
+    // garbage rows of the transposed A operand otherwise (harmless, but keep NaNs out of TMEM)
+    for (int i = threadIdx.x - 32; i < QT * 6; i += B_THREADS - 32) {
+      const int r = i / 6, c = 2 + i % 6;
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(smem + B_OFF_P + 3 * (QT * 128) + r * 128 + ((c ^ (r & 7)) << 4)) = z;
+      *reinterpret_cast<uint4*>(smem + B_OFF_DS + 3 * (QT * 128) + r * 128 + ((c ^ (r & 7)) << 4)) = z;
+    }
+    ptx::fence_proxy_async();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t sq = ptx::smem_u32(smem + B_OFF_Q), sdo = ptx::smem_u32(smem + B_OFF_DO);
+      const uint32_t sk = ptx::smem_u32(smem + B_OFF_K), sv = ptx::smem_u32(smem + B_OFF_V);
+      const uint32_t sp = ptx::smem_u32(smem + B_OFF_P), sds = ptx::smem_u32(smem + B_OFF_DS);
+      const uint32_t idesc_s = ptx::make_idesc_bf16(QT, KPAD, 0, 0);
+      const uint32_t idesc_dq = ptx::make_idesc_bf16(QT, DH, 0, 1);
+      const uint32_t idesc_kv = ptx::make_idesc_bf16(QT, DH, 1, 1);
+      for (int t = 0; t < 2; ++t) {
+        if (t == 1) {
+          ptx::mbar_wait(&bar_kv[0], 0, p.err_flag, 21);     // tile-0 MMAs no longer read Q/dO/P/dS
+          ptx::mbar_wait(bar_free, 0, p.err_flag, 22);       // dQ_0 drained, staging store done
+        }
+        ptx::mbar_arrive_expect_tx(&bar_load[t], 2 * Q_TILE_BYTES + (t == 0 ? 2 * KV_TILE_BYTES : 0));
+        ptx::tma_load_3d(smem + B_OFF_Q, &p.tmQ[g], &bar_load[t], h * DH, t * QT, b);
+        ptx::tma_load_3d(smem + B_OFF_DO, &p.tmDO[g], &bar_load[t], h * DH, t * QT, b);
+        if (t == 0) {
+          ptx::tma_load_3d(smem + B_OFF_K, &p.tmKV[g], &bar_load[t], D + h * DH, 0, b);
+          ptx::tma_load_3d(smem + B_OFF_V, &p.tmKV[g], &bar_load[t], 2 * D + h * DH, 0, b);
+        }
+        ptx::mbar_wait(&bar_load[t], 0, p.err_flag, 23);
+        ptx::tc_fence_after();
+        // S = Q_t K^T
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          ptx::umma_bf16(tmem_base, ptx::make_smem_desc(sq + k * 32, 16, 1024),
+                         ptx::make_smem_desc(sk + k * 32, 16, 1024), idesc_s, k > 0);
+        ptx::umma_commit(&bar_s[t]);
+        // P ready → dP = dO_t V^T (over S's columns) and dV += P^T dO_t
+        ptx::mbar_wait(&bar_p[t], 0, p.err_flag, 24);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          ptx::umma_bf16(tmem_base, ptx::make_smem_desc(sdo + k * 32, 16, 1024),
+                         ptx::make_smem_desc(sv + k * 32, 16, 1024), idesc_s, k > 0);
+        ptx::umma_commit(&bar_dp[t]);
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int k = 0; k < QT / 16; ++k)
+            ptx::umma_bf16(tmem_base + TM_DV + mt * DH,
+                           ptx::make_smem_desc(sp + 2 * mt * (QT * 128) + k * 2048, QT * 128, 1024),
+                           ptx::make_smem_desc(sdo + k * 2048, 8192, 1024), idesc_kv, (t > 0 || k > 0));
+        // dS ready → dQ_t = dS K (over dP's columns) and dK += dS^T Q_t
+        ptx::mbar_wait(&bar_ds[t], 0, p.err_flag, 25);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < KPAD / 16; ++j)
+          ptx::umma_bf16(tmem_base, ptx::make_smem_desc(sds + (j >> 2) * (QT * 128) + (j & 3) * 32, 16, 1024),
+                         ptx::make_smem_desc(sk + j * 2048, 8192, 1024), idesc_dq, j > 0);
+        ptx::umma_commit(&bar_dq[t]);
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int k = 0; k < QT / 16; ++k)
+            ptx::umma_bf16(tmem_base + TM_DK + mt * DH,
+                           ptx::make_smem_desc(sds + 2 * mt * (QT * 128) + k * 2048, QT * 128, 1024),
+                           ptx::make_smem_desc(sq + k * 2048, 8192, 1024), idesc_kv, (t > 0 || k > 0));
+        ptx::umma_commit(&bar_kv[t]);
+      }
+    }
+  } else {
+    const int q = warp & 3;                      // TMEM lane quarter
+    const int half = (warp - 1) >> 2;            // column half: 0 → keys [0,112), 1 → keys [112,208)
+    const int row = q * 32 + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint8_t* ptile = smem + B_OFF_P;
+    uint8_t* dstile = smem + B_OFF_DS;
+    const int col0 = half ? 112 : 0;
+    uint32_t r[32];
+    for (int t = 0; t < 2; ++t) {
+      const int qrow = t * QT + row;
+      const bool valid = qrow < NT;
+      const float lse2 = valid ? p.lse[g][((int64_t)b * NH + h) * NT + qrow] * LOG2E : 0.f;
+      // ---- P = exp(S/8 - lse) ----
+      ptx::mbar_wait(&bar_s[t], 0, p.err_flag, 26);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 3; ++c) {
+        ptx::tmem_ld_32x32(tlane + col0 + c * 32, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int key = col0 + c * 32 + j * 8 + i;
+            e[i] = (valid && key < NT) ? ptx::ex2_approx(fmaf(__uint_as_float(r[8 * j + i]), SCALE_LOG2E, -lse2)) : 0.f;
+          }
+          uint4 v;
+          v.x = pack2(e[0], e[1]); v.y = pack2(e[2], e[3]); v.z = pack2(e[4], e[5]); v.w = pack2(e[6], e[7]);
+          store_p_chunk(ptile, row, (col0 + c * 32) / 8 + j, v);
+        }
+      }
+      if (half == 0) {      // keys 96..111
+        ptx::tmem_ld_32x16(tlane + 96, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            e[i] = valid ? ptx::ex2_approx(fmaf(__uint_as_float(r[8 * j + i]), SCALE_LOG2E, -lse2)) : 0.f;
+          uint4 v;
+          v.x = pack2(e[0], e[1]); v.y = pack2(e[2], e[3]); v.z = pack2(e[4], e[5]); v.w = pack2(e[6], e[7]);
+          store_p_chunk(ptile, row, 12 + j, v);
+        }
+      }
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bar_p[t]);
+      // ---- D = rowsum(dO * O) (both halves compute it; dO from smem, O from global) ----
+      float Dr = 0.f;
+      if (valid) {
+        const uint4* orow = reinterpret_cast<const uint4*>(p.ctx[g] + ((int64_t)b * NT + qrow) * D + h * DH);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 ov = __ldg(orow + c);
+          const uint4 dv = *reinterpret_cast<const uint4*>(smem + B_OFF_DO + row * 128 + ((c ^ (row & 7)) << 4));
+          const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 o2 = *reinterpret_cast<const __nv_bfloat162*>(&ow[e]);
+            const __nv_bfloat162 d2 = *reinterpret_cast<const __nv_bfloat162*>(&dw[e]);
+            Dr = fmaf(__low2float(o2), __low2float(d2), Dr);
+            Dr = fmaf(__high2float(o2), __high2float(d2), Dr);
+          }
+        }
+      }
+      // ---- dS = P * (dP - D) / 8 ----
+      ptx::mbar_wait(&bar_dp[t], 0, p.err_flag, 27);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 3; ++c) {
+        ptx::tmem_ld_32x32(tlane + col0 + c * 32, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c8 = (col0 + c * 32) / 8 + j;
+          const uint4 pv = load_p_chunk(ptile, row, c8);
+          const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+          float d[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 p2 = *reinterpret_cast<const __nv_bfloat162*>(&pw[e]);
+            d[2 * e] = __low2float(p2) * (__uint_as_float(r[8 * j + 2 * e]) - Dr) * SCALE;
+            d[2 * e + 1] = __high2float(p2) * (__uint_as_float(r[8 * j + 2 * e + 1]) - Dr) * SCALE;
+          }
+          uint4 v;
+          v.x = pack2(d[0], d[1]); v.y = pack2(d[2], d[3]); v.z = pack2(d[4], d[5]); v.w = pack2(d[6], d[7]);
+          store_p_chunk(dstile, row, c8, v);
+        }
+      }
+      if (half == 0) {
+        ptx::tmem_ld_32x16(tlane + 96, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint4 pv = load_p_chunk(ptile, row, 12 + j);
+          const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+          float d[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 p2 = *reinterpret_cast<const __nv_bfloat162*>(&pw[e]);
+            d[2 * e] = __low2float(p2) * (__uint_as_float(r[8 * j + 2 * e]) - Dr) * SCALE;
+            d[2 * e + 1] = __high2float(p2) * (__uint_as_float(r[8 * j + 2 * e + 1]) - Dr) * SCALE;
+          }
+          uint4 v;
+          v.x = pack2(d[0], d[1]); v.y = pack2(d[2], d[3]); v.z = pack2(d[4], d[5]); v.w = pack2(d[6], d[7]);
+          store_p_chunk(dstile, row, 12 + j, v);
+        }
+      }
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bar_ds[t]);
+      // ---- dQ_t: TMEM [0,64) → bf16 → (after the tile's MMAs retired) staged in the Q buffer → TMA store ----
+      ptx::mbar_wait(&bar_dq[t], 0, p.err_flag, 28);
+      ptx::tc_fence_after();
+      ptx::tmem_ld_32x32(tlane + half * 32, r);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_wait(&bar_kv[t], 0, p.err_flag, 29);      // Q_t no longer read by the dK MMAs
+      uint8_t* stg = smem + B_OFF_Q;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 v;
+        v.x = pack2(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]));
+        v.y = pack2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+        v.z = pack2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+        v.w = pack2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+        *reinterpret_cast<uint4*>(stg + row * 128 + (((half * 4 + j) ^ (row & 7)) << 4)) = v;
+      }
+      ptx::fence_proxy_async();
+      ptx::bar_sync(1, 256);
+      if (threadIdx.x == 32) {
+        ptx::tma_store_3d(&p.tmDQKV[g], stg, h * DH, t * QT, b);
+        ptx::tma_commit_group();
+        ptx::tma_wait_group_read<0>();
+      }
+      if (t == 0) ptx::mbar_arrive(bar_free);
+    }
+    // ---- dK, dV: TMEM → bf16 → staged in the P buffer → TMA store (rows = keys) ----
+    // bar_kv[1] was waited above: every MMA has retired
+    ptx::tc_fence_after();
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {          // 0: dK, 1: dV
+#pragma unroll 1
+      for (int mt = 0; mt < 2; ++mt) {
+        ptx::tmem_ld_32x32(tlane + (which ? TM_DV : TM_DK) + mt * DH + half * 32, r);
+        ptx::tmem_ld_wait();
+        uint8_t* stg = smem + B_OFF_P + (which * 2 + mt) * Q_TILE_BYTES;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 v;
+          v.x = pack2(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]));
+          v.y = pack2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+          v.z = pack2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+          v.w = pack2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+          *reinterpret_cast<uint4*>(stg + row * 128 + (((half * 4 + j) ^ (row & 7)) << 4)) = v;
+        }
+      }
+    }
+    ptx::fence_proxy_async();
+    ptx::bar_sync(1, 256);
+    if (threadIdx.x == 32) {
+      for (int which = 0; which < 2; ++which)
+        for (int mt = 0; mt < 2; ++mt)
+          ptx::tma_store_3d(&p.tmDQKV[g], smem + B_OFF_P + (which * 2 + mt) * Q_TILE_BYTES,
+                            (1 + which) * D + h * DH, mt * QT, b);
+      ptx::tma_commit_group();
+      ptx::tma_wait_group<0>();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+int launch_attn_fwd_tc(const void* const* qkv, void* const* ctx, float* const* lse, int groups, int B,
+                       cudaStream_t s) {
+  AttnFwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.err_flag = tc_err_flag();
+  for (int g = 0; g < groups; ++g) {
+    V2S_TRY(tmap_get_3d(&p.tmQ[g], qkv[g], 3 * D, NT, B, 3 * D * 2, (uint64_t)NT * 3 * D * 2, DH, QT, true, 128));
+    V2S_TRY(tmap_get_3d(&p.tmKV[g], qkv[g], 3 * D, NT, B, 3 * D * 2, (uint64_t)NT * 3 * D * 2, DH, KPAD, true, 128));
+    V2S_TRY(tmap_get_3d(&p.tmCtx[g], ctx[g], D, NT, B, D * 2, (uint64_t)NT * D * 2, DH, QT, true, 128));
+    p.lse[g] = lse ? lse[g] : nullptr;
+  }
+  static bool attr = false;
+  if (!attr) {
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+    attr = true;
+  }
+  attn_fwd_tc_kernel<<<dim3(NH, B, groups), F_THREADS, F_SMEM, s>>>(p);
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace v2s
+
+namespace v2s {
+
+int launch_attn_bwd_tc(const void* const* qkv, const void* const* ctx, const float* const* lse,
+                       const void* const* dctx, void* const* dqkv, int groups, int B, cudaStream_t s) {
+  AttnBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.err_flag = tc_err_flag();
+  for (int g = 0; g < groups; ++g) {
+    V2S_TRY(tmap_get_3d(&p.tmQ[g], qkv[g], 3 * D, NT, B, 3 * D * 2, (uint64_t)NT * 3 * D * 2, DH, QT, true, 128));
+    V2S_TRY(tmap_get_3d(&p.tmKV[g], qkv[g], 3 * D, NT, B, 3 * D * 2, (uint64_t)NT * 3 * D * 2, DH, KPAD, true, 128));
+    V2S_TRY(tmap_get_3d(&p.tmDO[g], dctx[g], D, NT, B, D * 2, (uint64_t)NT * D * 2, DH, QT, true, 128));
+    V2S_TRY(tmap_get_3d(&p.tmDQKV[g], dqkv[g], 3 * D, NT, B, 3 * D * 2, (uint64_t)NT * 3 * D * 2, DH, QT, true, 128));
+    p.ctx[g] = static_cast<const bf16*>(ctx[g]);
+    p.lse[g] = lse[g];
+  }
+  static bool attr = false;
+  if (!attr) {
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+    attr = true;
+  }
+  attn_bwd_tc_kernel<<<dim3(NH, B, groups), B_THREADS, B_SMEM, s>>>(p);
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace v2s

@@ -180,11 +180,13 @@ inline const void* weight_ptr(const v2s_group_t& g, int at, int64_t off) {
 int launch_attention_fwd(const void* const* qkv, void* const* ctx, float* const* lse, int groups, int B, int at,
                          cudaStream_t s) {
   prof::Scope scope(prof::C_ATTN_F, 4.0 * B * NH * (double)NT * NT * DH * groups, s);
+  if (at == 1 && tc_enabled()) return launch_attn_fwd_tc(qkv, ctx, lse, groups, B, s);
   return launch_attn_fwd_simt(qkv, ctx, lse, groups, B, at, s);
 }
 int launch_attention_bwd(const void* const* qkv, const void* const* ctx, const float* const* lse,
                          const void* const* dctx, void* const* dqkv, int groups, int B, int at, cudaStream_t s) {
   prof::Scope scope(prof::C_ATTN_B, 8.0 * B * NH * (double)NT * NT * DH * groups, s);
+  if (at == 1 && tc_enabled()) return launch_attn_bwd_tc(qkv, ctx, lse, dctx, dqkv, groups, B, s);
   return launch_attn_bwd_simt(qkv, ctx, lse, dctx, dqkv, groups, B, at, s);
 }
 
@@ -756,6 +758,25 @@ int v2s_prof_report(char* host_buf, int64_t buf_bytes) {
   }
   prof::n_recs = 0;
   return 0;
+}
+
+// test hook: which = 0 forward (qkv -> ctx, lse), 1 backward (qkv, ctx, lse, dctx -> dqkv);
+// variant 0 = tensor-core kernels, 1 = SIMT reference kernels; bf16 tensors, one backbone
+int v2s_test_attention(int which, const void* qkv, void* ctx, float* lse, const void* dctx, void* dqkv, int batch,
+                       int variant, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const void* cq[1] = {qkv}; void* cc[1] = {ctx}; float* ls[1] = {lse};
+  const void* cctx[1] = {ctx}; const float* cls[1] = {lse}; const void* cd[1] = {dctx}; void* dq[1] = {dqkv};
+  if (which == 0) {
+    if (variant == 1) return launch_attn_fwd_simt(cq, cc, ls, 1, batch, 1, st);
+    return launch_attn_fwd_tc(cq, cc, ls, 1, batch, st);
+  }
+  if (which == 1) {
+    if (variant == 1) return launch_attn_bwd_simt(cq, cctx, cls, cd, dq, 1, batch, 1, st);
+    return launch_attn_bwd_tc(cq, cctx, cls, cd, dq, 1, batch, st);
+  }
+  set_error("v2s_test_attention: which must be 0 or 1");
+  return 1;
 }
 
 int v2s_debug_flag(void) { return gemm_tc_error_flag(); }

@@ -373,6 +373,43 @@ int get_map(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_
   return 0;
 }
 
+}  // namespace
+
+// rank-3 variant used by the attention kernels: tensor [d2][d1][d0] with byte strides s1, s2
+int tmap_get_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
+                uint64_t s2_bytes, uint32_t b0, uint32_t b1, bool is_bf16, int swizzle_bytes) {
+  if (!g_encode) { set_error("tensor maps not initialised (v2s_init)"); return 1; }
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.d0 = d0; key.d1 = d1 | (d2 << 32); key.stride1 = s1_bytes ^ (s2_bytes << 20); key.b0 = b0; key.b1 = b1;
+  key.dtype = (is_bf16 ? 1 : 0) | 0x100; key.swz = (uint32_t)swizzle_bytes;
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = it->second; return 0; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (s1_bytes & 15) || (s2_bytes & 15)) {
+    set_error("tmap_get_3d: tensor %p not 16-byte aligned for TMA", ptr);
+    return 1;
+  }
+  cuuint64_t gdim[3] = {d0, d1, d2};
+  cuuint64_t gstride[2] = {s1_bytes, s2_bytes};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle swz = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUtensorMap m;
+  CUresult r = g_encode(&m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                        const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(3d) failed (%d)", (int)r); return 1; }
+  if (g_maps.size() > 8192) g_maps.clear();
+  g_maps.emplace(key, m);
+  *out = m;
+  return 0;
+}
+int* tc_err_flag() { return g_err_flag; }
+bool tc_enabled() { return g_encode != nullptr && !g_disabled; }
+
+namespace {
+
 template <int EPI, bool OUT_BF16>
 int launch_kernel(const TcParams& p, cudaStream_t stream) {
   static bool attr_set = false;

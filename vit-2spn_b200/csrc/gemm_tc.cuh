@@ -1,5 +1,7 @@
 // tcgen05 / TMEM / TMA tensor-core GEMM family (bf16 operands, fp32 accumulate) — sm_100a only.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 #include "gemm_simt.cuh"
 
@@ -10,6 +12,11 @@ int gemm_tc_init();
 // tries to run `d` on the tensor-core path; *handled = 1 if it did (0: caller falls back to SIMT,
 // only ever taken for shapes/types the tcgen05 kernels do not cover, e.g. fp32 check mode)
 int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t stream, int* handled);
+// shared with the attention kernels: cached rank-3 tensor map, error flag, availability
+int tmap_get_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
+                uint64_t s2_bytes, uint32_t b0, uint32_t b1, bool is_bf16, int swizzle_bytes);
+int* tc_err_flag();
+bool tc_enabled();
 // reads and clears the device-side protocol error flag (0 = none); synchronises
 int gemm_tc_error_flag();
 // test hook behind v2s_test_gemm

@@ -31,6 +31,13 @@ int launch_attn_bwd_simt(const void* const* qkv, const void* const* ctx, const f
                          const void* const* dctx, void* const* dqkv, int groups, int B, int at,
                          cudaStream_t s);
 
+// tcgen05 versions (bf16 only)
+int launch_attn_fwd_tc(const void* const* qkv, void* const* ctx, float* const* lse, int groups, int B,
+                       cudaStream_t s);
+
+int launch_attn_bwd_tc(const void* const* qkv, const void* const* ctx, const float* const* lse,
+                       const void* const* dctx, void* const* dqkv, int groups, int B, cudaStream_t s);
+
 int launch_cosine_loss(const float* p, const float* z, float* loss, float* dp, int B, int accum,
                        float grad_scale, cudaStream_t s);
 int launch_adam(const v2s_range_t* ranges, int n, int64_t step, double lr, double b1, double b2, double eps,
