@@ -193,14 +193,14 @@ def patch_embed(p, x):
 
 
 def layer_norm(x, w, b):
-    mu = x.mean(dim=-1, keepdim=True)
-    var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)      # biased variance, as torch LayerNorm
-    return (x - mu) * torch.rsqrt(var + LN_EPS) * w + b
+    """nn.LayerNorm(192, eps=1e-12) (HF:325-326): biased variance.  Stated through F.layer_norm so
+    that the oracle can also be run under torch.autocast (bf16 parity oracle)."""
+    return F.layer_norm(x, (HIDDEN,), w, b, LN_EPS)
 
 
 def gelu_erf(x):
-    """HF ``hidden_act='gelu'`` → exact erf GELU (HF:297-298)."""
-    return 0.5 * x * (1.0 + torch.erf(x * (1.0 / math.sqrt(2.0))))
+    """HF ``hidden_act='gelu'`` → exact erf GELU 0.5 x (1 + erf(x / sqrt 2)) (HF:297-298)."""
+    return F.gelu(x)
 
 
 def attention(q, k, v):

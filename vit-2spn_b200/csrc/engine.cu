@@ -243,19 +243,24 @@ static int backbone_forward_impl(const v2s_group_t* gs, int G, int B, int mode, 
     GemmDesc d = make_gemm_desc();
     d.M = (int)MP; d.N = D; d.K = KPE; d.groups = G;
     d.a_rs = KPE; d.a_cs = 1; d.b_rs = 1; d.b_cs = KPE;
-    d.epi = EPI_PATCH; d.ldc = D;
-    const float* pp[MAXG];
+    d.ldc = D;
+    const float* pp[MAXG]; const float* tok[MAXG];
+    const bool two_pass = at == 1 && tc_enabled();   // tensor-core GEMM into patch rows, then assemble tokens
+    d.epi = two_pass ? EPI_STORE : EPI_PATCH;
     for (int g = 0; g < G; ++g) {
       x_cur[g] = reinterpret_cast<float*>(saved(g) ? sb(g, p.s_x[0]) : fb(g, p.f_xa));
+      // scratch for the [B*196,192] patch rows: the x_mid buffer of block 0 (written later)
+      float* tmp = reinterpret_cast<float*>(saved(g) ? sb(g, p.s_layer[0].x_mid) : fb(g, p.f_xb));
       d.A[g] = patches[g];
       d.B[g] = weight_ptr(gs[g], at, OFF_WPE);
       d.bias[g] = gs[g].params + OFF_BPE;
       d.aux[g] = gs[g].params + OFF_POS;
-      d.out[g] = x_cur[g];
-      pp[g] = gs[g].params;
+      d.out[g] = two_pass ? tmp : x_cur[g];
+      pp[g] = gs[g].params; tok[g] = tmp;
     }
     V2S_TRY(run_gemm(d, at, at, 0, st, prof::C_PATCH));
-    V2S_TRY(launch_cls_rows(pp, x_cur, G, B, st));
+    if (two_pass) V2S_TRY(launch_assemble_tokens(pp, tok, x_cur, G, B, st));
+    else V2S_TRY(launch_cls_rows(pp, x_cur, G, B, st));
   }
 
   // ---- 12 pre-LN blocks ----
@@ -473,7 +478,18 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
     const float* cdx[MAXG]; float* gr[MAXG]; void* pt[MAXG];
     for (int g = 0; g < G; ++g) { cdx[g] = dx[g]; gr[g] = gs[g].grads; pt[g] = sb(g, p.s_patches); }
     V2S_TRY(launch_embed_bwd(cdx, gr, G, B, st));
-    V2S_TRY(wgrad(dxlp, D, pt, KPE, OFF_WPE, true));
+    if (at == 1 && tc_enabled()) {          // compact the patch rows, then the ordinary tensor-core wgrad
+      const void* src[MAXG];
+      for (int g = 0; g < G; ++g) src[g] = dxlp[g];
+      V2S_TRY(launch_gather_patch_rows(src, tmp, G, B, at, st));
+      GemmDesc d = make_gemm_desc();
+      d.M = D; d.N = KPE; d.K = (int)MP; d.groups = G;
+      d.a_rs = 1; d.a_cs = D; d.b_rs = KPE; d.b_cs = 1; d.epi = EPI_ACCUM; d.ldc = KPE; d.split_k = split;
+      for (int g = 0; g < G; ++g) { d.A[g] = tmp[g]; d.B[g] = pt[g]; d.out[g] = gs[g].grads + OFF_WPE; }
+      V2S_TRY(run_gemm(d, at, at, 0, st, prof::C_WGRAD));
+    } else {
+      V2S_TRY(wgrad(dxlp, D, pt, KPE, OFF_WPE, true));
+    }
   }
   return 0;
 }

@@ -45,6 +45,22 @@ __global__ void cls_rows_kernel(G4<const float*> params, G4<float*> hidden) {
   hidden.p[g][(int64_t)b * NT * D + n] = p[OFF_CLS + n] + p[OFF_POS + n];
 }
 
+// hidden[b,0,:] = cls + pos[0];  hidden[b,1+p,:] = tok[b*196+p,:] + pos[1+p]   (HF:117-124)
+__global__ void assemble_tokens_kernel(G4<const float*> params, G4<const float*> tok, G4<float*> hidden) {
+  const int g = blockIdx.z, b = blockIdx.y, t = blockIdx.x, n = threadIdx.x;
+  const float* p = params.p[g];
+  const float pos = p[OFF_POS + (int64_t)t * D + n];
+  const float v = (t == 0) ? p[OFF_CLS + n] : tok.p[g][((int64_t)b * NP + t - 1) * D + n];
+  hidden.p[g][((int64_t)b * NT + t) * D + n] = v + pos;
+}
+
+// compact the patch-token rows of a [B,197,192] tensor into [B*196,192] (drops the CLS rows)
+template <typename T>
+__global__ void gather_patch_rows_kernel(G4<const T*> src, G4<T*> dst) {
+  const int g = blockIdx.z, b = blockIdx.y, pi = blockIdx.x, n = threadIdx.x;
+  dst.p[g][((int64_t)b * NP + pi) * D + n] = src.p[g][((int64_t)b * NT + 1 + pi) * D + n];
+}
+
 // ------------------------------------------------------------------------------------------
 // LayerNorm over D=192 (eps 1e-12): one warp per row, 6 elements per lane as 3 float2
 // ------------------------------------------------------------------------------------------
@@ -540,6 +556,22 @@ int launch_im2col(const float* const* x, void* const* out, int groups, int B, in
 
 int launch_cls_rows(const float* const* params, float* const* hidden, int groups, int B, cudaStream_t s) {
   cls_rows_kernel<<<dim3(B, groups), D, 0, s>>>(pack4<const float*>(params, groups), pack4<float*>(hidden, groups));
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_assemble_tokens(const float* const* params, const float* const* tok, float* const* hidden, int groups,
+                           int B, cudaStream_t s) {
+  assemble_tokens_kernel<<<dim3(NT, B, groups), D, 0, s>>>(pack4<const float*>(params, groups),
+                                                          pack4<const float*>(tok, groups), pack4<float*>(hidden, groups));
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_gather_patch_rows(const void* const* src, void* const* dst, int groups, int B, int at, cudaStream_t s) {
+  dim3 grid(NP, B, groups);
+  if (at == 0) gather_patch_rows_kernel<float><<<grid, D, 0, s>>>(pack4<const float*>(src, groups), pack4<float*>(dst, groups));
+  else gather_patch_rows_kernel<bf16><<<grid, D, 0, s>>>(pack4<const bf16*>(src, groups), pack4<bf16*>(dst, groups));
   V2S_LAUNCH_CHECK();
   return 0;
 }

@@ -8,6 +8,9 @@ namespace v2s {
 // type tag: 0 = fp32 activations, 1 = bf16 activations
 int launch_im2col(const float* const* x, void* const* out, int groups, int B, int at, cudaStream_t s);
 int launch_cls_rows(const float* const* params, float* const* hidden, int groups, int B, cudaStream_t s);
+int launch_assemble_tokens(const float* const* params, const float* const* tok, float* const* hidden, int groups,
+                           int B, cudaStream_t s);
+int launch_gather_patch_rows(const void* const* src, void* const* dst, int groups, int B, int at, cudaStream_t s);
 int launch_ln_fwd(const float* const* x, const float* const* gamma, const float* const* beta,
                   void* const* y, float* const* mean, float* const* rstd, int groups, int M, int at,
                   cudaStream_t s);
