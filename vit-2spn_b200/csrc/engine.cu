@@ -433,25 +433,25 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
     }
     // ---- MLP ----
     V2S_TRY(wgrad(dxlp, D, h, DF, lo + L_W2, false));                      // dW2 [192,768]
-    V2S_TRY(bias_grad(dxlp, D, lo + L_B2));
+    if (l == NL - 1) V2S_TRY(bias_grad(dxlp, D, lo + L_B2));               // lower blocks: fused into LN1-bwd above
     V2S_TRY(dgrad(dxlp, D, lo + L_W2, DF, big, EPI_DGELU, u));             // du = (dx W2) * gelu'(u)
     V2S_TRY(wgrad(big, DF, xn2, D, lo + L_W1, false));                     // dW1 [768,192]
     V2S_TRY(bias_grad(big, DF, lo + L_B1));
     V2S_TRY(dgrad(big, DF, lo + L_W1, D, tmp, EPI_STORE, nullptr));        // d xn2
     {
       const void* dy[MAXG]; const float *x[MAXG], *mu[MAXG], *rs[MAXG], *gm[MAXG];
-      float *dg[MAXG], *db[MAXG]; void* lp[MAXG];
+      float *dg[MAXG], *db[MAXG], *cs[MAXG]; void* lp[MAXG];
       for (int g = 0; g < G; ++g) {
         dy[g] = tmp[g]; x[g] = (const float*)sb(g, s.x_mid); mu[g] = (const float*)sb(g, s.mean2);
         rs[g] = (const float*)sb(g, s.rstd2); gm[g] = gs[g].params + lo + L_LN2W;
         dg[g] = gs[g].grads + lo + L_LN2W; db[g] = gs[g].grads + lo + L_LN2B; lp[g] = at ? dxlp[g] : nullptr;
+        cs[g] = gs[g].grads + lo + L_BO;          // d b_o = column sums of the gradient w.r.t. x_mid
       }
       { prof::Scope sc(prof::C_LN_B, (double)M * D * (12 + 2 * p.es) * G, st);
-        V2S_TRY(launch_ln_bwd(dy, x, mu, rs, gm, dx, lp, dg, db, G, (int)M, at, st)); }
+        V2S_TRY(launch_ln_bwd(dy, x, mu, rs, gm, dx, lp, dg, db, cs, G, (int)M, at, st)); }
     }
     // ---- attention ----
-    V2S_TRY(wgrad(dxlp, D, ctx, D, lo + L_WO, false));                     // dWo
-    V2S_TRY(bias_grad(dxlp, D, lo + L_BO));
+    V2S_TRY(wgrad(dxlp, D, ctx, D, lo + L_WO, false));                     // dWo (d b_o: fused into LN2-bwd)
     V2S_TRY(dgrad(dxlp, D, lo + L_WO, D, tmp, EPI_STORE, nullptr));        // d ctx
     {
       const void *cq[MAXG], *cc[MAXG], *cd[MAXG]; const float* ls[MAXG];
@@ -463,14 +463,16 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
     V2S_TRY(dgrad(big, 3 * D, lo + L_WQKV, D, tmp, EPI_STORE, nullptr));   // d xn1
     {
       const void* dy[MAXG]; const float *x[MAXG], *mu[MAXG], *rs[MAXG], *gm[MAXG];
-      float *dg[MAXG], *db[MAXG]; void* lp[MAXG];
+      float *dg[MAXG], *db[MAXG], *cs[MAXG]; void* lp[MAXG];
       for (int g = 0; g < G; ++g) {
         dy[g] = tmp[g]; x[g] = (const float*)sb(g, p.s_x[l]); mu[g] = (const float*)sb(g, s.mean1);
         rs[g] = (const float*)sb(g, s.rstd1); gm[g] = gs[g].params + lo + L_LN1W;
         dg[g] = gs[g].grads + lo + L_LN1W; db[g] = gs[g].grads + lo + L_LN1B; lp[g] = at ? dxlp[g] : nullptr;
+        // d b_2 of the block below = column sums of the gradient w.r.t. this block's input
+        cs[g] = l > 0 ? gs[g].grads + layer_off(l - 1) + L_B2 : nullptr;
       }
       { prof::Scope sc(prof::C_LN_B, (double)M * D * (12 + 2 * p.es) * G, st);
-        V2S_TRY(launch_ln_bwd(dy, x, mu, rs, gm, dx, lp, dg, db, G, (int)M, at, st)); }
+        V2S_TRY(launch_ln_bwd(dy, x, mu, rs, gm, dx, lp, dg, db, cs, G, (int)M, at, st)); }
     }
   }
   // ---- embeddings: d pos, d cls, d patch bias, d patch weight ----

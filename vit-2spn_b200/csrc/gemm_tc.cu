@@ -57,8 +57,8 @@ struct alignas(64) TcParams {
 // resolution); shares exp(-x^2/2) between gelu and gelu'.
 __device__ __forceinline__ void gelu_core(float x, float& cdf, float& pdf_e) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  const float e = exp2f(-0.72134752044448170f * x * x);   // exp(-x^2/2)
+  const float t = ptx::rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  const float e = ptx::ex2_approx(-0.72134752044448170f * x * x);   // exp(-x^2/2)
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);

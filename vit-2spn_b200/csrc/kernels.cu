@@ -2,6 +2,8 @@
 // token mean-pool, embedding backward, cosine loss (+backward), Adam, EMA, casts, dropout mask,
 // synthetic input pipeline.  All are coalesced / vectorised HBM kernels with warp-shuffle
 // reductions; grouped kernels use blockIdx.y|z as the backbone index.
+#include <string.h>
+
 #include "kernels.cuh"
 
 namespace v2s {
@@ -62,122 +64,184 @@ __global__ void gather_patch_rows_kernel(G4<const T*> src, G4<T*> dst) {
 }
 
 // ------------------------------------------------------------------------------------------
-// LayerNorm over D=192 (eps 1e-12): one warp per row, 6 elements per lane as 3 float2
+// LayerNorm over D=192 (eps 1e-12).  Half a warp per row: 16 lanes x 3 float4 = 192 floats, so a
+// warp keeps two rows (6 x 128-bit loads per lane) in flight; reductions are 4 shuffle steps.
 // ------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) ln_fwd_kernel(G4<const float*> x, G4<const float*> gamma,
-                                                     G4<const float*> beta, G4<T*> y, G4<float*> mean,
-                                                     G4<float*> rstd, int M) {
-  const int g = blockIdx.y;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= M) return;
-  const float2* xr = reinterpret_cast<const float2*>(x.p[g] + (int64_t)row * D);
-  float2 v[3];
-  float s = 0.f;
+struct LnFwdP {
+  const float* x[MAXG]; const float* gamma[MAXG]; const float* beta[MAXG];
+  void* y[MAXG]; float* mean[MAXG]; float* rstd[MAXG];
+  int M;
+};
+
+// sum over the 16 lanes of a half-warp; `mask` names exactly those lanes (the two half-warps of a
+// warp own different rows and may leave the row loop at different iterations)
+__device__ __forceinline__ float hw_sum(float v, unsigned mask) {
 #pragma unroll
-  for (int i = 0; i < 3; ++i) { v[i] = xr[lane + 32 * i]; s += v[i].x + v[i].y; }
-  const float mu = warp_sum(s) * (1.0f / D);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) { const float a = v[i].x - mu, b = v[i].y - mu; q += a * a + b * b; }
-  const float var = warp_sum(q) * (1.0f / D);
-  const float rs = 1.0f / sqrtf(var + LN_EPS);
-  const float2* gm = reinterpret_cast<const float2*>(gamma.p[g]);
-  const float2* bt = reinterpret_cast<const float2*>(beta.p[g]);
-  T* yr = y.p[g] + (int64_t)row * D;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const int c = lane + 32 * i;
-    const float2 gg = gm[c], bb = bt[c];
-    yr[2 * c] = from_f<T>((v[i].x - mu) * rs * gg.x + bb.x);
-    yr[2 * c + 1] = from_f<T>((v[i].y - mu) * rs * gg.y + bb.y);
-  }
-  if (lane == 0 && mean.p[g]) { mean.p[g][row] = mu; rstd.p[g][row] = rs; }
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+
+template <typename T> __device__ __forceinline__ void store4(T* dst, float a, float b, float c, float d);
+template <> __device__ __forceinline__ void store4<float>(float* dst, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(dst) = make_float4(a, b, c, d);
+}
+template <> __device__ __forceinline__ void store4<bf16>(bf16* dst, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(dst) = u;
+}
+template <typename T> __device__ __forceinline__ float4 load4(const T* src);
+template <> __device__ __forceinline__ float4 load4<float>(const float* src) { return *reinterpret_cast<const float4*>(src); }
+template <> __device__ __forceinline__ float4 load4<bf16>(const bf16* src) {
+  const uint2 u = *reinterpret_cast<const uint2*>(src);
+  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  return make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(G4<const T*> dy, G4<const float*> x,
-                                                     G4<const float*> mean, G4<const float*> rstd,
-                                                     G4<const float*> gamma, G4<float*> dres,
-                                                     G4<T*> dres_lp, G4<float*> dgamma, G4<float*> dbeta,
-                                                     int M) {
-  __shared__ float red[8][2 * D];
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const __grid_constant__ LnFwdP p) {
   const int g = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float2* gm = reinterpret_cast<const float2*>(gamma.p[g]);
-  float2 gg[3];
+  const int hw = threadIdx.x >> 4, l = threadIdx.x & 15;
+  const unsigned hmask = 0xffffu << (16 * (hw & 1));
+  const float* __restrict__ x = p.x[g];
+  T* __restrict__ y = static_cast<T*>(p.y[g]);
+  float4 gm[3], bt[3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) gg[i] = gm[lane + 32 * i];
-  float2 ag[3], ab[3];
+  for (int i = 0; i < 3; ++i) {
+    gm[i] = reinterpret_cast<const float4*>(p.gamma[g])[l + 16 * i];
+    bt[i] = reinterpret_cast<const float4*>(p.beta[g])[l + 16 * i];
+  }
+  for (int row = blockIdx.x * 16 + hw; row < p.M; row += gridDim.x * 16) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * D);
+    float4 v[3];
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) { ag[i] = make_float2(0.f, 0.f); ab[i] = make_float2(0.f, 0.f); }
+    for (int i = 0; i < 3; ++i) { v[i] = xr[l + 16 * i]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+    const float mu = hw_sum(s, hmask) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rs = 1.0f / sqrtf(hw_sum(q, hmask) * (1.0f / D) + LN_EPS);
+    T* yr = y + (int64_t)row * D;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      store4<T>(yr + 4 * (l + 16 * i), (v[i].x - mu) * rs * gm[i].x + bt[i].x, (v[i].y - mu) * rs * gm[i].y + bt[i].y,
+                (v[i].z - mu) * rs * gm[i].z + bt[i].z, (v[i].w - mu) * rs * gm[i].w + bt[i].w);
+    if (l == 0 && p.mean[g]) { p.mean[g][row] = mu; p.rstd[g][row] = rs; }
+  }
+}
 
-  for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
-    const float mu = mean.p[g][row], rs = rstd.p[g][row];
-    const float2* xr = reinterpret_cast<const float2*>(x.p[g] + (int64_t)row * D);
-    const T* dyr = dy.p[g] + (int64_t)row * D;
-    float2 xh[3], gd[3];
+// dres (fp32, in/out) += LN-backward(dy);  dres_lp = updated dres in the activation type;
+// dgamma / dbeta / (optional) dcolsum[n] += sum over rows of the UPDATED dres (= bias gradient of the
+// linear layer that consumes this residual-stream gradient).
+struct LnBwdP {
+  const void* dy[MAXG]; const float* x[MAXG]; const float* mean[MAXG]; const float* rstd[MAXG];
+  const float* gamma[MAXG]; float* dres[MAXG]; void* dres_lp[MAXG]; float* dgamma[MAXG]; float* dbeta[MAXG];
+  float* dcolsum[MAXG];
+  int M;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const __grid_constant__ LnBwdP p) {
+  __shared__ float red[16][3 * D];          // 36 KB
+  const int g = blockIdx.y;
+  const int hw = threadIdx.x >> 4, l = threadIdx.x & 15;
+  const unsigned hmask = 0xffffu << (16 * (hw & 1));
+  const T* __restrict__ dy = static_cast<const T*>(p.dy[g]);
+  const float* __restrict__ x = p.x[g];
+  float* __restrict__ dres = p.dres[g];
+  T* __restrict__ dlp = static_cast<T*>(p.dres_lp[g]);
+  float4 gm[3], ag[3], ab[3], ac[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    gm[i] = reinterpret_cast<const float4*>(p.gamma[g])[l + 16 * i];
+    ag[i] = ab[i] = ac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int row = blockIdx.x * 16 + hw; row < p.M; row += gridDim.x * 16) {
+    const float mu = p.mean[g][row], rs = p.rstd[g][row];
+    const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * D);
+    float4 xh[3], gd[3], d[3], o[3];
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      const int c = lane + 32 * i;
-      const float2 xv = xr[c];
-      const float d0 = to_f<T>(dyr[2 * c]), d1 = to_f<T>(dyr[2 * c + 1]);
-      xh[i] = make_float2((xv.x - mu) * rs, (xv.y - mu) * rs);
-      gd[i] = make_float2(d0 * gg[i].x, d1 * gg[i].y);
-      c1 += gd[i].x + gd[i].y;
-      c2 += gd[i].x * xh[i].x + gd[i].y * xh[i].y;
-      ag[i].x += d0 * xh[i].x; ag[i].y += d1 * xh[i].y;
-      ab[i].x += d0; ab[i].y += d1;
+      const float4 xv = xr[l + 16 * i];
+      d[i] = load4<T>(dy + (int64_t)row * D + 4 * (l + 16 * i));
+      o[i] = reinterpret_cast<const float4*>(dres + (int64_t)row * D)[l + 16 * i];
+      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      gd[i] = make_float4(d[i].x * gm[i].x, d[i].y * gm[i].y, d[i].z * gm[i].z, d[i].w * gm[i].w);
+      c1 += (gd[i].x + gd[i].y) + (gd[i].z + gd[i].w);
+      c2 += (gd[i].x * xh[i].x + gd[i].y * xh[i].y) + (gd[i].z * xh[i].z + gd[i].w * xh[i].w);
+      ag[i].x += d[i].x * xh[i].x; ag[i].y += d[i].y * xh[i].y; ag[i].z += d[i].z * xh[i].z; ag[i].w += d[i].w * xh[i].w;
+      ab[i].x += d[i].x; ab[i].y += d[i].y; ab[i].z += d[i].z; ab[i].w += d[i].w;
     }
-    c1 = warp_sum(c1) * (1.0f / D);
-    c2 = warp_sum(c2) * (1.0f / D);
-    float2* dr = reinterpret_cast<float2*>(dres.p[g] + (int64_t)row * D);
-    T* dl = dres_lp.p[g] ? dres_lp.p[g] + (int64_t)row * D : nullptr;
+    c1 = hw_sum(c1, hmask) * (1.0f / D);
+    c2 = hw_sum(c2, hmask) * (1.0f / D);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      const int c = lane + 32 * i;
-      float2 o = dr[c];
-      o.x += rs * (gd[i].x - c1 - xh[i].x * c2);
-      o.y += rs * (gd[i].y - c1 - xh[i].y * c2);
-      dr[c] = o;
-      if (dl) { dl[2 * c] = from_f<T>(o.x); dl[2 * c + 1] = from_f<T>(o.y); }
+      o[i].x += rs * (gd[i].x - c1 - xh[i].x * c2); o[i].y += rs * (gd[i].y - c1 - xh[i].y * c2);
+      o[i].z += rs * (gd[i].z - c1 - xh[i].z * c2); o[i].w += rs * (gd[i].w - c1 - xh[i].w * c2);
+      reinterpret_cast<float4*>(dres + (int64_t)row * D)[l + 16 * i] = o[i];
+      if (dlp) store4<T>(dlp + (int64_t)row * D + 4 * (l + 16 * i), o[i].x, o[i].y, o[i].z, o[i].w);
+      ac[i].x += o[i].x; ac[i].y += o[i].y; ac[i].z += o[i].z; ac[i].w += o[i].w;
     }
   }
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    const int c = 2 * (lane + 32 * i);
-    red[warp][c] = ag[i].x; red[warp][c + 1] = ag[i].y;
-    red[warp][D + c] = ab[i].x; red[warp][D + c + 1] = ab[i].y;
+    const int c = 4 * (l + 16 * i);
+    *reinterpret_cast<float4*>(&red[hw][c]) = ag[i];
+    *reinterpret_cast<float4*>(&red[hw][D + c]) = ab[i];
+    *reinterpret_cast<float4*>(&red[hw][2 * D + c]) = ac[i];
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+  for (int c = threadIdx.x; c < 3 * D; c += blockDim.x) {
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[w][c];
-    if (c < D) atomicAdd(dgamma.p[g] + c, s); else atomicAdd(dbeta.p[g] + (c - D), s);
+    for (int w = 0; w < 16; ++w) s += red[w][c];
+    if (c < D) atomicAdd(p.dgamma[g] + c, s);
+    else if (c < 2 * D) atomicAdd(p.dbeta[g] + (c - D), s);
+    else if (p.dcolsum[g]) atomicAdd(p.dcolsum[g] + (c - 2 * D), s);
   }
 }
 
-// db[n] += sum_m dy[m,n]
+// db[n] += sum_m dy[m,n]   (N a multiple of 8; 8 contiguous columns per thread, 128-bit loads)
+struct ColsumP {
+  const void* dy[MAXG]; float* db[MAXG];
+  int M, N, rows_per_block;
+};
+
 template <typename T>
-__global__ void colsum_kernel(G4<const T*> dy, G4<float*> db, int M, int N, int rows_per_block) {
-  __shared__ float red[8][33];
-  const int g = blockIdx.z;
-  const int n = blockIdx.x * 32 + threadIdx.x;
-  const int r0 = blockIdx.y * rows_per_block;
-  const int r1 = min(M, r0 + rows_per_block);
-  float s = 0.f;
-  if (n < N)
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) s += to_f<T>(dy.p[g][(int64_t)r * N + n]);
-  red[threadIdx.y][threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.y == 0 && n < N) {
-    float t = 0.f;
+__global__ void __launch_bounds__(256) colsum_kernel(const __grid_constant__ ColsumP p) {
+  __shared__ float red[2048];
+  const int g = blockIdx.y;
+  const int cols_t = p.N / 8;
+  int rows_t = 256 / cols_t;
+  if (rows_t * p.N > 2048) rows_t = 2048 / p.N;
+  const int ct = threadIdx.x % cols_t, rt = threadIdx.x / cols_t;
+  const T* __restrict__ dy = static_cast<const T*>(p.dy[g]);
+  float acc[8];
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
-    atomicAdd(db.p[g] + n, t);
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const int r0 = blockIdx.x * p.rows_per_block;
+  const int r1 = min(p.M, r0 + p.rows_per_block);
+  if (rt < rows_t) {
+    for (int r = r0 + rt; r < r1; r += rows_t) {
+      const T* src = dy + (int64_t)r * p.N + ct * 8;
+      const float4 a = load4<T>(src), b = load4<T>(src + 4);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[rt * p.N + ct * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < p.N; n += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < rows_t; ++w) s += red[w * p.N + n];
+    atomicAdd(p.db[g] + n, s);
   }
 }
 
@@ -578,49 +642,57 @@ int launch_gather_patch_rows(const void* const* src, void* const* dst, int group
 
 int launch_ln_fwd(const float* const* x, const float* const* gamma, const float* const* beta, void* const* y,
                   float* const* mean, float* const* rstd, int groups, int M, int at, cudaStream_t s) {
-  dim3 grid((M + 7) / 8, groups);
-  if (at == 0)
-    ln_fwd_kernel<float><<<grid, 256, 0, s>>>(pack4<const float*>(x, groups), pack4<const float*>(gamma, groups),
-                                              pack4<const float*>(beta, groups), pack4<float*>(y, groups),
-                                              pack4<float*>(mean, groups), pack4<float*>(rstd, groups), M);
-  else
-    ln_fwd_kernel<bf16><<<grid, 256, 0, s>>>(pack4<const float*>(x, groups), pack4<const float*>(gamma, groups),
-                                             pack4<const float*>(beta, groups), pack4<bf16*>(y, groups),
-                                             pack4<float*>(mean, groups), pack4<float*>(rstd, groups), M);
+  LnFwdP p;
+  memset(&p, 0, sizeof(p));
+  for (int g = 0; g < groups; ++g) {
+    p.x[g] = x[g]; p.gamma[g] = gamma[g]; p.beta[g] = beta[g]; p.y[g] = y[g];
+    p.mean[g] = mean ? mean[g] : nullptr; p.rstd[g] = rstd ? rstd[g] : nullptr;
+  }
+  p.M = M;
+  int bx = (M + 15) / 16;
+  if (bx > 148 * 6) bx = 148 * 6;
+  dim3 grid(bx, groups);
+  if (at == 0) ln_fwd_kernel<float><<<grid, 256, 0, s>>>(p);
+  else ln_fwd_kernel<bf16><<<grid, 256, 0, s>>>(p);
   V2S_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_ln_bwd(const void* const* dy, const float* const* x, const float* const* mean, const float* const* rstd,
                   const float* const* gamma, float* const* dres, void* const* dres_lp, float* const* dgamma,
-                  float* const* dbeta, int groups, int M, int at, cudaStream_t s) {
-  int bx = (M + 7) / 8;
+                  float* const* dbeta, float* const* dcolsum, int groups, int M, int at, cudaStream_t s) {
+  LnBwdP p;
+  memset(&p, 0, sizeof(p));
+  for (int g = 0; g < groups; ++g) {
+    p.dy[g] = dy[g]; p.x[g] = x[g]; p.mean[g] = mean[g]; p.rstd[g] = rstd[g]; p.gamma[g] = gamma[g];
+    p.dres[g] = dres[g]; p.dres_lp[g] = dres_lp ? dres_lp[g] : nullptr; p.dgamma[g] = dgamma[g]; p.dbeta[g] = dbeta[g];
+    p.dcolsum[g] = dcolsum ? dcolsum[g] : nullptr;
+  }
+  p.M = M;
+  int bx = (M + 15) / 16;
   if (bx > 148 * 4) bx = 148 * 4;
   dim3 grid(bx, groups);
-  if (at == 0)
-    ln_bwd_kernel<float><<<grid, 256, 0, s>>>(pack4<const float*>(dy, groups), pack4<const float*>(x, groups),
-                                              pack4<const float*>(mean, groups), pack4<const float*>(rstd, groups),
-                                              pack4<const float*>(gamma, groups), pack4<float*>(dres, groups),
-                                              pack4<float*>(dres_lp, groups), pack4<float*>(dgamma, groups),
-                                              pack4<float*>(dbeta, groups), M);
-  else
-    ln_bwd_kernel<bf16><<<grid, 256, 0, s>>>(pack4<const bf16*>(dy, groups), pack4<const float*>(x, groups),
-                                             pack4<const float*>(mean, groups), pack4<const float*>(rstd, groups),
-                                             pack4<const float*>(gamma, groups), pack4<float*>(dres, groups),
-                                             pack4<bf16*>(dres_lp, groups), pack4<float*>(dgamma, groups),
-                                             pack4<float*>(dbeta, groups), M);
+  if (at == 0) ln_bwd_kernel<float><<<grid, 256, 0, s>>>(p);
+  else ln_bwd_kernel<bf16><<<grid, 256, 0, s>>>(p);
   V2S_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_colsum(const void* const* dy, float* const* db, int groups, int M, int N, int t, cudaStream_t s) {
-  int splits = (M + 255) / 256;
-  if (splits > 128) splits = 128;
-  if (splits < 1) splits = 1;
-  const int rows_per_block = (M + splits - 1) / splits;
-  dim3 grid((N + 31) / 32, splits, groups), block(32, 8);
-  if (t == 0) colsum_kernel<float><<<grid, block, 0, s>>>(pack4<const float*>(dy, groups), pack4<float*>(db, groups), M, N, rows_per_block);
-  else colsum_kernel<bf16><<<grid, block, 0, s>>>(pack4<const bf16*>(dy, groups), pack4<float*>(db, groups), M, N, rows_per_block);
+  if (N % 8 || N > 2048) { set_error("colsum: N must be a multiple of 8 and <= 2048 (got %d)", N); return 1; }
+  ColsumP p;
+  memset(&p, 0, sizeof(p));
+  for (int g = 0; g < groups; ++g) { p.dy[g] = dy[g]; p.db[g] = db[g]; }
+  p.M = M; p.N = N;
+  int rows_t = 256 / (N / 8);
+  if (rows_t * N > 2048) rows_t = 2048 / N;
+  int bx = (M + rows_t * 16 - 1) / (rows_t * 16);     // >= 16 rows per row-lane
+  if (bx > 148 * 4) bx = 148 * 4;
+  if (bx < 1) bx = 1;
+  p.rows_per_block = (M + bx - 1) / bx;
+  dim3 grid(bx, groups);
+  if (t == 0) colsum_kernel<float><<<grid, 256, 0, s>>>(p);
+  else colsum_kernel<bf16><<<grid, 256, 0, s>>>(p);
   V2S_LAUNCH_CHECK();
   return 0;
 }

@@ -14,11 +14,12 @@ int launch_gather_patch_rows(const void* const* src, void* const* dst, int group
 int launch_ln_fwd(const float* const* x, const float* const* gamma, const float* const* beta,
                   void* const* y, float* const* mean, float* const* rstd, int groups, int M, int at,
                   cudaStream_t s);
-// dres (fp32, in/out) += LN-backward(dy); dres_lp (optional, activation type) = updated dres
+// dres (fp32, in/out) += LN-backward(dy); dres_lp (optional, activation type) = updated dres;
+// dcolsum (optional) += column sums of the updated dres (bias gradient of the next linear layer)
 int launch_ln_bwd(const void* const* dy, const float* const* x, const float* const* mean,
                   const float* const* rstd, const float* const* gamma, float* const* dres,
-                  void* const* dres_lp, float* const* dgamma, float* const* dbeta, int groups, int M,
-                  int at, cudaStream_t s);
+                  void* const* dres_lp, float* const* dgamma, float* const* dbeta, float* const* dcolsum,
+                  int groups, int M, int at, cudaStream_t s);
 // db[n] += sum_m dy[m,n]; src type tag `t`
 int launch_colsum(const void* const* dy, float* const* db, int groups, int M, int N, int t, cudaStream_t s);
 int launch_pool_fwd(const float* const* hidden, float* const* feat, const int64_t* feat_stride,
