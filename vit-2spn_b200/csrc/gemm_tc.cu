@@ -5,10 +5,13 @@
 //   C[M,N] (+)= A[M,K] * B[N,K]^T        A, B: K-major or MN-major (UMMA descriptor major bits)
 //
 // CTA = 384 threads: warp 0 TMA producer, warp 1 MMA issuer (single thread), warp 2 TMEM allocator,
-// warps 4..11 epilogue (two groups of four warps; a warp reads TMEM lane quarter warp%4, the two
-// groups take alternate 32-column chunks of the 128x192 accumulator).
+// warps 4..11 epilogue: two groups of four warps (a warp reads TMEM lane quarter warp%4); group g
+// drains the accumulator stage g, i.e. the CTA's even / odd tiles, so two epilogues and the MMAs of
+// a third tile overlap.  Each group walks its 128x192 accumulator in six 32-column chunks through a
+// ring of three 16 KB staging buffers: [TMA-load the auxiliary operand (residual / pre-GELU) into
+// the buffer] -> thread-per-row math in place -> TMA store (or reduce-add) out of the same buffer.
 // Tile = 128 x 192 x 64; 3-stage smem ring (A 16 KB + B 24 KB per stage); 2 accumulator stages in
-// TMEM (2 x 192 of 512 columns) so that the epilogue of tile i overlaps the MMAs of tile i+1.
+// TMEM (2 x 192 of 512 columns).
 #include <string.h>
 
 #include <unordered_map>
@@ -28,8 +31,9 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int CHUNK = 32;                         // epilogue column chunk
 constexpr int N_CHUNKS = BN / CHUNK;              // 6
 constexpr int STG_BYTES = BM * CHUNK * 4;         // 16384: one fp32 chunk (bf16 chunks use half)
+constexpr int N_STG = 3;                          // staging buffers per epilogue group
 constexpr int SMEM_STAGING_OFF = STAGES * STAGE_BYTES;                 // 122880
-constexpr int SMEM_BAR_OFF = SMEM_STAGING_OFF + 4 * STG_BYTES;         // 188416
+constexpr int SMEM_BAR_OFF = SMEM_STAGING_OFF + 2 * N_STG * STG_BYTES; // 221184
 constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 256 + 1024;                  // + alignment slack
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;                   // TMEM column stride between accumulator stages
@@ -91,8 +95,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;      // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;          // [2] accumulator drained
-  uint64_t* aux_bar = tempty_bar + 2;            // [2] per epilogue group: aux chunk landed
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aux_bar + 2);
+  uint64_t* aux_bar = tempty_bar + 2;            // [2][N_STG] per epilogue group and staging buffer: aux chunk landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aux_bar + 2 * N_STG);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -105,7 +109,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], 8); ptx::mbar_init(&aux_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], 4); }
+    for (int s = 0; s < 2 * N_STG; ++s) ptx::mbar_init(&aux_bar[s], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -190,76 +195,92 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     }
   } else if (warp >= 4) {
     // ================= epilogue =================
-    const int ge = (warp - 4) >> 2;                 // epilogue group 0/1
+    const int ge = (warp - 4) >> 2;                 // epilogue group = accumulator stage it drains
     const int q = warp & 3;                         // TMEM lane quarter
     const int row = q * 32 + lane;                  // row within the 128-row tile
     const bool issuer = (warp == 4 + 4 * ge) && lane == 0;
-    uint8_t* stg_out = smem + SMEM_STAGING_OFF + ge * 2 * STG_BYTES;
-    uint8_t* stg_aux = stg_out + STG_BYTES;
+    uint8_t* stg_base = smem + SMEM_STAGING_OFF + ge * N_STG * STG_BYTES;
+    uint64_t* abar = aux_bar + ge * N_STG;
     const int bar_id = 1 + ge;
-    int acc = 0; uint32_t acc_phase = 0;
-    uint32_t aux_phase = 0;
     constexpr bool HAS_AUX = (EPI == T_RESID || EPI == T_DGELU);
     constexpr int AUX_BYTES = (EPI == T_RESID) ? BM * CHUNK * 4 : BM * CHUNK * 2;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    const int first = blockIdx.x + ge * gridDim.x, stride = 2 * gridDim.x;
+
+    // auxiliary operand of this group's n-th chunk (chunks are numbered across the group's tiles)
+    auto issue_aux = [&](int n) {
+      const int t = first + (n / N_CHUNKS) * stride;
+      if (t >= p.total_tiles) return;
+      int g, m_tile, split, n_tile;
+      decode(t, g, m_tile, split, n_tile);
+      const int b = n % N_STG;
+      ptx::mbar_arrive_expect_tx(&abar[b], AUX_BYTES);
+      ptx::tma_load_2d(stg_base + b * STG_BYTES, &p.tmAux[g], &abar[b], n_tile * BN + (n % N_CHUNKS) * CHUNK, m_tile * BM);
+    };
+    if (HAS_AUX && issuer) { issue_aux(0); issue_aux(1); }
+
+    uint32_t acc_phase = 0;
+    int cnt = 0;                                    // running chunk counter of this group
+    for (int t = first; t < p.total_tiles; t += stride) {
       int g, m_tile, split, n_tile;
       decode(t, g, m_tile, split, n_tile);
       const int m0 = m_tile * BM, n0 = n_tile * BN;
-      if (HAS_AUX && issuer) {
-        ptx::mbar_arrive_expect_tx(&aux_bar[ge], AUX_BYTES);
-        ptx::tma_load_2d(stg_aux, &p.tmAux[g], &aux_bar[ge], n0 + ge * CHUNK, m0);
-      }
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 4);
+      ptx::mbar_wait(&tfull_bar[ge], acc_phase, p.err_flag, 4);
+      acc_phase ^= 1;
       ptx::tc_fence_after();
       const bool write_u = (EPI == T_GELU) && ((p.out2_mask >> g) & 1);
-      for (int c = ge; c < N_CHUNKS; c += 2) {
+      const float* bias = (EPI != T_ACCUM && EPI != T_DGELU) ? p.bias[g] : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < N_CHUNKS; ++c, ++cnt) {
         const int col0 = n0 + c * CHUNK;
+        const int b = cnt % N_STG;
+        uint8_t* stg = stg_base + b * STG_BYTES;
         uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE + c * CHUNK, r);
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + ge * ACC_STRIDE + c * CHUNK, r);
         ptx::tmem_ld_wait();
-        if (c + 2 >= N_CHUNKS) {                    // last TMEM read of this warp for this tile
+        if (c == N_CHUNKS - 1) {                    // accumulator fully read: hand the stage back to the MMA warp
           ptx::tc_fence_before();
-          if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) ptx::mbar_arrive(&tempty_bar[ge]);
         }
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (EPI != T_ACCUM && EPI != T_DGELU && p.bias[g] != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias[g] + col0);
+        if (bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col0 + 4 * i < p.N) b = __ldg(b4 + i);
-            v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col0 + 4 * i < p.N) bb = __ldg(b4 + i);
+            v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
           }
         }
+        // Buffer b is free here: its previous store (chunk cnt-3) was retired by the issuer's
+        // wait_group.read<1> after the store of chunk cnt-2, which precedes the barrier of chunk cnt-1.
         if (HAS_AUX) {
-          ptx::mbar_wait(&aux_bar[ge], aux_phase, p.err_flag, 5);
-          aux_phase ^= 1;
+          ptx::mbar_wait(&abar[b], (cnt / N_STG) & 1, p.err_flag, 5);
           if (EPI == T_RESID) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 a = *reinterpret_cast<const float4*>(stg_aux + row * 128 + ((j ^ (row & 7)) << 4));
-              v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+              float4* slot = reinterpret_cast<float4*>(stg + row * 128 + ((j ^ (row & 7)) << 4));
+              const float4 a = *slot;
+              *slot = make_float4(v[4 * j] + a.x, v[4 * j + 1] + a.y, v[4 * j + 2] + a.z, v[4 * j + 3] + a.w);
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 a = *reinterpret_cast<const uint4*>(stg_aux + row * 64 + ((j ^ ((row >> 1) & 3)) << 4));
+              uint4* slot = reinterpret_cast<uint4*>(stg + row * 64 + ((j ^ ((row >> 1) & 3)) << 4));
+              const uint4 a = *slot;
               const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+              uint32_t o[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const __nv_bfloat162 u2 = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
-                v[8 * j + 2 * e] *= gelu_grad_fast(__low2float(u2));
-                v[8 * j + 2 * e + 1] *= gelu_grad_fast(__high2float(u2));
+                o[e] = pack_bf16(v[8 * j + 2 * e] * gelu_grad_fast(__low2float(u2)),
+                                 v[8 * j + 2 * e + 1] * gelu_grad_fast(__high2float(u2)));
               }
+              *slot = make_uint4(o[0], o[1], o[2], o[3]);
             }
           }
-        }
-        // the previous TMA store out of this group's staging buffers must have finished reading them
-        if (issuer) ptx::tma_wait_group_read<0>();
-        ptx::bar_sync(bar_id, 128);
-        if (OUT_BF16) {
+        } else if (OUT_BF16) {
           if (EPI == T_GELU) {
             if (write_u) {
 #pragma unroll
@@ -267,7 +288,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
                 uint4 o;
                 o.x = pack_bf16(v[8 * j], v[8 * j + 1]); o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
                 o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-                *reinterpret_cast<uint4*>(stg_aux + row * 64 + ((j ^ ((row >> 1) & 3)) << 4)) = o;
+                *reinterpret_cast<uint4*>(stg + 8192 + row * 64 + ((j ^ ((row >> 1) & 3)) << 4)) = o;
               }
             }
 #pragma unroll
@@ -278,30 +299,27 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
             uint4 o;
             o.x = pack_bf16(v[8 * j], v[8 * j + 1]); o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
             o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-            *reinterpret_cast<uint4*>(stg_out + row * 64 + ((j ^ ((row >> 1) & 3)) << 4)) = o;
+            *reinterpret_cast<uint4*>(stg + row * 64 + ((j ^ ((row >> 1) & 3)) << 4)) = o;
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(stg_out + row * 128 + ((j ^ (row & 7)) << 4)) =
+            *reinterpret_cast<float4*>(stg + row * 128 + ((j ^ (row & 7)) << 4)) =
                 make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         ptx::fence_proxy_async();
         ptx::bar_sync(bar_id, 128);
         if (issuer) {
           if (col0 < p.N) {
-            if (EPI == T_ACCUM) ptx::tma_reduce_add_2d(&p.tmOut[g], stg_out, col0, m0);
-            else ptx::tma_store_2d(&p.tmOut[g], stg_out, col0, m0);
-            if (write_u) ptx::tma_store_2d(&p.tmOut2[g], stg_aux, col0, m0);
+            if (EPI == T_ACCUM) ptx::tma_reduce_add_2d(&p.tmOut[g], stg, col0, m0);
+            else ptx::tma_store_2d(&p.tmOut[g], stg, col0, m0);
+            if (write_u) ptx::tma_store_2d(&p.tmOut2[g], stg + 8192, col0, m0);
           }
           ptx::tma_commit_group();
-          if (HAS_AUX && c + 2 < N_CHUNKS) {        // aux buffer is free (all reads precede the barrier)
-            ptx::mbar_arrive_expect_tx(&aux_bar[ge], AUX_BYTES);
-            ptx::tma_load_2d(stg_aux, &p.tmAux[g], &aux_bar[ge], n0 + (c + 2) * CHUNK, m0);
-          }
+          ptx::tma_wait_group_read<1>();            // store of chunk cnt-1 has left its buffer
+          if (HAS_AUX) issue_aux(cnt + 2);          // ... which is the buffer of chunk cnt+2
         }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (issuer) ptx::tma_wait_group<0>();
   }
