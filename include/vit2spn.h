@@ -165,6 +165,8 @@ int v2s_test_attention(int which, const void* qkv, void* ctx, float* lse, const 
                        int batch, int variant, void* stream);
 /* reads and clears the device-side pipeline-protocol error flag of the tcgen05 kernels (0 = ok) */
 int v2s_debug_flag(void);
+/* per-role stall cycle counters of CTA 0 of the last tcgen05 GEMM (only with V2S_GEMM_DEBUG=1) */
+int v2s_debug_counters(int64_t* host32);
 int64_t v2s_launch_count(void); /* kernels launched by this library since load (bench: gpu_launches) */
 /* device-event timing per kernel class (bench.py roofline); off by default, enabling resets it */
 int v2s_prof_enable(int on);

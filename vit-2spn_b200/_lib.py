@@ -66,6 +66,7 @@ _SIGS = {
     "v2s_test_attention": (C.c_int, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "v2s_launch_count": (_i64, []),
     "v2s_debug_flag": (C.c_int, []),
+    "v2s_debug_counters": (C.c_int, [C.POINTER(_i64)]),
     "v2s_prof_enable": (C.c_int, [_i]),
     "v2s_prof_report": (C.c_int, [C.c_char_p, _i64]),
 }

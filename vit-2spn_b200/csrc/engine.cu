@@ -798,6 +798,7 @@ int v2s_test_attention(int which, const void* qkv, void* ctx, float* lse, const 
 }
 
 int v2s_debug_flag(void) { return gemm_tc_error_flag(); }
+int v2s_debug_counters(int64_t* host32) { return gemm_tc_debug_counters(reinterpret_cast<long long*>(host32)); }
 
 int v2s_test_gemm(int which, const void* a, const void* b, void* c, int m, int n, int k, int variant, void* stream) {
   return gemm_tc_test(which, a, b, c, m, n, k, variant, (cudaStream_t)stream);

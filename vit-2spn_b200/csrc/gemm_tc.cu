@@ -54,7 +54,10 @@ struct alignas(64) TcParams {
   int tiles_m, tiles_n, splits, kb_total, kb_per_split, groups, total_tiles;
   int a_mn, b_mn;
   int out2_mask;      // bit g: group g writes the secondary output (pre-GELU u)
+  int b_stationary;   // K <= 192: the CTA keeps its [192 x K] B tile in smem and walks m-tiles only
+  int ctas_per_combo; // b_stationary: CTAs sharing one (group, n_tile)
   int* err_flag;
+  long long* dbg;     // optional per-role cycle counters of CTA 0 (V2S_GEMM_DEBUG=1)
 };
 
 // fast erf-GELU for the bf16 path: Abramowitz-Stegun 7.1.26, |erf error| < 1.5e-7 (far below bf16
@@ -96,7 +99,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
   uint64_t* tfull_bar = empty_bar + STAGES;      // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;          // [2] accumulator drained
   uint64_t* aux_bar = tempty_bar + 2;            // [2][N_STG] per epilogue group and staging buffer: aux chunk landed
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aux_bar + 2 * N_STG);
+  uint64_t* bres_bar = aux_bar + 2 * N_STG;      // B-stationary tile landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -111,6 +115,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], 4); }
     for (int s = 0; s < 2 * N_STG; ++s) ptx::mbar_init(&aux_bar[s], 1);
+    ptx::mbar_init(bres_bar, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -123,61 +128,98 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
   const uint32_t tmem_base = *tmem_ptr;
 
   const int tiles_per_group = p.tiles_m * p.splits * p.tiles_n;
-  auto decode = [&](int t, int& g, int& m_tile, int& split, int& n_tile) {
+  // i-th tile of this CTA (same sequence for every warp role); false when the CTA is done
+  auto tile_at = [&](int i, int& g, int& m_tile, int& split, int& n_tile) -> bool {
+    if (p.b_stationary) {
+      const int combo = blockIdx.x / p.ctas_per_combo, rank = blockIdx.x % p.ctas_per_combo;
+      g = combo / p.tiles_n; n_tile = combo % p.tiles_n; split = 0;
+      m_tile = rank + i * p.ctas_per_combo;
+      return m_tile < p.tiles_m;
+    }
+    const int t = blockIdx.x + i * gridDim.x;
+    if (t >= p.total_tiles) return false;
     g = t / tiles_per_group;
     int r = t - g * tiles_per_group;
     n_tile = r % p.tiles_n; r /= p.tiles_n;
     split = r % p.splits;
     m_tile = r / p.splits;
+    return true;
   };
+  // smem map of the operand region: streaming mode = 3 stages of [A 16 KB | B 24 KB];
+  // B-stationary mode = [B tile: up to 3 k-blocks x 24 KB] followed by a 3-stage ring of A (16 KB)
+  uint8_t* bres = smem;
+  uint8_t* aring = smem + 3 * B_STAGE_BYTES;
 
   if (warp == 0 && lane == 0) {
     // ================= TMA producer =================
+    long long prod_wait = 0; const long long prod_t0 = clock64();
     int stage = 0; uint32_t phase = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      int g, m_tile, split, n_tile;
-      decode(t, g, m_tile, split, n_tile);
+    int g, m_tile, split, n_tile;
+    if (p.b_stationary && tile_at(0, g, m_tile, split, n_tile)) {
+      ptx::mbar_arrive_expect_tx(bres_bar, p.kb_total * B_STAGE_BYTES);
+      for (int kb = 0; kb < p.kb_total; ++kb) {
+        uint8_t* sb = bres + kb * B_STAGE_BYTES;
+        if (!p.b_mn) {
+          ptx::tma_load_2d(sb, &p.tmB[g], bres_bar, kb * BK, n_tile * BN);
+        } else {
+          ptx::tma_load_2d(sb, &p.tmB[g], bres_bar, n_tile * BN, kb * BK);
+          ptx::tma_load_2d(sb + 8192, &p.tmB[g], bres_bar, n_tile * BN + 64, kb * BK);
+          ptx::tma_load_2d(sb + 16384, &p.tmB[g], bres_bar, n_tile * BN + 128, kb * BK);
+        }
+      }
+    }
+    for (int i = 0; tile_at(i, g, m_tile, split, n_tile); ++i) {
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
+        const long long w0 = clock64();
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
-        uint8_t* sa = smem + stage * STAGE_BYTES;
+        prod_wait += clock64() - w0;
+        uint8_t* sa = p.b_stationary ? aring + stage * A_STAGE_BYTES : smem + stage * STAGE_BYTES;
         uint8_t* sb = sa + A_STAGE_BYTES;
-        ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], p.b_stationary ? A_STAGE_BYTES : STAGE_BYTES);
         if (!p.a_mn) {
           ptx::tma_load_2d(sa, &p.tmA[g], &full_bar[stage], kb * BK, m_tile * BM);
         } else {
           ptx::tma_load_2d(sa, &p.tmA[g], &full_bar[stage], m_tile * BM, kb * BK);
           ptx::tma_load_2d(sa + 8192, &p.tmA[g], &full_bar[stage], m_tile * BM + 64, kb * BK);
         }
-        if (!p.b_mn) {
-          ptx::tma_load_2d(sb, &p.tmB[g], &full_bar[stage], kb * BK, n_tile * BN);
-        } else {
-          ptx::tma_load_2d(sb, &p.tmB[g], &full_bar[stage], n_tile * BN, kb * BK);
-          ptx::tma_load_2d(sb + 8192, &p.tmB[g], &full_bar[stage], n_tile * BN + 64, kb * BK);
-          ptx::tma_load_2d(sb + 16384, &p.tmB[g], &full_bar[stage], n_tile * BN + 128, kb * BK);
+        if (!p.b_stationary) {
+          if (!p.b_mn) {
+            ptx::tma_load_2d(sb, &p.tmB[g], &full_bar[stage], kb * BK, n_tile * BN);
+          } else {
+            ptx::tma_load_2d(sb, &p.tmB[g], &full_bar[stage], n_tile * BN, kb * BK);
+            ptx::tma_load_2d(sb + 8192, &p.tmB[g], &full_bar[stage], n_tile * BN + 64, kb * BK);
+            ptx::tma_load_2d(sb + 16384, &p.tmB[g], &full_bar[stage], n_tile * BN + 128, kb * BK);
+          }
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    if (p.dbg && blockIdx.x == 0) { p.dbg[0] = prod_wait; p.dbg[1] = clock64() - prod_t0; }
   } else if (warp == 1 && lane == 0) {
     // ================= MMA issuer =================
     const uint32_t idesc = ptx::make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      int g, m_tile, split, n_tile;
-      decode(t, g, m_tile, split, n_tile);
+    int g, m_tile, split, n_tile;
+    long long w_full = 0, w_tempty = 0, ntiles = 0; const long long mma_t0 = clock64();
+    if (p.b_stationary && tile_at(0, g, m_tile, split, n_tile)) ptx::mbar_wait(bres_bar, 0, p.err_flag, 6);
+    for (int i = 0; tile_at(i, g, m_tile, split, n_tile); ++i) {
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      long long w0 = clock64();
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 2);
+      w_tempty += clock64() - w0; ++ntiles;
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
       for (int kb = kb0; kb < kb1; ++kb) {
+        w0 = clock64();
         ptx::mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
+        w_full += clock64() - w0;
         ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + stage * STAGE_BYTES);
-        const uint32_t sb = sa + A_STAGE_BYTES;
+        const uint32_t sa = ptx::smem_u32(p.b_stationary ? aring + stage * A_STAGE_BYTES : smem + stage * STAGE_BYTES);
+        const uint32_t sb = p.b_stationary ? ptx::smem_u32(bres + kb * B_STAGE_BYTES) : sa + A_STAGE_BYTES;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           // K-major: 16 elements = 32 B along the swizzled row; MN-major: 16 k-rows = 2048 B
@@ -193,6 +235,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
       ptx::umma_commit(&tfull_bar[acc]);           // accumulator complete → epilogue
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.dbg && blockIdx.x == 0) { p.dbg[2] = w_full; p.dbg[3] = w_tempty; p.dbg[4] = clock64() - mma_t0; p.dbg[5] = ntiles; }
   } else if (warp >= 4) {
     // ================= epilogue =================
     const int ge = (warp - 4) >> 2;                 // epilogue group = accumulator stage it drains
@@ -204,14 +247,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     const int bar_id = 1 + ge;
     constexpr bool HAS_AUX = (EPI == T_RESID || EPI == T_DGELU);
     constexpr int AUX_BYTES = (EPI == T_RESID) ? BM * CHUNK * 4 : BM * CHUNK * 2;
-    const int first = blockIdx.x + ge * gridDim.x, stride = 2 * gridDim.x;
 
     // auxiliary operand of this group's n-th chunk (chunks are numbered across the group's tiles)
     auto issue_aux = [&](int n) {
-      const int t = first + (n / N_CHUNKS) * stride;
-      if (t >= p.total_tiles) return;
       int g, m_tile, split, n_tile;
-      decode(t, g, m_tile, split, n_tile);
+      if (!tile_at(ge + 2 * (n / N_CHUNKS), g, m_tile, split, n_tile)) return;
       const int b = n % N_STG;
       ptx::mbar_arrive_expect_tx(&abar[b], AUX_BYTES);
       ptx::tma_load_2d(stg_base + b * STG_BYTES, &p.tmAux[g], &abar[b], n_tile * BN + (n % N_CHUNKS) * CHUNK, m_tile * BM);
@@ -220,11 +260,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
 
     uint32_t acc_phase = 0;
     int cnt = 0;                                    // running chunk counter of this group
-    for (int t = first; t < p.total_tiles; t += stride) {
-      int g, m_tile, split, n_tile;
-      decode(t, g, m_tile, split, n_tile);
+    long long e_tfull = 0, e_aux = 0, e_bar = 0, e_ld = 0; const long long epi_t0 = clock64();
+    int g, m_tile, split, n_tile;
+    for (int i = ge; tile_at(i, g, m_tile, split, n_tile); i += 2) {
       const int m0 = m_tile * BM, n0 = n_tile * BN;
+      long long w0 = clock64();
       ptx::mbar_wait(&tfull_bar[ge], acc_phase, p.err_flag, 4);
+      e_tfull += clock64() - w0;
       acc_phase ^= 1;
       ptx::tc_fence_after();
       const bool write_u = (EPI == T_GELU) && ((p.out2_mask >> g) & 1);
@@ -235,8 +277,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
         const int b = cnt % N_STG;
         uint8_t* stg = stg_base + b * STG_BYTES;
         uint32_t r[32];
+        w0 = clock64();
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + ge * ACC_STRIDE + c * CHUNK, r);
         ptx::tmem_ld_wait();
+        e_ld += clock64() - w0;
         if (c == N_CHUNKS - 1) {                    // accumulator fully read: hand the stage back to the MMA warp
           ptx::tc_fence_before();
           if (lane == 0) ptx::mbar_arrive(&tempty_bar[ge]);
@@ -256,7 +300,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
         // Buffer b is free here: its previous store (chunk cnt-3) was retired by the issuer's
         // wait_group.read<1> after the store of chunk cnt-2, which precedes the barrier of chunk cnt-1.
         if (HAS_AUX) {
+          w0 = clock64();
           ptx::mbar_wait(&abar[b], (cnt / N_STG) & 1, p.err_flag, 5);
+          e_aux += clock64() - w0;
           if (EPI == T_RESID) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -308,7 +354,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
                 make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         ptx::fence_proxy_async();
+        w0 = clock64();
         ptx::bar_sync(bar_id, 128);
+        e_bar += clock64() - w0;
         if (issuer) {
           if (col0 < p.N) {
             if (EPI == T_ACCUM) ptx::tma_reduce_add_2d(&p.tmOut[g], stg, col0, m0);
@@ -322,6 +370,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
       }
     }
     if (issuer) ptx::tma_wait_group<0>();
+    if (p.dbg && blockIdx.x == 0 && (threadIdx.x == 128 || threadIdx.x == 256 + 37)) {
+      long long* d = p.dbg + 8 + (threadIdx.x == 128 ? 0 : 8);
+      d[0] = e_tfull; d[1] = e_aux; d[2] = e_bar; d[3] = e_ld; d[4] = clock64() - epi_t0; d[5] = cnt;
+    }
   }
 
   ptx::tc_fence_before();
@@ -340,6 +392,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 int* g_err_flag = nullptr;      // device int, allocated once at init (4 bytes; the only allocation)
+long long* g_dbg = nullptr;     // 32 counters, only with V2S_GEMM_DEBUG=1
 int g_num_sms = 148;
 bool g_disabled = false;
 
@@ -435,7 +488,8 @@ int launch_kernel(const TcParams& p, cudaStream_t stream) {
     V2S_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI, OUT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     attr_set = true;
   }
-  const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+  int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+  if (p.b_stationary) grid = p.groups * p.tiles_n * p.ctas_per_combo;
   gemm_tc_kernel<EPI, OUT_BF16><<<grid, N_THREADS, SMEM_TOTAL, stream>>>(p);
   V2S_LAUNCH_CHECK();
   return 0;
@@ -458,8 +512,19 @@ int gemm_tc_init() {
   V2S_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   V2S_CUDA_OK(cudaMalloc(&g_err_flag, sizeof(int)));
   V2S_CUDA_OK(cudaMemset(g_err_flag, 0, sizeof(int)));
+  if (getenv("V2S_GEMM_DEBUG")) {
+    V2S_CUDA_OK(cudaMalloc(&g_dbg, 32 * sizeof(long long)));
+    V2S_CUDA_OK(cudaMemset(g_dbg, 0, 32 * sizeof(long long)));
+  }
   const char* env = getenv("V2S_GEMM");
   g_disabled = env && strcmp(env, "simt") == 0;   // debugging: route every GEMM through the SIMT kernel
+  return 0;
+}
+
+int gemm_tc_debug_counters(long long* host32) {
+  if (!g_dbg) { set_error("V2S_GEMM_DEBUG not set"); return 1; }
+  V2S_CUDA_OK(cudaMemcpy(host32, g_dbg, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+  V2S_CUDA_OK(cudaMemset(g_dbg, 0, 32 * sizeof(long long)));
   return 0;
 }
 
@@ -514,7 +579,15 @@ int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t strea
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
   p.total_tiles = d.groups * p.tiles_m * p.tiles_n * p.splits;
   p.a_mn = a_mn; p.b_mn = b_mn;
+  const int combos = d.groups * p.tiles_n;
+  if (epi != T_ACCUM && p.kb_total <= 3 && combos <= g_num_sms && !getenv("V2S_NO_BSTAT")) {
+    int cpc = g_num_sms / combos;
+    if (cpc > p.tiles_m) cpc = p.tiles_m;
+    p.b_stationary = 1;
+    p.ctas_per_combo = cpc;
+  }
   p.err_flag = g_err_flag;
+  p.dbg = g_dbg;
   const CUtensorMapSwizzle out_swz = out_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   for (int g = 0; g < d.groups; ++g) {
     if (!a_mn) V2S_TRY(get_map(&p.tmA[g], d.A[g], d.K, d.M, a_ld, BK, BM, true, CU_TENSOR_MAP_SWIZZLE_128B));

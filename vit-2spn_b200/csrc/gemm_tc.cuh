@@ -17,6 +17,7 @@ int tmap_get_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uin
                 uint64_t s2_bytes, uint32_t b0, uint32_t b1, bool is_bf16, int swizzle_bytes);
 int* tc_err_flag();
 bool tc_enabled();
+int gemm_tc_debug_counters(long long* host32);
 // reads and clears the device-side protocol error flag (0 = none); synchronises
 int gemm_tc_error_flag();
 // test hook behind v2s_test_gemm
