@@ -145,7 +145,7 @@ def main():
     import torch.distributed as dist
     import vit2spn
     from vit2spn import _lib
-    from oracle import vit2spn_oracle as orc
+    import numpy as np
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -160,22 +160,18 @@ def main():
     # ---- model, optimizer, synthetic device-resident data -------------------------------------
     torch.manual_seed(42)
     model = vit2spn.DualStreamNetwork().to(dev).train()
-    if world > 1:                                    # identical replicas
-        for s in model._stores() + [model._head_store]:
-            dist.broadcast(s.flat, 0)
+    vit2spn.parallel.broadcast_parameters(model)     # identical replicas
     opt = vit2spn.FusedAdam(model.parameters(), lr=1e-4)
-    opt.grad_scale = 1.0 / world
-    u8 = torch.from_numpy(orc.synthetic_octmnist_u8(2 * B, seed=1000 + rank)).to(dev)
+    # seeded raw OCTMNIST-shaped source images, uint8 [2B,1,28,28]; rank-dependent seed
+    u8 = torch.from_numpy(np.random.default_rng(1000 + rank).integers(0, 256, size=(2 * B, 1, 28, 28), dtype=np.uint8)).to(dev)
     views = torch.empty(2, B, 3, 224, 224, device=dev)
     _lib.init_device(local)
     _lib.check(_lib.lib.v2s_preprocess_u8(_lib.ptr(u8), _lib.ptr(views), 2 * B, _lib.stream_ptr()))
     x1, x2 = views[0], views[1]
 
     def grads_allreduce():
-        if world > 1:
-            for s in model._stores()[:2]:
-                dist.all_reduce(s.flat_grad[:s.active_numel])
-            dist.all_reduce(model._head_store.flat_grad)
+        if world > 1:      # one collective per optimizer step over 3 flat fp32 buckets; 1/world folded into Adam
+            vit2spn.parallel.allreduce_gradients(model, optimizer=opt)
 
     def step(a, b):
         loss = model.ssp_step(a, b, accumulation_steps=1)
