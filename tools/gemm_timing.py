@@ -2,7 +2,7 @@
 import ctypes as C
 import os
 import sys
-os.environ["V2S_GEMM_DEBUG"] = "1"
+os.environ.setdefault("V2S_GEMM_DEBUG", "1")
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -38,6 +38,8 @@ def run(which, m, n, k, label):
           f"epi1 wait_tfull {d[16]} bar {d[18]} tmem_ld {d[19]} total {d[20]} chunks {d[21]}")
 
 
+print("V2S_GEMM_DEBUG =", os.environ["V2S_GEMM_DEBUG"])
+run(0, 4 * 25216, 576, 192, "qkv fwd x4 (NT)")
 run(0, 25216, 576, 192, "qkv fwd (NT)")
 run(0, 25216, 768, 192, "fc1-like (NT, plain store)")
 run(0, 25216, 192, 768, "fc2-like (NT, plain store)")

@@ -24,17 +24,14 @@ namespace v2s {
 namespace {
 
 constexpr int BM = 128, BN = 192, BK = 64;
-constexpr int STAGES = 3;
+constexpr int MAX_STAGES = 6;                     // smem ring depth is chosen per variant on the host
 constexpr int A_STAGE_BYTES = BM * BK * 2;        // 16384
 constexpr int B_STAGE_BYTES = BN * BK * 2;        // 24576
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int CHUNK = 32;                         // epilogue column chunk
 constexpr int N_CHUNKS = BN / CHUNK;              // 6
-constexpr int STG_BYTES = BM * CHUNK * 4;         // 16384: one fp32 chunk (bf16 chunks use half)
-constexpr int N_STG = 3;                          // staging buffers per epilogue group
-constexpr int SMEM_STAGING_OFF = STAGES * STAGE_BYTES;                 // 122880
-constexpr int SMEM_BAR_OFF = SMEM_STAGING_OFF + 2 * N_STG * STG_BYTES; // 221184
-constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 256 + 1024;                  // + alignment slack
+constexpr int SMEM_LIMIT = 232448;                // 227 KB opt-in maximum per CTA
+constexpr int SMEM_BAR_BYTES = 512;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;                   // TMEM column stride between accumulator stages
 constexpr int N_THREADS = 384;
@@ -47,6 +44,15 @@ enum TcEpi : int {
   T_ACCUM = 4,   // global(fp32) += acc          (TMA reduce-add; split-K)
 };
 
+// per-variant epilogue staging: a ring of NSTG buffers of STG bytes per epilogue group.  Variants with an
+// auxiliary operand (prefetched two chunks ahead into the ring) and the plain bf16 store use 3 buffers;
+// bf16 chunks are 8 KB (SWIZZLE_64B), fp32 chunks and the GELU pair (u | h) 16 KB.
+template <int EPI, bool OUT_BF16> struct Cfg {
+  static constexpr int NSTG = (EPI == T_RESID || EPI == T_DGELU || (EPI == T_STORE && OUT_BF16)) ? 3 : 2;
+  static constexpr int STG = (OUT_BF16 && EPI != T_GELU) ? 8192 : 16384;
+  static constexpr int STAGING_BYTES = 2 * NSTG * STG;
+};
+
 struct alignas(64) TcParams {
   CUtensorMap tmA[MAXG], tmB[MAXG], tmOut[MAXG], tmOut2[MAXG], tmAux[MAXG];
   const float* bias[MAXG];
@@ -56,8 +62,11 @@ struct alignas(64) TcParams {
   int out2_mask;      // bit g: group g writes the secondary output (pre-GELU u)
   int b_stationary;   // K <= 192: the CTA keeps its [192 x K] B tile in smem and walks m-tiles only
   int ctas_per_combo; // b_stationary: CTAs sharing one (group, n_tile)
+  int stages;         // smem ring depth: [A|B] slots when streaming, A-only slots when B-stationary
+  int op_bytes;       // bytes of the operand region (staging ring starts here)
   int* err_flag;
   long long* dbg;     // optional per-role cycle counters of CTA 0 (V2S_GEMM_DEBUG=1)
+  int dbg_flags;      // experiments (V2S_GEMM_DEBUG=<n>): bit1 skip TMEM loads, bit2 skip staging + stores
 };
 
 // fast erf-GELU for the bf16 path: Abramowitz-Stegun 7.1.26, |erf error| < 1.5e-7 (far below bf16
@@ -94,15 +103,19 @@ template <int EPI, bool OUT_BF16>
 __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_BAR_OFF);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;      // [2] accumulator ready
+  constexpr int N_STG = Cfg<EPI, OUT_BF16>::NSTG, STG_BYTES = Cfg<EPI, OUT_BF16>::STG;
+  const int STAGES = p.stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.op_bytes + Cfg<EPI, OUT_BF16>::STAGING_BYTES);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;  // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;          // [2] accumulator drained
-  uint64_t* aux_bar = tempty_bar + 2;            // [2][N_STG] per epilogue group and staging buffer: aux chunk landed
-  uint64_t* bres_bar = aux_bar + 2 * N_STG;      // B-stationary tile landed
+  uint64_t* aux_bar = tempty_bar + 2;            // [2][3] per epilogue group and staging buffer: aux chunk landed
+  uint64_t* bres_bar = aux_bar + 6;              // B-stationary tile landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: tells the compiler it is warp-uniform, so that the single-thread
+  // roles below compile to straight uniform-datapath code (no per-lane convergence loops around TMA / MMA)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     for (int g = 0; g < p.groups; ++g) {
@@ -114,7 +127,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], 4); }
-    for (int s = 0; s < 2 * N_STG; ++s) ptx::mbar_init(&aux_bar[s], 1);
+    for (int s = 0; s < 6; ++s) ptx::mbar_init(&aux_bar[s], 1);
     ptx::mbar_init(bres_bar, 1);
     ptx::fence_barrier_init();
   }
@@ -125,7 +138,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   const int tiles_per_group = p.tiles_m * p.splits * p.tiles_n;
   // i-th tile of this CTA (same sequence for every warp role); false when the CTA is done
@@ -146,60 +159,73 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     return true;
   };
   // smem map of the operand region: streaming mode = 3 stages of [A 16 KB | B 24 KB];
-  // B-stationary mode = [B tile: up to 3 k-blocks x 24 KB] followed by a 3-stage ring of A (16 KB)
+  // B-stationary mode = [B tile: kb_total (<= 3) k-blocks x 24 KB] followed by a ring of A slots (16 KB)
   uint8_t* bres = smem;
-  uint8_t* aring = smem + 3 * B_STAGE_BYTES;
+  uint8_t* aring = smem + p.kb_total * B_STAGE_BYTES;
 
-  if (warp == 0 && lane == 0) {
-    // ================= TMA producer =================
+  if (warp == 0) {
+    // ================= TMA producer (whole warp walks the loop; one elected lane issues) =================
     long long prod_wait = 0; const long long prod_t0 = clock64();
     int stage = 0; uint32_t phase = 0;
     int g, m_tile, split, n_tile;
     if (p.b_stationary && tile_at(0, g, m_tile, split, n_tile)) {
-      ptx::mbar_arrive_expect_tx(bres_bar, p.kb_total * B_STAGE_BYTES);
-      for (int kb = 0; kb < p.kb_total; ++kb) {
-        uint8_t* sb = bres + kb * B_STAGE_BYTES;
-        if (!p.b_mn) {
-          ptx::tma_load_2d(sb, &p.tmB[g], bres_bar, kb * BK, n_tile * BN);
-        } else {
-          ptx::tma_load_2d(sb, &p.tmB[g], bres_bar, n_tile * BN, kb * BK);
-          ptx::tma_load_2d(sb + 8192, &p.tmB[g], bres_bar, n_tile * BN + 64, kb * BK);
-          ptx::tma_load_2d(sb + 16384, &p.tmB[g], bres_bar, n_tile * BN + 128, kb * BK);
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(bres_bar, p.kb_total * B_STAGE_BYTES);
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          uint8_t* sb = bres + kb * B_STAGE_BYTES;
+          if (!p.b_mn) {
+            ptx::tma_load_2d(sb, &p.tmB[g], bres_bar, kb * BK, n_tile * BN);
+          } else {
+            ptx::tma_load_2d(sb, &p.tmB[g], bres_bar, n_tile * BN, kb * BK);
+            ptx::tma_load_2d(sb + 8192, &p.tmB[g], bres_bar, n_tile * BN + 64, kb * BK);
+            ptx::tma_load_2d(sb + 16384, &p.tmB[g], bres_bar, n_tile * BN + 128, kb * BK);
+          }
         }
       }
+      __syncwarp();
     }
     for (int i = 0; tile_at(i, g, m_tile, split, n_tile); ++i) {
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
-        const long long w0 = clock64();
+        const long long w0 = p.dbg ? clock64() : 0;
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
-        prod_wait += clock64() - w0;
-        uint8_t* sa = p.b_stationary ? aring + stage * A_STAGE_BYTES : smem + stage * STAGE_BYTES;
-        uint8_t* sb = sa + A_STAGE_BYTES;
-        ptx::mbar_arrive_expect_tx(&full_bar[stage], p.b_stationary ? A_STAGE_BYTES : STAGE_BYTES);
-        if (!p.a_mn) {
-          ptx::tma_load_2d(sa, &p.tmA[g], &full_bar[stage], kb * BK, m_tile * BM);
-        } else {
-          ptx::tma_load_2d(sa, &p.tmA[g], &full_bar[stage], m_tile * BM, kb * BK);
-          ptx::tma_load_2d(sa + 8192, &p.tmA[g], &full_bar[stage], m_tile * BM + 64, kb * BK);
-        }
-        if (!p.b_stationary) {
-          if (!p.b_mn) {
-            ptx::tma_load_2d(sb, &p.tmB[g], &full_bar[stage], kb * BK, n_tile * BN);
+        if (p.dbg) prod_wait += clock64() - w0;
+        if (ptx::elect_one()) {
+          uint8_t* sa = p.b_stationary ? aring + stage * A_STAGE_BYTES : smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], p.b_stationary ? A_STAGE_BYTES : STAGE_BYTES);
+          if (!p.a_mn) {
+            ptx::tma_load_2d(sa, &p.tmA[g], &full_bar[stage], kb * BK, m_tile * BM);
           } else {
-            ptx::tma_load_2d(sb, &p.tmB[g], &full_bar[stage], n_tile * BN, kb * BK);
-            ptx::tma_load_2d(sb + 8192, &p.tmB[g], &full_bar[stage], n_tile * BN + 64, kb * BK);
-            ptx::tma_load_2d(sb + 16384, &p.tmB[g], &full_bar[stage], n_tile * BN + 128, kb * BK);
+            ptx::tma_load_2d(sa, &p.tmA[g], &full_bar[stage], m_tile * BM, kb * BK);
+            ptx::tma_load_2d(sa + 8192, &p.tmA[g], &full_bar[stage], m_tile * BM + 64, kb * BK);
+          }
+          if (!p.b_stationary) {
+            if (!p.b_mn) {
+              ptx::tma_load_2d(sb, &p.tmB[g], &full_bar[stage], kb * BK, n_tile * BN);
+            } else {
+              ptx::tma_load_2d(sb, &p.tmB[g], &full_bar[stage], n_tile * BN, kb * BK);
+              ptx::tma_load_2d(sb + 8192, &p.tmB[g], &full_bar[stage], n_tile * BN + 64, kb * BK);
+              ptx::tma_load_2d(sb + 16384, &p.tmB[g], &full_bar[stage], n_tile * BN + 128, kb * BK);
+            }
           }
         }
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-    if (p.dbg && blockIdx.x == 0) { p.dbg[0] = prod_wait; p.dbg[1] = clock64() - prod_t0; }
-  } else if (warp == 1 && lane == 0) {
-    // ================= MMA issuer =================
+    if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[0] = prod_wait; p.dbg[1] = clock64() - prod_t0; }
+  } else if (warp == 1) {
+    // ================= MMA issuer (whole warp walks the loop; one elected lane issues) =================
     const uint32_t idesc = ptx::make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+    // descriptor low words per smem slot; a K-step of 16 adds 32 B (K-major) or 2048 B (MN-major), >> 4
+    const uint32_t smem_base = ptx::smem_u32(smem);
+    const uint32_t a_step = p.a_mn ? (2048u >> 4) : (32u >> 4), b_step = p.b_mn ? (2048u >> 4) : (32u >> 4);
+    const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
+    const uint32_t a_slot0 = p.b_stationary ? p.kb_total * B_STAGE_BYTES : 0, a_slot_stride = p.b_stationary ? A_STAGE_BYTES : STAGE_BYTES;
+    const uint32_t b_slot0 = p.b_stationary ? 0 : A_STAGE_BYTES, b_slot_stride = p.b_stationary ? B_STAGE_BYTES : STAGE_BYTES;
+    const uint32_t a_lo0 = ptx::desc_lo(smem_base + a_slot0, a_lbo), b_lo0 = ptx::desc_lo(smem_base + b_slot0, b_lbo);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     int g, m_tile, split, n_tile;
@@ -208,42 +234,40 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     for (int i = 0; tile_at(i, g, m_tile, split, n_tile); ++i) {
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-      long long w0 = clock64();
+      long long w0 = p.dbg ? clock64() : 0;
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 2);
-      w_tempty += clock64() - w0; ++ntiles;
+      if (p.dbg) { w_tempty += clock64() - w0; ++ntiles; }
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
       for (int kb = kb0; kb < kb1; ++kb) {
-        w0 = clock64();
+        if (p.dbg) w0 = clock64();
         ptx::mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
-        w_full += clock64() - w0;
+        if (p.dbg) w_full += clock64() - w0;
         ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(p.b_stationary ? aring + stage * A_STAGE_BYTES : smem + stage * STAGE_BYTES);
-        const uint32_t sb = p.b_stationary ? ptx::smem_u32(bres + kb * B_STAGE_BYTES) : sa + A_STAGE_BYTES;
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // K-major: 16 elements = 32 B along the swizzled row; MN-major: 16 k-rows = 2048 B
-          const uint64_t da = p.a_mn ? ptx::make_smem_desc(sa + k * 2048, 8192, 1024)
-                                     : ptx::make_smem_desc(sa + k * 32, 16, 1024);
-          const uint64_t db = p.b_mn ? ptx::make_smem_desc(sb + k * 2048, 8192, 1024)
-                                     : ptx::make_smem_desc(sb + k * 32, 16, 1024);
-          ptx::umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        const uint32_t a_lo = a_lo0 + ((stage * a_slot_stride) >> 4);
+        const uint32_t b_lo = b_lo0 + (((p.b_stationary ? kb : stage) * b_slot_stride) >> 4);
+        if (ptx::elect_one()) {
+          ptx::umma_bf16_lohi(d_tmem, a_lo, b_lo, ptx::DESC_HI_SW128_SBO1024, idesc, kb > kb0 ? 1u : 0u);
+          ptx::umma_bf16_lohi(d_tmem, a_lo + a_step, b_lo + b_step, ptx::DESC_HI_SW128_SBO1024, idesc, 1u);
+          ptx::umma_bf16_lohi(d_tmem, a_lo + 2 * a_step, b_lo + 2 * b_step, ptx::DESC_HI_SW128_SBO1024, idesc, 1u);
+          ptx::umma_bf16_lohi(d_tmem, a_lo + 3 * a_step, b_lo + 3 * b_step, ptx::DESC_HI_SW128_SBO1024, idesc, 1u);
+          ptx::umma_commit(&empty_bar[stage]);       // frees the smem slot when these MMAs retire
+          if (kb == kb1 - 1) ptx::umma_commit(&tfull_bar[acc]);   // accumulator complete → epilogue
         }
-        ptx::umma_commit(&empty_bar[stage]);       // frees the smem stage when these MMAs retire
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      ptx::umma_commit(&tfull_bar[acc]);           // accumulator complete → epilogue
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (p.dbg && blockIdx.x == 0) { p.dbg[2] = w_full; p.dbg[3] = w_tempty; p.dbg[4] = clock64() - mma_t0; p.dbg[5] = ntiles; }
+    if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[2] = w_full; p.dbg[3] = w_tempty; p.dbg[4] = clock64() - mma_t0; p.dbg[5] = ntiles; }
   } else if (warp >= 4) {
     // ================= epilogue =================
     const int ge = (warp - 4) >> 2;                 // epilogue group = accumulator stage it drains
     const int q = warp & 3;                         // TMEM lane quarter
     const int row = q * 32 + lane;                  // row within the 128-row tile
-    const bool issuer = (warp == 4 + 4 * ge) && lane == 0;
-    uint8_t* stg_base = smem + SMEM_STAGING_OFF + ge * N_STG * STG_BYTES;
-    uint64_t* abar = aux_bar + ge * N_STG;
+    const bool issuer = (warp == 4 + 4 * ge) && lane == 0;   // lane 0 of the group's first warp owns the bulk-async groups
+    uint8_t* stg_base = smem + p.op_bytes + ge * N_STG * STG_BYTES;
+    uint64_t* abar = aux_bar + ge * 3;
     const int bar_id = 1 + ge;
     constexpr bool HAS_AUX = (EPI == T_RESID || EPI == T_DGELU);
     constexpr int AUX_BYTES = (EPI == T_RESID) ? BM * CHUNK * 4 : BM * CHUNK * 2;
@@ -278,13 +302,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
         uint8_t* stg = stg_base + b * STG_BYTES;
         uint32_t r[32];
         w0 = clock64();
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + ge * ACC_STRIDE + c * CHUNK, r);
-        ptx::tmem_ld_wait();
+        if (!(p.dbg_flags & 2)) {
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + ge * ACC_STRIDE + c * CHUNK, r);
+          ptx::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = 0;
+        }
         e_ld += clock64() - w0;
         if (c == N_CHUNKS - 1) {                    // accumulator fully read: hand the stage back to the MMA warp
           ptx::tc_fence_before();
           if (lane == 0) ptx::mbar_arrive(&tempty_bar[ge]);
         }
+        if (p.dbg_flags & 4) continue;
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -297,8 +327,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
             v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
           }
         }
-        // Buffer b is free here: its previous store (chunk cnt-3) was retired by the issuer's
-        // wait_group.read<1> after the store of chunk cnt-2, which precedes the barrier of chunk cnt-1.
+        // Buffer b is free here.  3-buffer rings: its previous store (chunk cnt-3) was retired by the
+        // issuer's wait_group.read<1> after the store of chunk cnt-2, which precedes the barrier of chunk
+        // cnt-1.  2-buffer rings: the issuer drains all stores before each barrier.
         if (HAS_AUX) {
           w0 = clock64();
           ptx::mbar_wait(&abar[b], (cnt / N_STG) & 1, p.err_flag, 5);
@@ -354,6 +385,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
                 make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         ptx::fence_proxy_async();
+        // two-buffer rings: the store of chunk cnt-1 must have left its buffer before anyone passes this
+        // barrier and starts writing chunk cnt+1 into it
+        if (N_STG == 2 && issuer) ptx::tma_wait_group_read<0>();
         w0 = clock64();
         ptx::bar_sync(bar_id, 128);
         e_bar += clock64() - w0;
@@ -364,8 +398,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
             if (write_u) ptx::tma_store_2d(&p.tmOut2[g], stg + 8192, col0, m0);
           }
           ptx::tma_commit_group();
-          ptx::tma_wait_group_read<1>();            // store of chunk cnt-1 has left its buffer
-          if (HAS_AUX) issue_aux(cnt + 2);          // ... which is the buffer of chunk cnt+2
+          if (N_STG == 3) ptx::tma_wait_group_read<1>();   // store of chunk cnt-1 has left its buffer
+          if (HAS_AUX) issue_aux(cnt + 2);                 // ... which is the buffer of chunk cnt+2
         }
       }
     }
@@ -394,6 +428,7 @@ EncodeTiledFn g_encode = nullptr;
 int* g_err_flag = nullptr;      // device int, allocated once at init (4 bytes; the only allocation)
 long long* g_dbg = nullptr;     // 32 counters, only with V2S_GEMM_DEBUG=1
 int g_num_sms = 148;
+int g_dbg_flags = 0;
 bool g_disabled = false;
 
 struct MapKey {
@@ -482,12 +517,28 @@ bool tc_enabled() { return g_encode != nullptr && !g_disabled; }
 namespace {
 
 template <int EPI, bool OUT_BF16>
-int launch_kernel(const TcParams& p, cudaStream_t stream) {
+int launch_kernel(TcParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    V2S_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI, OUT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    V2S_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI, OUT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set = true;
   }
+  // split the 227 KB between the operand ring and the epilogue staging ring of this variant
+  const int budget = SMEM_LIMIT - 1024 - SMEM_BAR_BYTES - Cfg<EPI, OUT_BF16>::STAGING_BYTES;
+  if (p.b_stationary) {
+    const int bres = p.kb_total * B_STAGE_BYTES;
+    int ring = (budget - bres) / A_STAGE_BYTES;
+    if (ring > MAX_STAGES) ring = MAX_STAGES;
+    p.stages = ring;
+    p.op_bytes = bres + ring * A_STAGE_BYTES;
+  } else {
+    int st = budget / STAGE_BYTES;
+    if (st > MAX_STAGES) st = MAX_STAGES;
+    p.stages = st;
+    p.op_bytes = st * STAGE_BYTES;
+  }
+  if (p.stages < 2) { set_error("gemm_tc: shared-memory budget leaves %d pipeline stages", p.stages); return 1; }
+  const int SMEM_TOTAL = p.op_bytes + Cfg<EPI, OUT_BF16>::STAGING_BYTES + SMEM_BAR_BYTES + 1024;
   int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   if (p.b_stationary) grid = p.groups * p.tiles_n * p.ctas_per_combo;
   gemm_tc_kernel<EPI, OUT_BF16><<<grid, N_THREADS, SMEM_TOTAL, stream>>>(p);
@@ -513,6 +564,7 @@ int gemm_tc_init() {
   V2S_CUDA_OK(cudaMalloc(&g_err_flag, sizeof(int)));
   V2S_CUDA_OK(cudaMemset(g_err_flag, 0, sizeof(int)));
   if (getenv("V2S_GEMM_DEBUG")) {
+    g_dbg_flags = atoi(getenv("V2S_GEMM_DEBUG"));
     V2S_CUDA_OK(cudaMalloc(&g_dbg, 32 * sizeof(long long)));
     V2S_CUDA_OK(cudaMemset(g_dbg, 0, 32 * sizeof(long long)));
   }
@@ -588,6 +640,7 @@ int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t strea
   }
   p.err_flag = g_err_flag;
   p.dbg = g_dbg;
+  p.dbg_flags = g_dbg_flags;
   const CUtensorMapSwizzle out_swz = out_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   for (int g = 0; g < d.groups; ++g) {
     if (!a_mn) V2S_TRY(get_map(&p.tmA[g], d.A[g], d.K, d.M, a_ld, BK, BM, true, CU_TENSOR_MAP_SWIZZLE_128B));
