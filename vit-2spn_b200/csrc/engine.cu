@@ -394,13 +394,26 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
 
   const int split = wgrad_split(M);
   // dW[N_out, K_in] += dY[M, N_out]^T * X[M, K_in]   (token dimension is the reduction)
-  auto wgrad = [&](void* const* dy, int n_out, void* const* x, int k_in, int64_t goff, bool remap) -> int {
+  // bias_goff >= 0: also accumulate the bias gradient (column sums of dY) — inside the tensor-core wgrad
+  // kernel (extra N=16 MMA against a ones tile), or with the column-sum kernel on the SIMT path
+  const bool tc = at == 1 && tc_enabled();
+  auto wgrad = [&](void* const* dy, int n_out, void* const* x, int k_in, int64_t goff, bool remap,
+                   int64_t bias_goff = -1) -> int {
+    if (bias_goff >= 0 && !tc) {
+      const void* src[MAXG]; float* dst[MAXG];
+      for (int g = 0; g < G; ++g) { src[g] = dy[g]; dst[g] = gs[g].grads + bias_goff; }
+      prof::Scope sc(prof::C_COLSUM, (double)M * n_out * p.es * G, st);
+      V2S_TRY(launch_colsum(src, dst, G, (int)M, n_out, at, st));
+    }
     GemmDesc d = make_gemm_desc();
     d.M = n_out; d.N = k_in; d.K = remap ? (int)MP : (int)M; d.groups = G;
     d.a_rs = 1; d.a_cs = n_out; d.b_rs = k_in; d.b_cs = 1;
     d.a_remap = remap ? 2 : 0;
     d.epi = EPI_ACCUM; d.ldc = k_in; d.split_k = split;
-    for (int g = 0; g < G; ++g) { d.A[g] = dy[g]; d.B[g] = x[g]; d.out[g] = gs[g].grads + goff; }
+    for (int g = 0; g < G; ++g) {
+      d.A[g] = dy[g]; d.B[g] = x[g]; d.out[g] = gs[g].grads + goff;
+      d.rowsum_out[g] = (bias_goff >= 0 && tc) ? gs[g].grads + bias_goff : nullptr;
+    }
     return run_gemm(d, at, at, 0, st, prof::C_WGRAD);
   };
   // dX[M, K_in] = dY[M, N_out] * W[N_out, K_in]
@@ -435,8 +448,7 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
     V2S_TRY(wgrad(dxlp, D, h, DF, lo + L_W2, false));                      // dW2 [192,768]
     if (l == NL - 1) V2S_TRY(bias_grad(dxlp, D, lo + L_B2));               // lower blocks: fused into LN1-bwd above
     V2S_TRY(dgrad(dxlp, D, lo + L_W2, DF, big, EPI_DGELU, u));             // du = (dx W2) * gelu'(u)
-    V2S_TRY(wgrad(big, DF, xn2, D, lo + L_W1, false));                     // dW1 [768,192]
-    V2S_TRY(bias_grad(big, DF, lo + L_B1));
+    V2S_TRY(wgrad(big, DF, xn2, D, lo + L_W1, false, lo + L_B1));          // dW1 [768,192] and d b1
     V2S_TRY(dgrad(big, DF, lo + L_W1, D, tmp, EPI_STORE, nullptr));        // d xn2
     {
       const void* dy[MAXG]; const float *x[MAXG], *mu[MAXG], *rs[MAXG], *gm[MAXG];
@@ -458,8 +470,7 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
       for (int g = 0; g < G; ++g) { cq[g] = qkv[g]; cc[g] = ctx[g]; cd[g] = tmp[g]; ls[g] = (const float*)sb(g, s.lse); }
       V2S_TRY(launch_attention_bwd(cq, cc, ls, cd, big, G, B, at, st));    // d qkv in `big` [M,576]
     }
-    V2S_TRY(wgrad(big, 3 * D, xn1, D, lo + L_WQKV, false));                // dWqkv [576,192]
-    V2S_TRY(bias_grad(big, 3 * D, lo + L_BQKV));
+    V2S_TRY(wgrad(big, 3 * D, xn1, D, lo + L_WQKV, false, lo + L_BQKV));   // dWqkv [576,192] and d b_qkv
     V2S_TRY(dgrad(big, 3 * D, lo + L_WQKV, D, tmp, EPI_STORE, nullptr));   // d xn1
     {
       const void* dy[MAXG]; const float *x[MAXG], *mu[MAXG], *rs[MAXG], *gm[MAXG];

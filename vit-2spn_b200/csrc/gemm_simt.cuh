@@ -33,6 +33,7 @@ struct GemmDesc {
   const float* mask[MAXG];
   void* out[MAXG];
   void* out2[MAXG];
+  float* rowsum_out[MAXG];  // EPI_ACCUM, tensor-core path only: rowsum_out[m] += sum_k A(m,k) (bias gradient for free)
   int64_t ldc;
   float alpha;
 };

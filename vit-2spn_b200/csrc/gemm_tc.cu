@@ -31,7 +31,7 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int CHUNK = 32;                         // epilogue column chunk
 constexpr int N_CHUNKS = BN / CHUNK;              // 6
 constexpr int SMEM_LIMIT = 232448;                // 227 KB opt-in maximum per CTA
-constexpr int SMEM_BAR_BYTES = 512;
+constexpr int SMEM_BAR_BYTES = 3072;             // mbarriers (first 1 KB) + 2 KB constant ones tile for the row-sum MMA
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;                   // TMEM column stride between accumulator stages
 constexpr int N_THREADS = 384;
@@ -56,6 +56,7 @@ template <int EPI, bool OUT_BF16> struct Cfg {
 struct alignas(64) TcParams {
   CUtensorMap tmA[MAXG], tmB[MAXG], tmOut[MAXG], tmOut2[MAXG], tmAux[MAXG];
   const float* bias[MAXG];
+  float* rowsum[MAXG];  // T_ACCUM: rowsum[m] += sum_k A(m,k), computed by an extra N=16 MMA against a ones tile
   int M, N, K;
   int tiles_m, tiles_n, splits, kb_total, kb_per_split, groups, total_tiles;
   int a_mn, b_mn;
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
   uint64_t* aux_bar = tempty_bar + 2;            // [2][3] per epilogue group and staging buffer: aux chunk landed
   uint64_t* bres_bar = aux_bar + 6;              // B-stationary tile landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
+  uint8_t* ones_tile = reinterpret_cast<uint8_t*>(full_bar) + 1024;   // [16 rows x 128 B] K-major: row 0 = 1.0, rows 1..15 = 0
 
   // warp index through a shuffle: tells the compiler it is warp-uniform, so that the single-thread
   // roles below compile to straight uniform-datapath code (no per-lane convergence loops around TMA / MMA)
@@ -134,6 +136,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
   if (warp == 2) {
     ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
     ptx::tmem_relinquish();
+  }
+  if (EPI == T_ACCUM && warp == 3) {
+    // bf16 1.0 = 0x3F80; the swizzle only permutes 16-byte chunks inside a row, so a constant row is layout-proof
+    for (int i = lane; i < 2048 / 4; i += 32)
+      reinterpret_cast<uint32_t*>(ones_tile)[i] = (i < 32) ? 0x3F803F80u : 0u;
+    ptx::fence_proxy_async();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -226,6 +234,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     const uint32_t a_slot0 = p.b_stationary ? p.kb_total * B_STAGE_BYTES : 0, a_slot_stride = p.b_stationary ? A_STAGE_BYTES : STAGE_BYTES;
     const uint32_t b_slot0 = p.b_stationary ? 0 : A_STAGE_BYTES, b_slot_stride = p.b_stationary ? B_STAGE_BYTES : STAGE_BYTES;
     const uint32_t a_lo0 = ptx::desc_lo(smem_base + a_slot0, a_lbo), b_lo0 = ptx::desc_lo(smem_base + b_slot0, b_lbo);
+    const uint32_t idesc_rs = ptx::make_idesc_bf16(BM, 16, p.a_mn, 0);
+    const uint32_t ones_lo = ptx::desc_lo(ptx::smem_u32(ones_tile), 16);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     int g, m_tile, split, n_tile;
@@ -251,6 +261,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
           ptx::umma_bf16_lohi(d_tmem, a_lo + a_step, b_lo + b_step, ptx::DESC_HI_SW128_SBO1024, idesc, 1u);
           ptx::umma_bf16_lohi(d_tmem, a_lo + 2 * a_step, b_lo + 2 * b_step, ptx::DESC_HI_SW128_SBO1024, idesc, 1u);
           ptx::umma_bf16_lohi(d_tmem, a_lo + 3 * a_step, b_lo + 3 * b_step, ptx::DESC_HI_SW128_SBO1024, idesc, 1u);
+          if (EPI == T_ACCUM && n_tile == 0 && p.rowsum[g] != nullptr) {
+            // row sums of A (= bias gradient in a wgrad) into accumulator columns [192,208): A x ones
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_bf16_lohi(d_tmem + BN, a_lo + k * a_step, ones_lo, ptx::DESC_HI_SW128_SBO1024, idesc_rs,
+                                  (kb > kb0 || k > 0) ? 1u : 0u);
+          }
           ptx::umma_commit(&empty_bar[stage]);       // frees the smem slot when these MMAs retire
           if (kb == kb1 - 1) ptx::umma_commit(&tfull_bar[acc]);   // accumulator complete → epilogue
         }
@@ -311,6 +328,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
         }
         e_ld += clock64() - w0;
         if (c == N_CHUNKS - 1) {                    // accumulator fully read: hand the stage back to the MMA warp
+          if (EPI == T_ACCUM && n_tile == 0 && p.rowsum[g] != nullptr) {
+            uint32_t rs[16];
+            ptx::tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + ge * ACC_STRIDE + BN, rs);
+            ptx::tmem_ld_wait();
+            if (m0 + row < p.M) atomicAdd(p.rowsum[g] + m0 + row, __uint_as_float(rs[0]));
+          }
           ptx::tc_fence_before();
           if (lane == 0) ptx::mbar_arrive(&tempty_bar[ge]);
         }
@@ -656,6 +679,7 @@ int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t strea
     if (epi == T_RESID) V2S_TRY(get_map(&p.tmAux[g], d.resid[g], d.N, d.M, d.ldc, CHUNK, BM, false, CU_TENSOR_MAP_SWIZZLE_128B));
     if (epi == T_DGELU) V2S_TRY(get_map(&p.tmAux[g], d.aux[g], d.N, d.M, d.ldc, CHUNK, BM, true, CU_TENSOR_MAP_SWIZZLE_64B));
     p.bias[g] = (epi == T_ACCUM || epi == T_DGELU) ? nullptr : d.bias[g];
+    p.rowsum[g] = (epi == T_ACCUM) ? d.rowsum_out[g] : nullptr;
   }
   int rc;
   switch (epi) {

@@ -71,6 +71,7 @@ class FlatStore:
         self.flat_lp = None
         self._grad_views = None
         self.lp_fresh = False        # set by the fused Adam / EMA kernels that refresh the shadow
+        self._ver = -1
         self.reflatten()
         _STORES.add(self)
 
@@ -106,9 +107,19 @@ class FlatStore:
         if self.flat_lp is None or self.flat_lp.device != self.flat.device:
             self.flat_lp = torch.empty(self.numel, dtype=torch.bfloat16, device=self.flat.device)
             self.lp_fresh = False
-        if refresh and not self.lp_fresh:
+        if refresh and not (self.lp_fresh and self._ver == self._version_sum()):
             check(lib.v2s_cast_bf16(ptr(self.flat), ptr(self.flat_lp), self.numel, stream_ptr()), "cast_bf16")
+            self.lp_fresh = False
         return self.flat_lp
+
+    def _version_sum(self):
+        # in-place updates through torch (optimizers, load_state_dict, p.add_()) bump Parameter._version;
+        # the library's own Adam / EMA kernels refresh the shadow themselves and call mark_lp_fresh()
+        return sum(p._version for p in self.params)
+
+    def mark_lp_fresh(self):
+        self.lp_fresh = True
+        self._ver = self._version_sum()
 
     def grads(self):
         """Flat gradient buffer; (re)attaches ``p.grad`` views.  After ``zero_grad(set_to_none=True)``
@@ -594,6 +605,8 @@ class DualStreamNetwork(nn.Module):
         lp = (C.c_void_p * 2)(st[2].lp(refresh=False).data_ptr(), st[3].lp(refresh=False).data_ptr())
         m = globals().get("momentum", 0.999) if self.momentum is None else self.momentum
         check(lib.v2s_ema_update(tg, on, lp, 2, n, float(m), stream_ptr()), "ema_update")
+        st[2].mark_lp_fresh()
+        st[3].mark_lp_fresh()
 
     # -- fused native step (no autograd graph): fwd + loss + bwd in the library --------------
     def ssp_step(self, x1, x2, accumulation_steps=1, grad_scale=1.0, with_backward=True):

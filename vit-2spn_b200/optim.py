@@ -92,8 +92,14 @@ class FusedAdam(torch.optim.Optimizer):
                 launches.setdefault(step + 1, []).append(r)
                 for p, _ in active:
                     self.state[p]["step"] += 1
-                if lp is not None:
-                    store.lp_fresh = True
+                if lp is not None and store.active_numel == store.numel or lp is not None and getattr(store, "_lp_tail_ok", False):
+                    store.mark_lp_fresh()
+                elif lp is not None:
+                    # the kernel refreshes only the trained prefix; the never-trained tail (final LN, pooler)
+                    # is constant, so one full cast makes every later refresh complete
+                    store.lp(refresh=True)
+                    store._lp_tail_ok = True
+                    store.mark_lp_fresh()
             for p in with_grad:
                 if id(p) in covered:
                     continue
