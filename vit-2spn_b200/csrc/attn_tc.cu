@@ -24,6 +24,13 @@ constexpr int P_TILE_BYTES = 4 * QT * 128;     // 65536: four 64-key column bloc
 constexpr float SCALE = 0.125f;                // 64^-0.5
 constexpr float SCALE_LOG2E = 0.125f * 1.4426950408889634f;
 
+// one UMMA with SWIZZLE_128B operands given by smem address + leading-dimension byte offset (SBO = 1024)
+__device__ __forceinline__ void mma(uint32_t d_tmem, uint32_t a_addr, uint32_t a_lbo, uint32_t b_addr, uint32_t b_lbo,
+                                    uint32_t idesc, bool accumulate) {
+  ptx::umma_bf16_lohi(d_tmem, ptx::desc_lo(a_addr, a_lbo), ptx::desc_lo(b_addr, b_lbo), ptx::DESC_HI_SW128_SBO1024,
+                      idesc, accumulate ? 1u : 0u);
+}
+
 // ---- forward --------------------------------------------------------------------------------
 constexpr int F_OFF_Q = 0;                                  // 2 tiles
 constexpr int F_OFF_K = 2 * Q_TILE_BYTES;                   // 32768
@@ -60,7 +67,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) attn_fwd_tc_kernel(const __grid_
   uint64_t* bar_o = bar_p + 2;        // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_o + 2);
   const int h = blockIdx.x, b = blockIdx.y, g = blockIdx.z;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
 
   if (warp == 0) {
     if (lane == 0) {
@@ -75,40 +82,46 @@ __global__ void __launch_bounds__(F_THREADS, 1) attn_fwd_tc_kernel(const __grid_
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    // control warp: every lane walks the same path and waits on the barriers; one elected lane issues
+    if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(bar_load, 2 * Q_TILE_BYTES + 2 * KV_TILE_BYTES);
       ptx::tma_load_3d(smem + F_OFF_Q, &p.tmQ[g], bar_load, h * DH, 0, b);
       ptx::tma_load_3d(smem + F_OFF_Q + Q_TILE_BYTES, &p.tmQ[g], bar_load, h * DH, QT, b);
       ptx::tma_load_3d(smem + F_OFF_K, &p.tmKV[g], bar_load, D + h * DH, 0, b);
       ptx::tma_load_3d(smem + F_OFF_V, &p.tmKV[g], bar_load, 2 * D + h * DH, 0, b);
-      ptx::mbar_wait(bar_load, 0, p.err_flag, 11);
-      ptx::tc_fence_after();
-      const uint32_t idesc_s = ptx::make_idesc_bf16(QT, KPAD, 0, 0);
-      const uint32_t sk = ptx::smem_u32(smem + F_OFF_K);
-      for (int t = 0; t < 2; ++t) {
-        const uint32_t sq = ptx::smem_u32(smem + F_OFF_Q + t * Q_TILE_BYTES);
+    }
+    __syncwarp();
+    ptx::mbar_wait(bar_load, 0, p.err_flag, 11);
+    ptx::tc_fence_after();
+    const uint32_t idesc_s = ptx::make_idesc_bf16(QT, KPAD, 0, 0);
+    const uint32_t idesc_o = ptx::make_idesc_bf16(QT, DH, 0, 1);
+    const uint32_t sbase = ptx::smem_u32(smem);
+    const uint32_t sk = sbase + F_OFF_K, sv = sbase + F_OFF_V;
+    if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
-          ptx::umma_bf16(tmem_base + t * 256, ptx::make_smem_desc(sq + k * 32, 16, 1024),
-                         ptx::make_smem_desc(sk + k * 32, 16, 1024), idesc_s, k > 0);
+      for (int t = 0; t < 2; ++t) {
+        const uint32_t sq = sbase + F_OFF_Q + t * Q_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) mma(tmem_base + t * 256, sq + k * 32, 16, sk + k * 32, 16, idesc_s, k > 0);
         ptx::umma_commit(&bar_s[t]);
       }
-      const uint32_t idesc_o = ptx::make_idesc_bf16(QT, DH, 0, 1);
-      const uint32_t sv = ptx::smem_u32(smem + F_OFF_V);
-      for (int t = 0; t < 2; ++t) {
-        ptx::mbar_wait(&bar_p[t], 0, p.err_flag, 12);
-        ptx::tc_fence_after();
-        const uint32_t sp = ptx::smem_u32(smem + F_OFF_P + t * P_TILE_BYTES);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      ptx::mbar_wait(&bar_p[t], 0, p.err_flag, 12);
+      ptx::tc_fence_after();
+      const uint32_t sp = sbase + F_OFF_P + t * P_TILE_BYTES;
+      if (ptx::elect_one()) {
 #pragma unroll
         for (int j = 0; j < KPAD / 16; ++j)
-          ptx::umma_bf16(tmem_base + t * 256,
-                         ptx::make_smem_desc(sp + (j >> 2) * (QT * 128) + (j & 3) * 32, 16, 1024),
-                         ptx::make_smem_desc(sv + j * 2048, 8192, 1024), idesc_o, j > 0);
+          mma(tmem_base + t * 256, sp + (j >> 2) * (QT * 128) + (j & 3) * 32, 16, sv + j * 2048, 8192, idesc_o, j > 0);
         ptx::umma_commit(&bar_o[t]);
       }
+      __syncwarp();
     }
   } else {
     const int t = (warp - 1) >> 2;              // query tile
@@ -251,7 +264,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
   uint64_t* bar_free = bar_kv + 2;    // [1] count 256: tile-0 buffers and TMEM[0,208) reusable
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_free + 1);
   const int h = blockIdx.x, b = blockIdx.y, g = blockIdx.z;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
 
   if (warp == 0) {
     if (lane == 0) {
@@ -280,21 +293,23 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t sq = ptx::smem_u32(smem + B_OFF_Q), sdo = ptx::smem_u32(smem + B_OFF_DO);
-      const uint32_t sk = ptx::smem_u32(smem + B_OFF_K), sv = ptx::smem_u32(smem + B_OFF_V);
-      const uint32_t sp = ptx::smem_u32(smem + B_OFF_P), sds = ptx::smem_u32(smem + B_OFF_DS);
-      const uint32_t idesc_s = ptx::make_idesc_bf16(QT, KPAD, 0, 0);
-      const uint32_t idesc_dq = ptx::make_idesc_bf16(QT, DH, 0, 1);
-      const uint32_t idesc_kv = ptx::make_idesc_bf16(QT, DH, 1, 1);
-      for (int t = 0; t < 2; ++t) {
-        if (t == 1) {
-          ptx::mbar_wait(&bar_kv[0], 0, p.err_flag, 21);     // tile-0 MMAs no longer read Q/dO/P/dS
-          ptx::mbar_wait(bar_free, 0, p.err_flag, 22);       // dQ_0 drained, staging store done
-        }
+    // control warp: every lane walks the same path and waits on the barriers; one elected lane issues
+    const uint32_t sbase = ptx::smem_u32(smem);
+    const uint32_t sq = sbase + B_OFF_Q, sdo = sbase + B_OFF_DO, sk = sbase + B_OFF_K, sv = sbase + B_OFF_V;
+    const uint32_t sp = sbase + B_OFF_P, sds = sbase + B_OFF_DS;
+    const uint32_t idesc_s = ptx::make_idesc_bf16(QT, KPAD, 0, 0);
+    const uint32_t idesc_dq = ptx::make_idesc_bf16(QT, DH, 0, 1);
+    const uint32_t idesc_kv = ptx::make_idesc_bf16(QT, DH, 1, 1);
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t) {
+      if (t == 1) {
+        ptx::mbar_wait(&bar_kv[0], 0, p.err_flag, 21);     // tile-0 MMAs no longer read Q/dO/P/dS
+        ptx::mbar_wait(bar_free, 0, p.err_flag, 22);       // dQ_0 drained, staging store done
+      }
+      if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(&bar_load[t], 2 * Q_TILE_BYTES + (t == 0 ? 2 * KV_TILE_BYTES : 0));
         ptx::tma_load_3d(smem + B_OFF_Q, &p.tmQ[g], &bar_load[t], h * DH, t * QT, b);
         ptx::tma_load_3d(smem + B_OFF_DO, &p.tmDO[g], &bar_load[t], h * DH, t * QT, b);
@@ -302,44 +317,48 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
           ptx::tma_load_3d(smem + B_OFF_K, &p.tmKV[g], &bar_load[t], D + h * DH, 0, b);
           ptx::tma_load_3d(smem + B_OFF_V, &p.tmKV[g], &bar_load[t], 2 * D + h * DH, 0, b);
         }
-        ptx::mbar_wait(&bar_load[t], 0, p.err_flag, 23);
-        ptx::tc_fence_after();
-        // S = Q_t K^T
+      }
+      __syncwarp();
+      ptx::mbar_wait(&bar_load[t], 0, p.err_flag, 23);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {      // S = Q_t K^T
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
-          ptx::umma_bf16(tmem_base, ptx::make_smem_desc(sq + k * 32, 16, 1024),
-                         ptx::make_smem_desc(sk + k * 32, 16, 1024), idesc_s, k > 0);
+        for (int k = 0; k < DH / 16; ++k) mma(tmem_base, sq + k * 32, 16, sk + k * 32, 16, idesc_s, k > 0);
         ptx::umma_commit(&bar_s[t]);
-        // P ready → dP = dO_t V^T (over S's columns) and dV += P^T dO_t
-        ptx::mbar_wait(&bar_p[t], 0, p.err_flag, 24);
-        ptx::tc_fence_after();
+      }
+      __syncwarp();
+      // P ready → dP = dO_t V^T (over S's columns) and dV += P^T dO_t
+      ptx::mbar_wait(&bar_p[t], 0, p.err_flag, 24);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
-          ptx::umma_bf16(tmem_base, ptx::make_smem_desc(sdo + k * 32, 16, 1024),
-                         ptx::make_smem_desc(sv + k * 32, 16, 1024), idesc_s, k > 0);
+        for (int k = 0; k < DH / 16; ++k) mma(tmem_base, sdo + k * 32, 16, sv + k * 32, 16, idesc_s, k > 0);
         ptx::umma_commit(&bar_dp[t]);
+#pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
           for (int k = 0; k < QT / 16; ++k)
-            ptx::umma_bf16(tmem_base + TM_DV + mt * DH,
-                           ptx::make_smem_desc(sp + 2 * mt * (QT * 128) + k * 2048, QT * 128, 1024),
-                           ptx::make_smem_desc(sdo + k * 2048, 8192, 1024), idesc_kv, (t > 0 || k > 0));
-        // dS ready → dQ_t = dS K (over dP's columns) and dK += dS^T Q_t
-        ptx::mbar_wait(&bar_ds[t], 0, p.err_flag, 25);
-        ptx::tc_fence_after();
+            mma(tmem_base + TM_DV + mt * DH, sp + 2 * mt * (QT * 128) + k * 2048, QT * 128, sdo + k * 2048, 8192,
+                idesc_kv, (t > 0 || k > 0));
+      }
+      __syncwarp();
+      // dS ready → dQ_t = dS K (over dP's columns) and dK += dS^T Q_t
+      ptx::mbar_wait(&bar_ds[t], 0, p.err_flag, 25);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
 #pragma unroll
         for (int j = 0; j < KPAD / 16; ++j)
-          ptx::umma_bf16(tmem_base, ptx::make_smem_desc(sds + (j >> 2) * (QT * 128) + (j & 3) * 32, 16, 1024),
-                         ptx::make_smem_desc(sk + j * 2048, 8192, 1024), idesc_dq, j > 0);
+          mma(tmem_base, sds + (j >> 2) * (QT * 128) + (j & 3) * 32, 16, sk + j * 2048, 8192, idesc_dq, j > 0);
         ptx::umma_commit(&bar_dq[t]);
+#pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
           for (int k = 0; k < QT / 16; ++k)
-            ptx::umma_bf16(tmem_base + TM_DK + mt * DH,
-                           ptx::make_smem_desc(sds + 2 * mt * (QT * 128) + k * 2048, QT * 128, 1024),
-                           ptx::make_smem_desc(sq + k * 2048, 8192, 1024), idesc_kv, (t > 0 || k > 0));
+            mma(tmem_base + TM_DK + mt * DH, sds + 2 * mt * (QT * 128) + k * 2048, QT * 128, sq + k * 2048, 8192,
+                idesc_kv, (t > 0 || k > 0));
         ptx::umma_commit(&bar_kv[t]);
       }
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;                      // TMEM lane quarter
