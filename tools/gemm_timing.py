@@ -13,7 +13,9 @@ dev = torch.device("cuda:0")
 
 
 def run(which, m, n, k, label):
-    if which == 0:
+    if which == 3:
+        a = torch.randn(m, k, device=dev).bfloat16(); b = torch.randn(n, k, device=dev).bfloat16(); c = torch.empty(m, n, device=dev, dtype=torch.float32)
+    elif which == 0:
         a = torch.randn(m, k, device=dev).bfloat16(); b = torch.randn(n, k, device=dev).bfloat16(); c = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
     elif which == 1:
         a = torch.randn(m, k, device=dev).bfloat16(); b = torch.randn(k, n, device=dev).bfloat16(); c = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
@@ -40,6 +42,9 @@ def run(which, m, n, k, label):
 
 print("V2S_GEMM_DEBUG =", os.environ["V2S_GEMM_DEBUG"])
 run(0, 4 * 25216, 576, 192, "qkv fwd x4 (NT)")
+run(3, 4 * 25216, 576, 192, "qkv x4 fp32 out")
+run(0, 8 * 25216, 576, 192, "qkv fwd x8 (NT)")
+run(3, 8 * 25216, 576, 192, "qkv x8 fp32 out")
 run(0, 25216, 576, 192, "qkv fwd (NT)")
 run(0, 25216, 768, 192, "fc1-like (NT, plain store)")
 run(0, 25216, 192, 768, "fc2-like (NT, plain store)")

@@ -4,10 +4,10 @@
 //
 //   C[M,N] (+)= A[M,K] * B[N,K]^T        A, B: K-major or MN-major (UMMA descriptor major bits)
 //
-// CTA = 384 threads: warp 0 TMA producer, warp 1 MMA issuer (single thread), warp 2 TMEM allocator,
-// warps 4..11 epilogue: two groups of four warps (a warp reads TMEM lane quarter warp%4); group g
-// drains the accumulator stage g, i.e. the CTA's even / odd tiles, so two epilogues and the MMAs of
-// a third tile overlap.  Each group walks its 128x192 accumulator in six 32-column chunks through a
+// CTA = 640 threads: warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warp 2 TMEM allocator,
+// warps 4..19 epilogue: two groups of eight warps (warps w, w+4 of a group read TMEM lane quarter w%4 and
+// take the two 16-column halves of a chunk); group g drains accumulator stage g, i.e. the CTA's even /
+// odd tiles, so two epilogues and the MMAs of a third tile overlap.  Each group walks its 128x192 accumulator in six 32-column chunks through a
 // ring of three 16 KB staging buffers: [TMA-load the auxiliary operand (residual / pre-GELU) into
 // the buffer] -> thread-per-row math in place -> TMA store (or reduce-add) out of the same buffer.
 // Tile = 128 x 192 x 64; 3-stage smem ring (A 16 KB + B 24 KB per stage); 2 accumulator stages in
@@ -34,7 +34,7 @@ constexpr int SMEM_LIMIT = 232448;                // 227 KB opt-in maximum per C
 constexpr int SMEM_BAR_BYTES = 3072;             // mbarriers (first 1 KB) + 2 KB constant ones tile for the row-sum MMA
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;                   // TMEM column stride between accumulator stages
-constexpr int N_THREADS = 384;
+constexpr int N_THREADS = 640;                    // 4 control/idle warps + 16 epilogue warps
 
 enum TcEpi : int {
   T_STORE = 0,   // out = acc (+bias)            OutT = bf16 | fp32
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], 4); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], 8); }
     for (int s = 0; s < 6; ++s) ptx::mbar_init(&aux_bar[s], 1);
     ptx::mbar_init(bres_bar, 1);
     ptx::fence_barrier_init();
@@ -279,10 +279,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[2] = w_full; p.dbg[3] = w_tempty; p.dbg[4] = clock64() - mma_t0; p.dbg[5] = ntiles; }
   } else if (warp >= 4) {
     // ================= epilogue =================
-    const int ge = (warp - 4) >> 2;                 // epilogue group = accumulator stage it drains
+    // 16 warps = 2 groups of 8.  Group ge drains accumulator stage ge.  Inside a group, warps w and w+4 share
+    // TMEM lane quarter w%4 and split every 32-column chunk into two 16-column halves (thread = one row x 16 cols).
+    const int ge = (warp - 4) >> 3;                 // epilogue group = accumulator stage it drains
     const int q = warp & 3;                         // TMEM lane quarter
+    const int hf = ((warp - 4) >> 2) & 1;           // column half of the chunk
     const int row = q * 32 + lane;                  // row within the 128-row tile
-    const bool issuer = (warp == 4 + 4 * ge) && lane == 0;   // lane 0 of the group's first warp owns the bulk-async groups
+    const bool issuer = (warp == 4 + 8 * ge) && lane == 0;   // owns the group's bulk-async (TMA store) groups
     uint8_t* stg_base = smem + p.op_bytes + ge * N_STG * STG_BYTES;
     uint64_t* abar = aux_bar + ge * 3;
     const int bar_id = 1 + ge;
@@ -305,32 +308,34 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     int g, m_tile, split, n_tile;
     for (int i = ge; tile_at(i, g, m_tile, split, n_tile); i += 2) {
       const int m0 = m_tile * BM, n0 = n_tile * BN;
-      long long w0 = clock64();
+      long long w0 = p.dbg ? clock64() : 0;
       ptx::mbar_wait(&tfull_bar[ge], acc_phase, p.err_flag, 4);
-      e_tfull += clock64() - w0;
+      if (p.dbg) e_tfull += clock64() - w0;
       acc_phase ^= 1;
       ptx::tc_fence_after();
       const bool write_u = (EPI == T_GELU) && ((p.out2_mask >> g) & 1);
       const float* bias = (EPI != T_ACCUM && EPI != T_DGELU) ? p.bias[g] : nullptr;
+      const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + ge * ACC_STRIDE;
 #pragma unroll 1
       for (int c = 0; c < N_CHUNKS; ++c, ++cnt) {
-        const int col0 = n0 + c * CHUNK;
+        const int col0 = n0 + c * CHUNK;            // first column of the chunk
+        const int colh = col0 + hf * 16;            // first column of this thread's half
         const int b = cnt % N_STG;
         uint8_t* stg = stg_base + b * STG_BYTES;
-        uint32_t r[32];
-        w0 = clock64();
+        uint32_t r[16];
+        if (p.dbg) w0 = clock64();
         if (!(p.dbg_flags & 2)) {
-          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + ge * ACC_STRIDE + c * CHUNK, r);
+          ptx::tmem_ld_32x16(tlane + c * CHUNK + hf * 16, r);
           ptx::tmem_ld_wait();
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = 0;
+          for (int k = 0; k < 16; ++k) r[k] = 0;
         }
-        e_ld += clock64() - w0;
+        if (p.dbg) e_ld += clock64() - w0;
         if (c == N_CHUNKS - 1) {                    // accumulator fully read: hand the stage back to the MMA warp
-          if (EPI == T_ACCUM && n_tile == 0 && p.rowsum[g] != nullptr) {
+          if (EPI == T_ACCUM && hf == 0 && n_tile == 0 && p.rowsum[g] != nullptr) {
             uint32_t rs[16];
-            ptx::tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + ge * ACC_STRIDE + BN, rs);
+            ptx::tmem_ld_32x16(tlane + BN, rs);
             ptx::tmem_ld_wait();
             if (m0 + row < p.M) atomicAdd(p.rowsum[g] + m0 + row, __uint_as_float(rs[0]));
           }
@@ -338,36 +343,37 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
           if (lane == 0) ptx::mbar_arrive(&tempty_bar[ge]);
         }
         if (p.dbg_flags & 4) continue;
-        float v[32];
+        float v[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]);
         if (bias != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
+          const float4* b4 = reinterpret_cast<const float4*>(bias + colh);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int k = 0; k < 4; ++k) {
             float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col0 + 4 * i < p.N) bb = __ldg(b4 + i);
-            v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+            if (colh + 4 * k < p.N) bb = __ldg(b4 + k);
+            v[4 * k] += bb.x; v[4 * k + 1] += bb.y; v[4 * k + 2] += bb.z; v[4 * k + 3] += bb.w;
           }
         }
         // Buffer b is free here.  3-buffer rings: its previous store (chunk cnt-3) was retired by the
         // issuer's wait_group.read<1> after the store of chunk cnt-2, which precedes the barrier of chunk
         // cnt-1.  2-buffer rings: the issuer drains all stores before each barrier.
+        // fp32 rows are 128 B (8 x 16-B pieces, SWIZZLE_128B), bf16 rows 64 B (4 pieces, SWIZZLE_64B)
         if (HAS_AUX) {
-          w0 = clock64();
+          if (p.dbg) w0 = clock64();
           ptx::mbar_wait(&abar[b], (cnt / N_STG) & 1, p.err_flag, 5);
-          e_aux += clock64() - w0;
+          if (p.dbg) e_aux += clock64() - w0;
           if (EPI == T_RESID) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4* slot = reinterpret_cast<float4*>(stg + row * 128 + ((j ^ (row & 7)) << 4));
+            for (int j = 0; j < 4; ++j) {
+              float4* slot = reinterpret_cast<float4*>(stg + row * 128 + (((hf * 4 + j) ^ (row & 7)) << 4));
               const float4 a = *slot;
               *slot = make_float4(v[4 * j] + a.x, v[4 * j + 1] + a.y, v[4 * j + 2] + a.z, v[4 * j + 3] + a.w);
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4* slot = reinterpret_cast<uint4*>(stg + row * 64 + ((j ^ ((row >> 1) & 3)) << 4));
+            for (int j = 0; j < 2; ++j) {
+              uint4* slot = reinterpret_cast<uint4*>(stg + row * 64 + (((hf * 2 + j) ^ ((row >> 1) & 3)) << 4));
               const uint4 a = *slot;
               const uint32_t w[4] = {a.x, a.y, a.z, a.w};
               uint32_t o[4];
@@ -384,36 +390,36 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
           if (EPI == T_GELU) {
             if (write_u) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
+              for (int j = 0; j < 2; ++j) {
                 uint4 o;
                 o.x = pack_bf16(v[8 * j], v[8 * j + 1]); o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
                 o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-                *reinterpret_cast<uint4*>(stg + 8192 + row * 64 + ((j ^ ((row >> 1) & 3)) << 4)) = o;
+                *reinterpret_cast<uint4*>(stg + 8192 + row * 64 + (((hf * 2 + j) ^ ((row >> 1) & 3)) << 4)) = o;
               }
             }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+            for (int k = 0; k < 16; ++k) v[k] = gelu_fast(v[k]);
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 2; ++j) {
             uint4 o;
             o.x = pack_bf16(v[8 * j], v[8 * j + 1]); o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
             o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-            *reinterpret_cast<uint4*>(stg + row * 64 + ((j ^ ((row >> 1) & 3)) << 4)) = o;
+            *reinterpret_cast<uint4*>(stg + row * 64 + (((hf * 2 + j) ^ ((row >> 1) & 3)) << 4)) = o;
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(stg + row * 128 + ((j ^ (row & 7)) << 4)) =
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(stg + row * 128 + (((hf * 4 + j) ^ (row & 7)) << 4)) =
                 make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         ptx::fence_proxy_async();
         // two-buffer rings: the store of chunk cnt-1 must have left its buffer before anyone passes this
         // barrier and starts writing chunk cnt+1 into it
         if (N_STG == 2 && issuer) ptx::tma_wait_group_read<0>();
-        w0 = clock64();
-        ptx::bar_sync(bar_id, 128);
-        e_bar += clock64() - w0;
+        if (p.dbg) w0 = clock64();
+        ptx::bar_sync(bar_id, 256);
+        if (p.dbg) e_bar += clock64() - w0;
         if (issuer) {
           if (col0 < p.N) {
             if (EPI == T_ACCUM) ptx::tma_reduce_add_2d(&p.tmOut[g], stg, col0, m0);
@@ -427,7 +433,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
       }
     }
     if (issuer) ptx::tma_wait_group<0>();
-    if (p.dbg && blockIdx.x == 0 && (threadIdx.x == 128 || threadIdx.x == 256 + 37)) {
+    if (p.dbg && blockIdx.x == 0 && (threadIdx.x == 128 || threadIdx.x == 384 + 37)) {
       long long* d = p.dbg + 8 + (threadIdx.x == 128 ? 0 : 8);
       d[0] = e_tfull; d[1] = e_aux; d[2] = e_bar; d[3] = e_ld; d[4] = clock64() - epi_t0; d[5] = cnt;
     }
@@ -705,7 +711,8 @@ int gemm_tc_test(int which, const void* a, const void* b, void* c, int m, int n,
   if (which == 0) { d.a_rs = k; d.a_cs = 1; d.b_rs = 1; d.b_cs = k; d.epi = EPI_STORE; }
   else if (which == 1) { d.a_rs = k; d.a_cs = 1; d.b_rs = n; d.b_cs = 1; d.epi = EPI_STORE; }
   else if (which == 2) { d.a_rs = 1; d.a_cs = m; d.b_rs = n; d.b_cs = 1; d.epi = EPI_ACCUM; to = 0; d.split_k = 1; }
-  else { set_error("gemm_tc_test: which must be 0..2"); return 1; }
+  else if (which == 3) { d.a_rs = k; d.a_cs = 1; d.b_rs = 1; d.b_cs = k; d.epi = EPI_STORE; to = 0; }   // NT, fp32 out
+  else { set_error("gemm_tc_test: which must be 0..3"); return 1; }
   if (variant == 1) return launch_gemm_simt(d, 1, 1, to, stream);
   int handled = 0;
   V2S_TRY(launch_gemm_tc(d, 1, 1, to, stream, &handled));
