@@ -344,3 +344,77 @@ def test_full_size_properties_b128_bf16(dev):
     assert abs(l.item() - full.item()) < 1e-5
     gn = sum(float(p.grad.double().pow(2).sum()) for p in model.parameters() if p.grad is not None) ** 0.5
     assert np.isfinite(gn) and gn > 0
+
+
+def test_finetune_model_backbone_gradients(dev):
+    """SURVEY §8f N2 / ref:octmnist_ft_vit2spn.py:73-104: FineTunedModel forward + weighted CE backward through
+    the accelerated backbone (fp32 check mode) against the oracle backbone + the same torch head."""
+    import vit2spn
+    from oracle import vit2spn_oracle as orc
+    torch.manual_seed(3)
+    state = orc.init_state(9, 0.02)
+    sub = orc.sub_state(state, "online_network_1")
+    model = vit2spn.FineTunedModel(num_classes=4)
+    model.backbone.vit.load_state_dict(sub, strict=True)
+    model.to(dev).train()
+    model.backbone.vit.compute_mode = "fp32"
+    model.fc[3].p = 0.0
+    x = orc.synthetic_views(6, seed=2)[0]
+    y = torch.tensor([0, 1, 2, 3, 1, 2])
+    crit = torch.nn.CrossEntropyLoss(weight=torch.tensor([1.0, 2.0, 0.5, 1.5]))
+    opt = vit2spn.FusedAdam(model.parameters(), lr=1e-4, weight_decay=1e-4)       # ref:192
+    opt.zero_grad()
+    loss = crit.to(dev)(model(x.to(dev)), y.to(dev))
+    loss.backward()
+    # oracle: same head weights on CPU
+    import copy
+    head = copy.deepcopy(model.fc).cpu()
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sub.items()}
+    o_loss = crit(head(orc.backbone_features(leaves, x)), y)
+    o_loss.backward()
+    assert abs(loss.item() - o_loss.item()) <= 1e-5 * abs(o_loss.item()) + 1e-6
+    got = {n: p.grad for n, p in model.backbone.vit.named_parameters() if p.grad is not None}
+    ref = {k: v.grad for k, v in leaves.items() if v.grad is not None and not (k.startswith("layernorm.") or k.startswith("pooler."))}
+    assert set(got) == set(ref)
+    rel, worst = _rel_l2(got, ref)
+    assert rel < 1e-4, (rel, worst)
+    for (n, p), (_, q) in zip(model.fc.named_parameters(), head.named_parameters()):
+        torch.testing.assert_close(p.grad.cpu(), q.grad, rtol=1e-3, atol=1e-6)
+    before = model.fc[0].weight.detach().clone()
+    opt.step()                                     # head tensors go through the per-tensor ranges of the Adam kernel
+    assert not torch.equal(before, model.fc[0].weight.detach())
+
+
+def test_single_stream_variant_step(dev):
+    """SURVEY §8f N3 / ref:dsn_ssn/ssp_single.py:103-138 on the accelerated backbones (fp32 check mode)."""
+    import vit2spn
+    from oracle import vit2spn_oracle as orc
+    state = orc.init_state(13, 0.01)
+    m = vit2spn.SingleStreamNetwork()
+    m.online_network.vit.load_state_dict(orc.sub_state(state, "online_network_1"), strict=True)
+    m.target_network.vit.load_state_dict(orc.sub_state(state, "target_network_1"), strict=True)
+    m.to(dev).train()
+    m.projection_head[2].p = 0.0
+    for net in (m.online_network, m.target_network):
+        net.vit.compute_mode = "fp32"
+    v1, v2 = orc.synthetic_views(3, seed=4)
+    pred, tgt = m(v1.to(dev), v2.to(dev))
+    loss = -torch.mean(torch.nn.CosineSimilarity(dim=1)(pred, tgt))
+    loss.backward()
+    import copy
+    ph, qh = copy.deepcopy(m.projection_head).cpu(), copy.deepcopy(m.prediction_head).cpu()
+    leaves = {k: v.clone().requires_grad_(True) for k, v in orc.sub_state(state, "online_network_1").items()}
+    fo = orc.backbone_features(leaves, v1)
+    with torch.no_grad():
+        ft = orc.backbone_features(orc.sub_state(state, "target_network_1"), v2)
+    o_loss = -torch.mean(torch.nn.CosineSimilarity(dim=1)(qh(ph(fo)), ph(ft).detach()))
+    o_loss.backward()
+    assert abs(loss.item() - o_loss.item()) <= 1e-5 * abs(o_loss.item()) + 1e-6
+    got = {n: p.grad for n, p in m.online_network.vit.named_parameters() if p.grad is not None}
+    ref = {k: v.grad for k, v in leaves.items() if v.grad is not None and not (k.startswith("layernorm.") or k.startswith("pooler."))}
+    rel, worst = _rel_l2(got, ref)
+    assert rel < 1e-4, (rel, worst)
+    t0 = m.target_network.vit.embeddings.position_embeddings.detach().clone()
+    o0 = m.online_network.vit.embeddings.position_embeddings.detach().clone()
+    m.update_target_network()                      # default momentum 0.99, as the reference's signature
+    assert torch.equal(0.99 * t0 + (1 - 0.99) * o0, m.target_network.vit.embeddings.position_embeddings.detach())

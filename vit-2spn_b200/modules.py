@@ -650,6 +650,40 @@ class DualStreamNetwork(nn.Module):
         return loss[0]
 
 
+class SingleStreamNetwork(nn.Module):
+    """ref:dsn_ssn/ssp_single.py:103-138 — the single-stream ablation: one online and one
+    EMA target backbone on the accelerated path; its small heads (Linear(192,1024)-ReLU-Dropout-Linear(1024,128),
+    prediction head) are left to torch."""
+
+    def __init__(self):
+        super().__init__()
+        self.online_network = ViTBackbone()
+        self.target_network = ViTBackbone()
+        for param in self.target_network.parameters():
+            param.requires_grad = False
+        self.projection_head = nn.Sequential(nn.Linear(192, 1024), nn.ReLU(), nn.Dropout(0.3), nn.Linear(1024, 128))
+        self.prediction_head = nn.Sequential(nn.Linear(128, 128), nn.ReLU(), nn.Linear(128, 128))
+
+    def forward(self, view1, view2):
+        feat_online = self.online_network(view1)
+        with torch.no_grad():
+            feat_target = self.target_network(view2)
+        online_proj_feat = self.projection_head(feat_online)
+        online_pred_feat = self.prediction_head(online_proj_feat)
+        target_proj_feat = self.projection_head(feat_target).detach()
+        return online_pred_feat, target_proj_feat
+
+    def update_target_network(self, momentum=0.99):
+        so, st = self.online_network.vit._store, self.target_network.vit._store
+        so.ensure(); st.ensure()
+        _require_cuda(so.flat, "model parameters")
+        tg = (C.c_void_p * 1)(st.flat.data_ptr())
+        on = (C.c_void_p * 1)(so.flat.data_ptr())
+        lp = (C.c_void_p * 1)(st.lp(refresh=False).data_ptr())
+        check(lib.v2s_ema_update(tg, on, lp, 1, so.numel, float(momentum), stream_ptr()), "ema_update")
+        st.mark_lp_fresh()
+
+
 class FineTunedModel(nn.Module):
     """ref:octmnist_ft_vit2spn.py:73-87 — accelerated backbone + the reference's small fc head
     (BatchNorm1d/Dropout head: <0.1 % of the FLOPs, left to torch)."""
