@@ -361,10 +361,11 @@ def test_finetune_model_backbone_gradients(dev):
     model.fc[3].p = 0.0
     x = orc.synthetic_views(6, seed=2)[0]
     y = torch.tensor([0, 1, 2, 3, 1, 2])
-    crit = torch.nn.CrossEntropyLoss(weight=torch.tensor([1.0, 2.0, 0.5, 1.5]))
+    w = torch.tensor([1.0, 2.0, 0.5, 1.5])
+    crit, crit_dev = torch.nn.CrossEntropyLoss(weight=w), torch.nn.CrossEntropyLoss(weight=w.to(dev))
     opt = vit2spn.FusedAdam(model.parameters(), lr=1e-4, weight_decay=1e-4)       # ref:192
     opt.zero_grad()
-    loss = crit.to(dev)(model(x.to(dev)), y.to(dev))
+    loss = crit_dev(model(x.to(dev)), y.to(dev))
     loss.backward()
     # oracle: same head weights on CPU
     import copy

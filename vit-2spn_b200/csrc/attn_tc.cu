@@ -32,13 +32,16 @@ __device__ __forceinline__ void mma(uint32_t d_tmem, uint32_t a_addr, uint32_t a
 }
 
 // ---- forward --------------------------------------------------------------------------------
-constexpr int F_OFF_Q = 0;                                  // 2 tiles
-constexpr int F_OFF_K = 2 * Q_TILE_BYTES;                   // 32768
-constexpr int F_OFF_V = F_OFF_K + KV_TILE_BYTES;            // 59392
-constexpr int F_OFF_P = F_OFF_V + KV_TILE_BYTES;            // 86016 (2 tiles)
-constexpr int F_OFF_BAR = F_OFF_P + 2 * P_TILE_BYTES;       // 217088
+// One CTA per (query tile, head, image, backbone): 160 threads (warp 0 control, warps 1..4 = one softmax
+// thread per query row), 107 KB of smem and 256 TMEM columns, so two CTAs share an SM and the MMA phase
+// of one overlaps the softmax phase of the other.  P (64 KB) is written over K once S = Q K^T has retired.
+constexpr int F_OFF_Q = 0;                                  // 16 KB (later: O staging)
+constexpr int F_OFF_V = Q_TILE_BYTES;                       // 16384
+constexpr int F_OFF_KP = F_OFF_V + KV_TILE_BYTES;           // 43008: K (26 KB), then P (64 KB) in the same place
+constexpr int F_OFF_BAR = F_OFF_KP + P_TILE_BYTES;          // 108544
 constexpr int F_SMEM = F_OFF_BAR + 128 + 1024;
-constexpr int F_THREADS = 288;                              // warp 0 control, warps 1..8 softmax
+constexpr int F_THREADS = 160;
+static_assert(F_OFF_KP % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 
 struct alignas(64) AttnFwdParams {
   CUtensorMap tmQ[MAXG], tmKV[MAXG], tmCtx[MAXG];
@@ -58,25 +61,24 @@ __device__ __forceinline__ void store_p_chunk(uint8_t* tile, int r, int c8, uint
   *reinterpret_cast<uint4*>(tile + block * (QT * 128) + r * 128 + ((chunk ^ (r & 7)) << 4)) = v;
 }
 
-__global__ void __launch_bounds__(F_THREADS, 1) attn_fwd_tc_kernel(const __grid_constant__ AttnFwdParams p) {
+__global__ void __launch_bounds__(F_THREADS, 2) attn_fwd_tc_kernel(const __grid_constant__ AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + F_OFF_BAR);
-  uint64_t* bar_s = bar_load + 1;     // [2]
-  uint64_t* bar_p = bar_s + 2;        // [2]
-  uint64_t* bar_o = bar_p + 2;        // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_o + 2);
-  const int h = blockIdx.x, b = blockIdx.y, g = blockIdx.z;
+  uint64_t* bar_s = bar_load + 1;
+  uint64_t* bar_p = bar_s + 1;
+  uint64_t* bar_o = bar_p + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_o + 1);
+  const int t = blockIdx.x & 1, h = blockIdx.x >> 1, b = blockIdx.y, g = blockIdx.z;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
 
   if (warp == 0) {
     if (lane == 0) {
-      ptx::mbar_init(bar_load, 1);
-      for (int t = 0; t < 2; ++t) { ptx::mbar_init(&bar_s[t], 1); ptx::mbar_init(&bar_p[t], 128); ptx::mbar_init(&bar_o[t], 1); }
+      ptx::mbar_init(bar_load, 1); ptx::mbar_init(bar_s, 1); ptx::mbar_init(bar_p, 128); ptx::mbar_init(bar_o, 1);
       ptx::fence_barrier_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_ptr, 512);
+    ptx::tmem_alloc(tmem_ptr, 256);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -87,10 +89,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) attn_fwd_tc_kernel(const __grid_
   if (warp == 0) {
     // control warp: every lane walks the same path and waits on the barriers; one elected lane issues
     if (ptx::elect_one()) {
-      ptx::mbar_arrive_expect_tx(bar_load, 2 * Q_TILE_BYTES + 2 * KV_TILE_BYTES);
-      ptx::tma_load_3d(smem + F_OFF_Q, &p.tmQ[g], bar_load, h * DH, 0, b);
-      ptx::tma_load_3d(smem + F_OFF_Q + Q_TILE_BYTES, &p.tmQ[g], bar_load, h * DH, QT, b);
-      ptx::tma_load_3d(smem + F_OFF_K, &p.tmKV[g], bar_load, D + h * DH, 0, b);
+      ptx::mbar_arrive_expect_tx(bar_load, Q_TILE_BYTES + 2 * KV_TILE_BYTES);
+      ptx::tma_load_3d(smem + F_OFF_Q, &p.tmQ[g], bar_load, h * DH, t * QT, b);
+      ptx::tma_load_3d(smem + F_OFF_KP, &p.tmKV[g], bar_load, D + h * DH, 0, b);
       ptx::tma_load_3d(smem + F_OFF_V, &p.tmKV[g], bar_load, 2 * D + h * DH, 0, b);
     }
     __syncwarp();
@@ -99,38 +100,29 @@ __global__ void __launch_bounds__(F_THREADS, 1) attn_fwd_tc_kernel(const __grid_
     const uint32_t idesc_s = ptx::make_idesc_bf16(QT, KPAD, 0, 0);
     const uint32_t idesc_o = ptx::make_idesc_bf16(QT, DH, 0, 1);
     const uint32_t sbase = ptx::smem_u32(smem);
-    const uint32_t sk = sbase + F_OFF_K, sv = sbase + F_OFF_V;
+    const uint32_t sq = sbase + F_OFF_Q, skp = sbase + F_OFF_KP, sv = sbase + F_OFF_V;
     if (ptx::elect_one()) {
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const uint32_t sq = sbase + F_OFF_Q + t * Q_TILE_BYTES;
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k) mma(tmem_base + t * 256, sq + k * 32, 16, sk + k * 32, 16, idesc_s, k > 0);
-        ptx::umma_commit(&bar_s[t]);
-      }
+      for (int k = 0; k < DH / 16; ++k) mma(tmem_base, sq + k * 32, 16, skp + k * 32, 16, idesc_s, k > 0);
+      ptx::umma_commit(bar_s);
     }
     __syncwarp();
+    ptx::mbar_wait(bar_p, 0, p.err_flag, 12);
+    ptx::tc_fence_after();
+    if (ptx::elect_one()) {
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      ptx::mbar_wait(&bar_p[t], 0, p.err_flag, 12);
-      ptx::tc_fence_after();
-      const uint32_t sp = sbase + F_OFF_P + t * P_TILE_BYTES;
-      if (ptx::elect_one()) {
-#pragma unroll
-        for (int j = 0; j < KPAD / 16; ++j)
-          mma(tmem_base + t * 256, sp + (j >> 2) * (QT * 128) + (j & 3) * 32, 16, sv + j * 2048, 8192, idesc_o, j > 0);
-        ptx::umma_commit(&bar_o[t]);
-      }
-      __syncwarp();
+      for (int j = 0; j < KPAD / 16; ++j)
+        mma(tmem_base, skp + (j >> 2) * (QT * 128) + (j & 3) * 32, 16, sv + j * 2048, 8192, idesc_o, j > 0);
+      ptx::umma_commit(bar_o);
     }
+    __syncwarp();
   } else {
-    const int t = (warp - 1) >> 2;              // query tile
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const int qrow = t * QT + row;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + t * 256;
-    uint8_t* ptile = smem + F_OFF_P + t * P_TILE_BYTES;
-    ptx::mbar_wait(&bar_s[t], 0, p.err_flag, 13);
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint8_t* ptile = smem + F_OFF_KP;
+    ptx::mbar_wait(bar_s, 0, p.err_flag, 13);   // S complete: K is dead, its smem becomes P
     ptx::tc_fence_after();
     // pass 1: row maximum over the 197 real keys
     float mx = -INFINITY;
@@ -183,12 +175,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) attn_fwd_tc_kernel(const __grid_
     }
     ptx::fence_proxy_async();
     ptx::tc_fence_before();
-    ptx::mbar_arrive(&bar_p[t]);
+    ptx::mbar_arrive(bar_p);
     if (qrow < NT && p.lse[g]) p.lse[g][((int64_t)b * NH + h) * NT + qrow] = mx * SCALE + __logf(sum);
     const float inv = 1.0f / sum;
-    ptx::mbar_wait(&bar_o[t], 0, p.err_flag, 14);
+    ptx::mbar_wait(bar_o, 0, p.err_flag, 14);
     ptx::tc_fence_after();
-    uint8_t* stg = smem + F_OFF_Q + t * Q_TILE_BYTES;       // Q tile is dead once S is complete
+    uint8_t* stg = smem + F_OFF_Q;              // the Q tile is dead once S is complete
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       ptx::tmem_ld_32x32(taddr + c * 32, r);
@@ -204,8 +196,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) attn_fwd_tc_kernel(const __grid_
       }
     }
     ptx::fence_proxy_async();
-    ptx::bar_sync(1 + t, 128);
-    if (row == 0) {
+    ptx::bar_sync(1, 128);
+    if (threadIdx.x == 32) {
       ptx::tma_store_3d(&p.tmCtx[g], stg, h * DH, t * QT, b);   // rows >= 197 are clipped by TMA
       ptx::tma_commit_group();
       ptx::tma_wait_group<0>();
@@ -215,7 +207,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) attn_fwd_tc_kernel(const __grid_
   __syncthreads();
   if (warp == 0) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    ptx::tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -558,7 +550,7 @@ int launch_attn_fwd_tc(const void* const* qkv, void* const* ctx, float* const* l
     V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
     attr = true;
   }
-  attn_fwd_tc_kernel<<<dim3(NH, B, groups), F_THREADS, F_SMEM, s>>>(p);
+  attn_fwd_tc_kernel<<<dim3(NH * 2, B, groups), F_THREADS, F_SMEM, s>>>(p);
   V2S_LAUNCH_CHECK();
   return 0;
 }
