@@ -380,7 +380,7 @@ def test_finetune_model_backbone_gradients(dev):
     rel, worst = _rel_l2(got, ref)
     assert rel < 1e-4, (rel, worst)
     for (n, p), (_, q) in zip(model.fc.named_parameters(), head.named_parameters()):
-        torch.testing.assert_close(p.grad.cpu(), q.grad, rtol=1e-3, atol=1e-6)
+        torch.testing.assert_close(p.grad.cpu(), q.grad, rtol=1e-3, atol=1e-5)
     before = model.fc[0].weight.detach().clone()
     opt.step()                                     # head tensors go through the per-tensor ranges of the Adam kernel
     assert not torch.equal(before, model.fc[0].weight.detach())

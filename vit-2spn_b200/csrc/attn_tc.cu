@@ -81,10 +81,12 @@ __global__ void __launch_bounds__(F_THREADS, 2) attn_fwd_tc_kernel(const __grid_
     ptx::tmem_alloc(tmem_ptr, 256);
     ptx::tmem_relinquish();
   }
+  ptx::pdl_launch_dependents();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+  ptx::pdl_wait();                  // prologue above overlapped the predecessor's tail
 
   if (warp == 0) {
     // control warp: every lane walks the same path and waits on the barriers; one elected lane issues
@@ -282,10 +284,12 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
     }
     ptx::fence_proxy_async();
   }
+  ptx::pdl_launch_dependents();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+  ptx::pdl_wait();                  // prologue above overlapped the predecessor's tail
 
   if (warp == 0) {
     // control warp: every lane walks the same path and waits on the barriers; one elected lane issues
@@ -550,7 +554,7 @@ int launch_attn_fwd_tc(const void* const* qkv, void* const* ctx, float* const* l
     V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
     attr = true;
   }
-  attn_fwd_tc_kernel<<<dim3(NH * 2, B, groups), F_THREADS, F_SMEM, s>>>(p);
+  V2S_CUDA_OK(launch_pdl(attn_fwd_tc_kernel, dim3(NH * 2, B, groups), dim3(F_THREADS), (size_t)F_SMEM, s, p));
   V2S_LAUNCH_CHECK();
   return 0;
 }
@@ -577,7 +581,7 @@ int launch_attn_bwd_tc(const void* const* qkv, const void* const* ctx, const flo
     V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
     attr = true;
   }
-  attn_bwd_tc_kernel<<<dim3(NH, B, groups), B_THREADS, B_SMEM, s>>>(p);
+  V2S_CUDA_OK(launch_pdl(attn_bwd_tc_kernel, dim3(NH, B, groups), dim3(B_THREADS), (size_t)B_SMEM, s, p));
   V2S_LAUNCH_CHECK();
   return 0;
 }

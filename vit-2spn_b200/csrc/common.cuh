@@ -3,6 +3,9 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
+
+#include <utility>
 
 #include "../../include/vit2spn.h"
 
@@ -92,6 +95,20 @@ extern int64_t g_launch_count;
     int _r = (expr);              \
     if (_r != 0) return _r;       \
   } while (0)
+
+// ---- launch with programmatic stream serialization (PDL); the kernel must call ptx::pdl_wait() ----
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- device helpers ---------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f(T v);

@@ -143,10 +143,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
       reinterpret_cast<uint32_t*>(ones_tile)[i] = (i < 32) ? 0x3F803F80u : 0u;
     ptx::fence_proxy_async();
   }
+  ptx::pdl_launch_dependents();     // the next kernel may start its own prologue while this one runs
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+  ptx::pdl_wait();                  // everything above overlapped the predecessor's tail; its outputs are visible now
 
   const int tiles_per_group = p.tiles_m * p.splits * p.tiles_n;
   // i-th tile of this CTA (same sequence for every warp role); false when the CTA is done
@@ -570,7 +572,7 @@ int launch_kernel(TcParams& p, cudaStream_t stream) {
   const int SMEM_TOTAL = p.op_bytes + Cfg<EPI, OUT_BF16>::STAGING_BYTES + SMEM_BAR_BYTES + 1024;
   int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   if (p.b_stationary) grid = p.groups * p.tiles_n * p.ctas_per_combo;
-  gemm_tc_kernel<EPI, OUT_BF16><<<grid, N_THREADS, SMEM_TOTAL, stream>>>(p);
+  V2S_CUDA_OK(launch_pdl(gemm_tc_kernel<EPI, OUT_BF16>, dim3(grid), dim3(N_THREADS), (size_t)SMEM_TOTAL, stream, p));
   V2S_LAUNCH_CHECK();
   return 0;
 }

@@ -101,6 +101,8 @@ template <> __device__ __forceinline__ float4 load4<bf16>(const bf16* src) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const __grid_constant__ LnFwdP p) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int g = blockIdx.y;
   const int hw = threadIdx.x >> 4, l = threadIdx.x & 15;
   const unsigned hmask = 0xffffu << (16 * (hw & 1));
@@ -148,6 +150,8 @@ struct LnBwdP {
 template <typename T>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const __grid_constant__ LnBwdP p) {
   __shared__ float red[16][3 * D];          // 36 KB
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int g = blockIdx.y;
   const int hw = threadIdx.x >> 4, l = threadIdx.x & 15;
   const unsigned hmask = 0xffffu << (16 * (hw & 1));
@@ -652,8 +656,8 @@ int launch_ln_fwd(const float* const* x, const float* const* gamma, const float*
   int bx = (M + 15) / 16;
   if (bx > 148 * 6) bx = 148 * 6;
   dim3 grid(bx, groups);
-  if (at == 0) ln_fwd_kernel<float><<<grid, 256, 0, s>>>(p);
-  else ln_fwd_kernel<bf16><<<grid, 256, 0, s>>>(p);
+  if (at == 0) V2S_CUDA_OK(launch_pdl(ln_fwd_kernel<float>, grid, dim3(256), 0, s, p));
+  else V2S_CUDA_OK(launch_pdl(ln_fwd_kernel<bf16>, grid, dim3(256), 0, s, p));
   V2S_LAUNCH_CHECK();
   return 0;
 }
@@ -672,8 +676,8 @@ int launch_ln_bwd(const void* const* dy, const float* const* x, const float* con
   int bx = (M + 15) / 16;
   if (bx > 148 * 4) bx = 148 * 4;
   dim3 grid(bx, groups);
-  if (at == 0) ln_bwd_kernel<float><<<grid, 256, 0, s>>>(p);
-  else ln_bwd_kernel<bf16><<<grid, 256, 0, s>>>(p);
+  if (at == 0) V2S_CUDA_OK(launch_pdl(ln_bwd_kernel<float>, grid, dim3(256), 0, s, p));
+  else V2S_CUDA_OK(launch_pdl(ln_bwd_kernel<bf16>, grid, dim3(256), 0, s, p));
   V2S_LAUNCH_CHECK();
   return 0;
 }

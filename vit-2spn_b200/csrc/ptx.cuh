@@ -112,6 +112,14 @@ template <int N> __device__ __forceinline__ void tma_wait_group() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------
+// launch_dependents: the next kernel in the stream (if launched with the programmatic-serialization
+// attribute) may begin once every CTA of this grid has executed this or exited.  wait: blocks until the
+// preceding grid has completed and its memory is visible.  Everything a kernel does BEFORE pdl_wait()
+// (barrier init, TMEM allocation, tensor-map prefetch) overlaps the tail of its predecessor.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- named barriers ---------------------------------------------------------------------------
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
