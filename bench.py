@@ -208,6 +208,13 @@ def main():
     l0 = _lib.lib.v2s_launch_count()
     ms_total = timed(lambda: step(x1, x2), args.steps)
     launches = int(_lib.lib.v2s_launch_count() - l0)
+    # host-side cost of enqueueing one step (no device wait inside): tells CPU-bound from GPU-bound
+    torch.cuda.synchronize()
+    h0 = time.perf_counter()
+    for _ in range(5):
+        step(x1, x2)
+    host_ms = (time.perf_counter() - h0) / 5 * 1e3
+    torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     flag = _lib.lib.v2s_debug_flag()
     ms_per_step = ms_total / args.steps
@@ -300,7 +307,7 @@ def main():
             "step_tflops_per_gpu": step_tflops,
             "step_frac_of_bf16_peak": step_tflops / pk["bf16_tflops_sustained"],
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks, "kernel_classes": classes, "debug_flag": flag,
+            "clocks": clocks, "kernel_classes": classes, "debug_flag": flag, "host_enqueue_ms_per_step": host_ms,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

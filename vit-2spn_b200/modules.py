@@ -70,6 +70,7 @@ class FlatStore:
         self.flat_grad = None
         self.flat_lp = None
         self._grad_views = None
+        self._active = None
         self.lp_fresh = False        # set by the fused Adam / EMA kernels that refresh the shadow
         self._ver = -1
         self.reflatten()
@@ -90,6 +91,7 @@ class FlatStore:
         self.flat_grad = None
         self.flat_lp = None
         self._grad_views = None
+        self._active = None
         self.lp_fresh = False
 
     def ensure(self):
@@ -127,9 +129,15 @@ class FlatStore:
         if self.flat_grad is None or self.flat_grad.device != self.flat.device:
             self.flat_grad = torch.zeros(self.numel, dtype=torch.float32, device=self.flat.device)
             self._grad_views = self._views(self.flat_grad)
-        # tensors past active_numel (final LN, pooler) are never used: grad stays None
-        active = [(p, v) for p, v, o in zip(self.params, self._grad_views, self.offsets)
-                  if o < self.active_numel and p.requires_grad]
+            self._active = None
+        if self._active is None or len(self._active) != self._n_trainable():
+            # tensors past active_numel (final LN, pooler) are never used: grad stays None
+            self._active = [(p, v) for p, v, o in zip(self.params, self._grad_views, self.offsets)
+                            if o < self.active_numel and p.requires_grad]
+        active = self._active
+        # fast path (steady state of a training loop): every .grad is still our view
+        if all(p.grad is v for p, v in active):
+            return self.flat_grad
         n_none = sum(1 for p, _ in active if p.grad is None)
         if n_none == len(active):
             self.flat_grad.zero_()
@@ -140,10 +148,20 @@ class FlatStore:
                 if p.grad is None:
                     v.zero_()
                     p.grad = v
-                elif p.grad.data_ptr() != v.data_ptr():
+                elif p.grad is not v and p.grad.data_ptr() != v.data_ptr():
                     v.copy_(p.grad)            # someone else accumulated a gradient: keep it
                     p.grad = v
         return self.flat_grad
+
+    def _n_trainable(self):
+        return sum(1 for p, o in zip(self.params, self.offsets) if o < self.active_numel and p.requires_grad)
+
+    def zero_grads_fast(self):
+        """One memset instead of 200 ``p.grad = None``: the views stay attached (used by FusedAdam.zero_grad)."""
+        if self.flat_grad is not None and self.grads_attached():
+            self.flat_grad.zero_()
+            return True
+        return False
 
     def grads_attached(self):
         """True if every trainable parameter's ``.grad`` is the matching view of the flat grad buffer."""
@@ -151,7 +169,7 @@ class FlatStore:
             return False
         for p, v, o in zip(self.params, self._grad_views, self.offsets):
             if o < self.active_numel and p.requires_grad:
-                if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                if p.grad is not v and (p.grad is None or p.grad.data_ptr() != v.data_ptr()):
                     return False
         return True
 

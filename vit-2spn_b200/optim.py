@@ -24,7 +24,9 @@ class FusedAdam(torch.optim.Optimizer):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False,
                         foreach=None, capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False)
         super().__init__(params, defaults)
-        self._flat_state = {}      # id(store) -> (store, exp_avg_flat, exp_avg_sq_flat)
+        self._flat_state = {}      # id(store) -> [store, exp_avg_flat, exp_avg_sq_flat, step]
+        self._psets = {}
+        self._all_ids = None
         self.grad_scale = 1.0      # multiplies every gradient inside the kernel (1/world_size, 1/loss_scale)
 
     def _state_for(self, p, m_view=None, v_view=None):
@@ -35,27 +37,22 @@ class FusedAdam(torch.optim.Optimizer):
             st["exp_avg_sq"] = v_view if v_view is not None else torch.zeros_like(p, memory_format=torch.preserve_format)
         return st
 
-    def _store_ranges(self, group_params):
-        """Split the group's parameters into whole-store flat ranges and leftovers."""
-        pset = {id(p) for p in group_params}
-        ranges, covered = [], set()
-        for store in list(_STORES):
-            active = [(p, o) for p, o in zip(store.params, store.offsets)
-                      if o < store.active_numel and p.requires_grad]
-            if not active or any(id(p) not in pset for p, _ in active):
-                continue
-            if store.flat is None or not store.flat.is_cuda or not store.grads_attached():
-                continue
-            if store.active_numel % 4:
-                continue
-            key = id(store)
-            ent = self._flat_state.get(key)
-            if ent is None or ent[1].device != store.flat.device:
-                m = torch.zeros(store.numel, dtype=torch.float32, device=store.flat.device)
-                v = torch.zeros(store.numel, dtype=torch.float32, device=store.flat.device)
-                ent = (store, m, v)
-                self._flat_state[key] = ent
-            _, m, v = ent
+    def _store_plan(self, store, pset):
+        """(active params, m_flat, v_flat) if the whole store can be updated as one flat range."""
+        active = [(p, o) for p, o in zip(store.params, store.offsets) if o < store.active_numel and p.requires_grad]
+        if not active or any(id(p) not in pset for p, _ in active):
+            return None
+        if store.flat is None or not store.flat.is_cuda or store.active_numel % 4:
+            return None
+        key = id(store)
+        ent = self._flat_state.get(key)
+        if ent is None or ent[1].device != store.flat.device:
+            m = torch.zeros(store.numel, dtype=torch.float32, device=store.flat.device)
+            v = torch.zeros(store.numel, dtype=torch.float32, device=store.flat.device)
+            ent = [store, m, v, None]          # [.., step count of the store (python int, lazily synced to state)]
+            self._flat_state[key] = ent
+        _, m, v, step = ent
+        if step is None:
             steps = set()
             for p, o in active:
                 mv, vv = m[o:o + p.numel()].view(p.shape), v[o:o + p.numel()].view(p.shape)
@@ -66,10 +63,53 @@ class FusedAdam(torch.optim.Optimizer):
                     vv.copy_(st["exp_avg_sq"]); st["exp_avg_sq"] = vv
                 steps.add(float(st["step"]))
             if len(steps) != 1:
-                continue                                            # inconsistent history: per-tensor path
-            ranges.append((store, m, v, active, int(steps.pop())))
-            covered.update(id(p) for p, _ in active)
-        return ranges, covered
+                return None                                          # inconsistent history: per-tensor path
+            ent[3] = int(steps.pop())
+        return active, ent
+
+    def _all_param_ids(self):
+        n = sum(len(g["params"]) for g in self.param_groups)
+        if self._all_ids is None or len(self._all_ids) != n:
+            self._all_ids = {id(p) for g in self.param_groups for p in g["params"]}
+        return self._all_ids
+
+    def _sync_steps(self):
+        """Write the per-store step counters back into the per-parameter state (state_dict layout of torch)."""
+        for store, m, v, step in self._flat_state.values():
+            if step is None:
+                continue
+            for p, o in zip(store.params, store.offsets):
+                if p in self.state and o < store.active_numel:
+                    self.state[p]["step"] = torch.tensor(float(step), dtype=torch.float32)
+
+    def state_dict(self):
+        self._sync_steps()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        for ent in self._flat_state.values():
+            ent[3] = None                       # re-derive the flat views and step counters from the loaded state
+
+    def zero_grad(self, set_to_none: bool = True):
+        """Flat-buffer fast path: ONE memset per store, ``.grad`` views stay attached (they read as zeros
+        instead of None).  Parameters outside vit2spn stores follow torch's semantics."""
+        handled = set()
+        mine = self._all_param_ids()
+        for store in list(_STORES):
+            # only stores whose trainable parameters all belong to this optimizer
+            if store.flat_grad is None or not all(id(p) in mine for p in store.params if p.requires_grad):
+                continue
+            if store.zero_grads_fast():
+                handled.update(id(p) for p in store.params)
+        for group in self.param_groups:
+            for p in group["params"]:
+                if id(p) in handled or p.grad is None:
+                    continue
+                if set_to_none:
+                    p.grad = None
+                else:
+                    p.grad.detach_(); p.grad.zero_()
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -81,45 +121,51 @@ class FusedAdam(torch.optim.Optimizer):
             lr, (b1, b2), eps, wd = group["lr"], group["betas"], group["eps"], group["weight_decay"]
             if group.get("amsgrad") or group.get("maximize"):
                 raise NotImplementedError("FusedAdam: amsgrad/maximize are not used by the reference")
-            with_grad = [p for p in group["params"] if p.grad is not None]
-            store_ranges, covered = self._store_ranges(with_grad)
-            # group launches by step count (the kernel takes one bias correction per launch)
-            launches = {}
-            for store, m, v, active, step in store_ranges:
+            params = group["params"]
+            pset = self._psets.get(id(group))
+            if pset is None or len(pset) != len(params):
+                pset = {id(p) for p in params}
+                self._psets[id(group)] = pset
+            launches, covered = {}, set()
+            for store in list(_STORES):
+                if store.flat_grad is None or not store.grads_attached():
+                    continue
+                plan = self._store_plan(store, pset)
+                if plan is None:
+                    continue
+                active, ent = plan
+                _, m, v, step = ent
                 lp = store.flat_lp
-                r = Range(store.flat.data_ptr(), store.flat_grad.data_ptr(), m.data_ptr(), v.data_ptr(),
-                          lp.data_ptr() if lp is not None else None, store.active_numel)
-                launches.setdefault(step + 1, []).append(r)
-                for p, _ in active:
-                    self.state[p]["step"] += 1
-                if lp is not None and store.active_numel == store.numel or lp is not None and getattr(store, "_lp_tail_ok", False):
-                    store.mark_lp_fresh()
-                elif lp is not None:
-                    # the kernel refreshes only the trained prefix; the never-trained tail (final LN, pooler)
-                    # is constant, so one full cast makes every later refresh complete
+                if lp is not None and store.active_numel != store.numel and not getattr(store, "_lp_tail_ok", False):
+                    # the kernel refreshes only the trained prefix of the bf16 shadow; the never-trained tail
+                    # (final LN, pooler) is constant, so one full cast makes every later refresh complete
                     store.lp(refresh=True)
                     store._lp_tail_ok = True
-                    store.mark_lp_fresh()
-            for p in with_grad:
-                if id(p) in covered:
-                    continue
-                if not p.is_cuda:
-                    raise RuntimeError("FusedAdam: parameter on CPU — vit2spn has no CPU fallback")
-                if p.grad.is_sparse or p.dtype != torch.float32:
-                    raise RuntimeError("FusedAdam supports dense fp32 parameters only")
-                st = self._state_for(p)
-                g = p.grad.contiguous()
-                if not p.is_contiguous():
-                    raise RuntimeError("FusedAdam: non-contiguous parameter")
-                step = int(float(st["step"]))
-                st["step"] += 1
                 launches.setdefault(step + 1, []).append(
-                    Range(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), None,
-                          p.numel()))
-                launches.setdefault(("keep", step + 1), []).append(g)
+                    Range(store.flat.data_ptr(), store.flat_grad.data_ptr(), m.data_ptr(), v.data_ptr(),
+                          lp.data_ptr() if lp is not None else None, store.active_numel))
+                ent[3] = step + 1
+                if lp is not None:
+                    store.mark_lp_fresh()
+                covered.update(id(p) for p, _ in active)
+            keep = []
+            if len(covered) != len(params):
+                for p in params:
+                    if id(p) in covered or p.grad is None:
+                        continue
+                    if not p.is_cuda:
+                        raise RuntimeError("FusedAdam: parameter on CPU — vit2spn has no CPU fallback")
+                    if p.grad.is_sparse or p.dtype != torch.float32 or not p.is_contiguous():
+                        raise RuntimeError("FusedAdam supports dense contiguous fp32 parameters only")
+                    st = self._state_for(p)
+                    g = p.grad.contiguous()
+                    keep.append(g)
+                    step = int(float(st["step"]))
+                    st["step"] += 1
+                    launches.setdefault(step + 1, []).append(
+                        Range(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), None,
+                              p.numel()))
             for key, rs in launches.items():
-                if isinstance(key, tuple):
-                    continue
                 for i in range(0, len(rs), 4):
                     chunk = rs[i:i + 4]
                     arr = (Range * len(chunk))(*chunk)
