@@ -38,7 +38,9 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
   const bool a_kfast = (d.a_cs == 1);
   const bool b_kfast = (d.b_rs == 1);
 
-  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+  // register-prefetch double buffering: the global loads of tile k+1 are in flight while tile k is multiplied
+  float ra[4], rb[4];
+  auto load_tile = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int e = tid + i * 256;
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
         const int64_t col = d.a_remap == 2 ? remap_row(k) : (int64_t)k;
         v = to_f<TA>(A[row * d.a_rs + col * d.a_cs]);
       }
-      As[kk][mm] = v;
+      ra[i] = v;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -64,9 +66,22 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
         const int64_t krow = d.b_remap ? remap_row(k) : (int64_t)k;
         v = to_f<TB>(B[krow * d.b_rs + (int64_t)n * d.b_cs]);
       }
-      Bs[kk][nn] = v;
+      rb[i] = v;
     }
-    __syncthreads();
+  };
+  auto store_tile = [&]() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;
+      if (a_kfast) As[e % BK][e / BK] = ra[i]; else As[e / BM][e % BM] = ra[i];
+      if (b_kfast) Bs[e % BK][e / BK] = rb[i]; else Bs[e / BN][e % BN] = rb[i];
+    }
+  };
+  if (k_begin < k_end) { load_tile(k_begin); store_tile(); }
+  __syncthreads();
+  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+    const bool has_next = k0 + BK < k_end;
+    if (has_next) load_tile(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
@@ -79,6 +94,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
+    if (has_next) { store_tile(); __syncthreads(); }
   }
 
   // ---- epilogue ----

@@ -651,8 +651,10 @@ int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t strea
   p.kb_total = (d.K + BK - 1) / BK;
   p.splits = 1;
   if (epi == T_ACCUM) {
+    // split-K so that the launch is ONE balanced wave: base * splits <= #SMs (a second, partial wave of a few
+    // tiles would double the makespan of these long-K tiles)
     const int base = d.groups * p.tiles_m * p.tiles_n;
-    int s = (g_num_sms + base - 1) / base;
+    int s = g_num_sms / base;
     const int max_s = p.kb_total / 4 > 0 ? p.kb_total / 4 : 1;
     if (s > max_s) s = max_s;
     if (s < 1) s = 1;

@@ -48,19 +48,32 @@ __global__ void cls_rows_kernel(G4<const float*> params, G4<float*> hidden) {
 }
 
 // hidden[b,0,:] = cls + pos[0];  hidden[b,1+p,:] = tok[b*196+p,:] + pos[1+p]   (HF:117-124)
-__global__ void assemble_tokens_kernel(G4<const float*> params, G4<const float*> tok, G4<float*> hidden) {
-  const int g = blockIdx.z, b = blockIdx.y, t = blockIdx.x, n = threadIdx.x;
-  const float* p = params.p[g];
-  const float pos = p[OFF_POS + (int64_t)t * D + n];
-  const float v = (t == 0) ? p[OFF_CLS + n] : tok.p[g][((int64_t)b * NP + t - 1) * D + n];
-  hidden.p[g][((int64_t)b * NT + t) * D + n] = v + pos;
+// one float4 per thread; blockIdx.y = image, blockIdx.z = backbone
+__global__ void __launch_bounds__(256) assemble_tokens_kernel(G4<const float*> params, G4<const float*> tok,
+                                                              G4<float*> hidden) {
+  const int g = blockIdx.z, b = blockIdx.y;
+  const float* __restrict__ p = params.p[g];
+  const float* __restrict__ tk = tok.p[g];
+  float* __restrict__ h = hidden.p[g];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NT * (D / 4); i += gridDim.x * blockDim.x) {
+    const int t = i / (D / 4), c = (i % (D / 4)) * 4;
+    const float4 pos = *reinterpret_cast<const float4*>(p + OFF_POS + (int64_t)t * D + c);
+    const float4 v = (t == 0) ? *reinterpret_cast<const float4*>(p + OFF_CLS + c)
+                              : *reinterpret_cast<const float4*>(tk + ((int64_t)b * NP + t - 1) * D + c);
+    *reinterpret_cast<float4*>(h + ((int64_t)b * NT + t) * D + c) =
+        make_float4(v.x + pos.x, v.y + pos.y, v.z + pos.z, v.w + pos.w);
+  }
 }
 
-// compact the patch-token rows of a [B,197,192] tensor into [B*196,192] (drops the CLS rows)
+// compact the patch-token rows of a [B,197,192] tensor into [B*196,192] (drops the CLS rows); 8 bytes per thread
 template <typename T>
-__global__ void gather_patch_rows_kernel(G4<const T*> src, G4<T*> dst) {
-  const int g = blockIdx.z, b = blockIdx.y, pi = blockIdx.x, n = threadIdx.x;
-  dst.p[g][((int64_t)b * NP + pi) * D + n] = src.p[g][((int64_t)b * NT + 1 + pi) * D + n];
+__global__ void __launch_bounds__(256) gather_patch_rows_kernel(G4<const T*> src, G4<T*> dst) {
+  const int g = blockIdx.z, b = blockIdx.y;
+  constexpr int V = 8 / sizeof(T);                 // elements per 8-byte access
+  const T* __restrict__ s = src.p[g] + ((int64_t)b * NT + 1) * D;
+  T* __restrict__ d = dst.p[g] + (int64_t)b * NP * D;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NP * D / V; i += gridDim.x * blockDim.x)
+    reinterpret_cast<uint2*>(d)[i] = reinterpret_cast<const uint2*>(s)[i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -257,15 +270,30 @@ __global__ void pool_fwd_kernel(G4<const float*> hidden, G4<float*> feat, G4<int
   feat.p[g][(int64_t)b * stride.p[g] + n] = s * (1.0f / NT);
 }
 
+// dx[b,t,:] = dfeat[b,:] / 197 (+ dhidden[b,t,:]); also the activation-type copy.  float4 per thread.
 template <typename T>
-__global__ void pool_bwd_kernel(G4<const float*> dfeat, G4<int64_t> stride, G4<const float*> dhidden,
-                                G4<float*> dx, G4<T*> dx_lp) {
-  const int g = blockIdx.z, b = blockIdx.y, t = blockIdx.x, n = threadIdx.x;
-  const int64_t idx = ((int64_t)b * NT + t) * D + n;
-  float v = dfeat.p[g] ? dfeat.p[g][(int64_t)b * stride.p[g] + n] * (1.0f / NT) : 0.f;
-  if (dhidden.p[g]) v += dhidden.p[g][idx];
-  dx.p[g][idx] = v;
-  if (dx_lp.p[g]) dx_lp.p[g][idx] = from_f<T>(v);
+__global__ void __launch_bounds__(256) pool_bwd_kernel(G4<const float*> dfeat, G4<int64_t> stride, G4<const float*> dhidden,
+                                                       G4<float*> dx, G4<T*> dx_lp) {
+  const int g = blockIdx.z, b = blockIdx.y;
+  const float* __restrict__ df = dfeat.p[g];
+  const float* __restrict__ dh = dhidden.p[g];
+  float* __restrict__ o = dx.p[g];
+  T* __restrict__ ol = dx_lp.p[g];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NT * (D / 4); i += gridDim.x * blockDim.x) {
+    const int c = (i % (D / 4)) * 4;
+    const int64_t idx = (int64_t)b * NT * D + (int64_t)i * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (df) {
+      const float4 f = *reinterpret_cast<const float4*>(df + (int64_t)b * stride.p[g] + c);
+      v = make_float4(f.x * (1.0f / NT), f.y * (1.0f / NT), f.z * (1.0f / NT), f.w * (1.0f / NT));
+    }
+    if (dh) {
+      const float4 a = *reinterpret_cast<const float4*>(dh + idx);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    *reinterpret_cast<float4*>(o + idx) = v;
+    if (ol) store4<T>(ol + idx, v.x, v.y, v.z, v.w);
+  }
 }
 
 // d pos / d cls / d patch-bias from the gradient of the embedding output
@@ -630,16 +658,16 @@ int launch_cls_rows(const float* const* params, float* const* hidden, int groups
 
 int launch_assemble_tokens(const float* const* params, const float* const* tok, float* const* hidden, int groups,
                            int B, cudaStream_t s) {
-  assemble_tokens_kernel<<<dim3(NT, B, groups), D, 0, s>>>(pack4<const float*>(params, groups),
+  assemble_tokens_kernel<<<dim3(8, B, groups), 256, 0, s>>>(pack4<const float*>(params, groups),
                                                           pack4<const float*>(tok, groups), pack4<float*>(hidden, groups));
   V2S_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_gather_patch_rows(const void* const* src, void* const* dst, int groups, int B, int at, cudaStream_t s) {
-  dim3 grid(NP, B, groups);
-  if (at == 0) gather_patch_rows_kernel<float><<<grid, D, 0, s>>>(pack4<const float*>(src, groups), pack4<float*>(dst, groups));
-  else gather_patch_rows_kernel<bf16><<<grid, D, 0, s>>>(pack4<const bf16*>(src, groups), pack4<bf16*>(dst, groups));
+  dim3 grid(8, B, groups);
+  if (at == 0) gather_patch_rows_kernel<float><<<grid, 256, 0, s>>>(pack4<const float*>(src, groups), pack4<float*>(dst, groups));
+  else gather_patch_rows_kernel<bf16><<<grid, 256, 0, s>>>(pack4<const bf16*>(src, groups), pack4<bf16*>(dst, groups));
   V2S_LAUNCH_CHECK();
   return 0;
 }
@@ -714,12 +742,18 @@ int launch_pool_bwd(const float* const* dfeat, const int64_t* dfeat_stride, cons
                     float* const* dx, void* const* dx_lp, int groups, int B, int at, cudaStream_t s) {
   G4<int64_t> st;
   for (int i = 0; i < MAXG; ++i) st.p[i] = i < groups ? dfeat_stride[i] : 0;
-  dim3 grid(NT, B, groups);
+  for (int i = 0; i < groups; ++i)
+    if ((dfeat[i] && ((reinterpret_cast<uintptr_t>(dfeat[i]) & 15) || (dfeat_stride[i] & 3))) ||
+        (dhidden[i] && (reinterpret_cast<uintptr_t>(dhidden[i]) & 15))) {
+      set_error("pool_bwd: dfeat / dhidden must be 16-byte aligned with a row stride that is a multiple of 4 floats");
+      return 1;
+    }
+  dim3 grid(8, B, groups);
   if (at == 0)
-    pool_bwd_kernel<float><<<grid, D, 0, s>>>(pack4<const float*>(dfeat, groups), st, pack4<const float*>(dhidden, groups),
+    pool_bwd_kernel<float><<<grid, 256, 0, s>>>(pack4<const float*>(dfeat, groups), st, pack4<const float*>(dhidden, groups),
                                               pack4<float*>(dx, groups), pack4<float*>(dx_lp, groups));
   else
-    pool_bwd_kernel<bf16><<<grid, D, 0, s>>>(pack4<const float*>(dfeat, groups), st, pack4<const float*>(dhidden, groups),
+    pool_bwd_kernel<bf16><<<grid, 256, 0, s>>>(pack4<const float*>(dfeat, groups), st, pack4<const float*>(dhidden, groups),
                                              pack4<float*>(dx, groups), pack4<bf16*>(dx_lp, groups));
   V2S_LAUNCH_CHECK();
   return 0;

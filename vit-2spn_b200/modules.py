@@ -649,8 +649,8 @@ class DualStreamNetwork(nn.Module):
             ]
             _run_forward(groups, B, mode, ws)
             mask_o, mask_t = self._dropout_masks(B, dev)
-            out = torch.empty(1 + B * 384, dtype=torch.float32, device=dev)
-            loss, dfeat = out[:1], out[1:].view(B, 384)
+            out = torch.empty(4 + B * 384, dtype=torch.float32, device=dev)     # dfeat stays 16-byte aligned
+            loss, dfeat = out[:1], out[4:].view(B, 384)
             base, nbytes = _aligned(ws)
             hg = hs.grads() if with_backward else None
             check(lib.v2s_heads_loss_fwd_bwd(ptr(hs.flat), ptr(hg), ptr(feat_o), ptr(feat_t), ptr(mask_o), ptr(mask_t),
