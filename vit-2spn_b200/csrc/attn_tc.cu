@@ -470,14 +470,15 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bar_ds[t]);
-      // ---- dQ_t: TMEM [0,64) → bf16 → (after the tile's MMAs retired) staged in the Q buffer → TMA store ----
+      // ---- dQ_t: TMEM [0,64) → bf16 → staged in the (dead) dO buffer → TMA store ----
       ptx::mbar_wait(&bar_dq[t], 0, p.err_flag, 28);
       ptx::tc_fence_after();
       ptx::tmem_ld_32x32(tlane + half * 32, r);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
-      ptx::mbar_wait(&bar_kv[t], 0, p.err_flag, 29);      // Q_t no longer read by the dK MMAs
-      uint8_t* stg = smem + B_OFF_Q;
+      // bar_dq also covers the dV MMAs issued before dQ, so the dO tile is dead here: stage dQ in it without
+      // waiting for the dK MMAs (which still read Q_t and dS)
+      uint8_t* stg = smem + B_OFF_DO;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 v;
@@ -497,7 +498,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
       if (t == 0) ptx::mbar_arrive(bar_free);
     }
     // ---- dK, dV: TMEM → bf16 → staged in the P buffer → TMA store (rows = keys) ----
-    // bar_kv[1] was waited above: every MMA has retired
+    ptx::mbar_wait(&bar_kv[1], 0, p.err_flag, 29);       // every MMA has retired
     ptx::tc_fence_after();
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {          // 0: dK, 1: dV

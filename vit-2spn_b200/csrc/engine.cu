@@ -264,6 +264,10 @@ static int backbone_forward_impl(const v2s_group_t* gs, int G, int B, int mode, 
   }
 
   // ---- 12 pre-LN blocks ----
+  // On the tensor-core path every LayerNorm except the first is fused into the epilogue of the GEMM that
+  // produces its input row (attention projection → LN2, fc2 → LN1 of the next block): V2S_NO_LNFUSE=1 disables.
+  const bool ln_fuse = at == 1 && tc_enabled() && !getenv("V2S_NO_LNFUSE");
+  bool ln1_done = false;
   for (int l = 0; l < NL; ++l) {
     const int64_t lo = layer_off(l);
     const float *xin[MAXG], *gam[MAXG], *bet[MAXG];
@@ -285,8 +289,10 @@ static int backbone_forward_impl(const v2s_group_t* gs, int G, int B, int mode, 
       }
       gam[g] = gs[g].params + lo + L_LN1W; bet[g] = gs[g].params + lo + L_LN1B;
     }
-    { prof::Scope sc(prof::C_LN_F, (double)M * D * (4 + p.es) * G, st);
-      V2S_TRY(launch_ln_fwd(xin, gam, bet, xn, mean, rstd, G, (int)M, at, st)); }
+    if (!ln1_done) {
+      prof::Scope sc(prof::C_LN_F, (double)M * D * (4 + p.es) * G, st);
+      V2S_TRY(launch_ln_fwd(xin, gam, bet, xn, mean, rstd, G, (int)M, at, st));
+    }
     {  // fused QKV projection
       GemmDesc d = make_gemm_desc();
       d.M = (int)M; d.N = 3 * D; d.K = D; d.groups = G;
@@ -309,6 +315,12 @@ static int backbone_forward_impl(const v2s_group_t* gs, int G, int B, int mode, 
       for (int g = 0; g < G; ++g) {
         d.A[g] = ctx[g]; d.B[g] = weight_ptr(gs[g], at, lo + L_WO);
         d.bias[g] = gs[g].params + lo + L_BO; d.resid[g] = xin[g]; d.out[g] = xmid[g];
+        if (ln_fuse) {     // LN2 of this block, fused
+          d.ln_out[g] = saved(g) ? (void*)sb(g, p.s_layer[l].xn2) : (void*)fb(g, p.f_xn);
+          d.ln_gamma[g] = gs[g].params + lo + L_LN2W; d.ln_beta[g] = gs[g].params + lo + L_LN2B;
+          d.ln_mean[g] = saved(g) ? (float*)sb(g, p.s_layer[l].mean2) : nullptr;
+          d.ln_rstd[g] = saved(g) ? (float*)sb(g, p.s_layer[l].rstd2) : nullptr;
+        }
       }
       V2S_TRY(run_gemm(d, at, at, 0, st, prof::C_PROJ));
     }
@@ -321,8 +333,10 @@ static int backbone_forward_impl(const v2s_group_t* gs, int G, int B, int mode, 
         if (saved(g)) { xn2[g] = sb(g, p.s_layer[l].xn2); m2[g] = (float*)sb(g, p.s_layer[l].mean2); r2[g] = (float*)sb(g, p.s_layer[l].rstd2); }
         else { xn2[g] = fb(g, p.f_xn); m2[g] = nullptr; r2[g] = nullptr; }
       }
-      { prof::Scope sc(prof::C_LN_F, (double)M * D * (4 + p.es) * G, st);
-        V2S_TRY(launch_ln_fwd(xm, gam, bet, xn2, m2, r2, G, (int)M, at, st)); }
+      if (!ln_fuse) {
+        prof::Scope sc(prof::C_LN_F, (double)M * D * (4 + p.es) * G, st);
+        V2S_TRY(launch_ln_fwd(xm, gam, bet, xn2, m2, r2, G, (int)M, at, st));
+      }
       GemmDesc d = make_gemm_desc();   // fc1 + GELU
       d.M = (int)M; d.N = DF; d.K = D; d.groups = G;
       d.a_rs = D; d.a_cs = 1; d.b_rs = 1; d.b_cs = D; d.epi = EPI_BIAS_GELU; d.ldc = DF;
@@ -339,8 +353,16 @@ static int backbone_forward_impl(const v2s_group_t* gs, int G, int B, int mode, 
       for (int g = 0; g < G; ++g) {
         d.A[g] = h[g]; d.B[g] = weight_ptr(gs[g], at, lo + L_W2);
         d.bias[g] = gs[g].params + lo + L_B2; d.resid[g] = xmid[g]; d.out[g] = xout[g];
+        if (ln_fuse && l + 1 < NL) {     // LN1 of the next block, fused
+          const int64_t ln = layer_off(l + 1);
+          d.ln_out[g] = saved(g) ? (void*)sb(g, p.s_layer[l + 1].xn1) : (void*)fb(g, p.f_xn);
+          d.ln_gamma[g] = gs[g].params + ln + L_LN1W; d.ln_beta[g] = gs[g].params + ln + L_LN1B;
+          d.ln_mean[g] = saved(g) ? (float*)sb(g, p.s_layer[l + 1].mean1) : nullptr;
+          d.ln_rstd[g] = saved(g) ? (float*)sb(g, p.s_layer[l + 1].rstd1) : nullptr;
+        }
       }
       V2S_TRY(run_gemm(d, at, at, 0, st, prof::C_FC2));
+      ln1_done = ln_fuse && l + 1 < NL;
     }
     for (int g = 0; g < G; ++g) x_cur[g] = xout[g];
   }

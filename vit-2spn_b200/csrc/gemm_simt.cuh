@@ -33,6 +33,12 @@ struct GemmDesc {
   const float* mask[MAXG];
   void* out[MAXG];
   void* out2[MAXG];
+  // EPI_BIAS_RESID, tensor-core path, N == 192 only: LayerNorm of the result row fused into the epilogue
+  void* ln_out[MAXG];          // bf16 [M,192] normalised output (NULL: no fusion)
+  const float* ln_gamma[MAXG];
+  const float* ln_beta[MAXG];
+  float* ln_mean[MAXG];        // optional [M]
+  float* ln_rstd[MAXG];
   float* rowsum_out[MAXG];  // EPI_ACCUM, tensor-core path only: rowsum_out[m] += sum_k A(m,k) (bias gradient for free)
   int64_t ldc;
   float alpha;

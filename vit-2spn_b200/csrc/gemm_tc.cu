@@ -31,7 +31,7 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int CHUNK = 32;                         // epilogue column chunk
 constexpr int N_CHUNKS = BN / CHUNK;              // 6
 constexpr int SMEM_LIMIT = 232448;                // 227 KB opt-in maximum per CTA
-constexpr int SMEM_BAR_BYTES = 3072;             // mbarriers (first 1 KB) + 2 KB constant ones tile for the row-sum MMA
+constexpr int SMEM_BAR_BYTES = 8192;             // mbarriers (1 KB) + 2 KB ones tile (row-sum MMA) + 4 KB LayerNorm partial sums
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;                   // TMEM column stride between accumulator stages
 constexpr int N_THREADS = 640;                    // 4 control/idle warps + 16 epilogue warps
@@ -56,6 +56,9 @@ template <int EPI, bool OUT_BF16> struct Cfg {
 struct alignas(64) TcParams {
   CUtensorMap tmA[MAXG], tmB[MAXG], tmOut[MAXG], tmOut2[MAXG], tmAux[MAXG];
   const float* bias[MAXG];
+  // T_RESID with fused LayerNorm (ln != 0, N == 192): xn = LN(out) * gamma + beta -> tmOut2 (bf16), stats -> ln_mean/rstd
+  const float* ln_gamma[MAXG]; const float* ln_beta[MAXG]; float* ln_mean[MAXG]; float* ln_rstd[MAXG];
+  int ln;
   float* rowsum[MAXG];  // T_ACCUM: rowsum[m] += sum_k A(m,k), computed by an extra N=16 MMA against a ones tile
   int M, N, K;
   int tiles_m, tiles_n, splits, kb_total, kb_per_split, groups, total_tiles;
@@ -113,7 +116,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
   uint64_t* aux_bar = tempty_bar + 2;            // [2][3] per epilogue group and staging buffer: aux chunk landed
   uint64_t* bres_bar = aux_bar + 6;              // B-stationary tile landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
-  uint8_t* ones_tile = reinterpret_cast<uint8_t*>(full_bar) + 1024;   // [16 rows x 128 B] K-major: row 0 = 1.0, rows 1..15 = 0
+  uint8_t* ones_tile = reinterpret_cast<uint8_t*>(full_bar) + 1024;
+  float2* ln_part = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(full_bar) + 3072);   // [2 groups][2 halves][128 rows]   // [16 rows x 128 B] K-major: row 0 = 1.0, rows 1..15 = 0
 
   // warp index through a shuffle: tells the compiler it is warp-uniform, so that the single-thread
   // roles below compile to straight uniform-datapath code (no per-lane convergence loops around TMA / MMA)
@@ -294,15 +298,21 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     constexpr bool HAS_AUX = (EPI == T_RESID || EPI == T_DGELU);
     constexpr int AUX_BYTES = (EPI == T_RESID) ? BM * CHUNK * 4 : BM * CHUNK * 2;
 
-    // auxiliary operand of this group's n-th chunk (chunks are numbered across the group's tiles)
+    // With the fused LayerNorm every tile takes 12 ring slots: 6 residual chunks (pass 1) + 6 normalised chunks.
+    const bool LN = (EPI == T_RESID) && p.ln != 0;
+    const int RPT = LN ? 2 * N_CHUNKS : N_CHUNKS;      // ring slots per tile
+    // auxiliary operand of ring slot n of this group (slots are numbered across the group's tiles)
     auto issue_aux = [&](int n) {
+      const int c = n % RPT;
+      if (c >= N_CHUNKS) return;                       // a pass-2 slot: nothing to prefetch
       int g, m_tile, split, n_tile;
-      if (!tile_at(ge + 2 * (n / N_CHUNKS), g, m_tile, split, n_tile)) return;
+      if (!tile_at(ge + 2 * (n / RPT), g, m_tile, split, n_tile)) return;
       const int b = n % N_STG;
       ptx::mbar_arrive_expect_tx(&abar[b], AUX_BYTES);
-      ptx::tma_load_2d(stg_base + b * STG_BYTES, &p.tmAux[g], &abar[b], n_tile * BN + (n % N_CHUNKS) * CHUNK, m_tile * BM);
+      ptx::tma_load_2d(stg_base + b * STG_BYTES, &p.tmAux[g], &abar[b], n_tile * BN + c * CHUNK, m_tile * BM);
     };
     if (HAS_AUX && issuer) { issue_aux(0); issue_aux(1); }
+    uint32_t aux_phase = 0;                            // bit b: parity of the next aux arrival on ring buffer b
 
     uint32_t acc_phase = 0;
     int cnt = 0;                                    // running chunk counter of this group
@@ -318,6 +328,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
       const bool write_u = (EPI == T_GELU) && ((p.out2_mask >> g) & 1);
       const float* bias = (EPI != T_ACCUM && EPI != T_DGELU) ? p.bias[g] : nullptr;
       const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + ge * ACC_STRIDE;
+      float ln_s1 = 0.f, ln_s2 = 0.f;
 #pragma unroll 1
       for (int c = 0; c < N_CHUNKS; ++c, ++cnt) {
         const int col0 = n0 + c * CHUNK;            // first column of the chunk
@@ -334,7 +345,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
           for (int k = 0; k < 16; ++k) r[k] = 0;
         }
         if (p.dbg) e_ld += clock64() - w0;
-        if (c == N_CHUNKS - 1) {                    // accumulator fully read: hand the stage back to the MMA warp
+        if (c == N_CHUNKS - 1 && !LN) {             // accumulator fully read: hand the stage back to the MMA warp
           if (EPI == T_ACCUM && hf == 0 && n_tile == 0 && p.rowsum[g] != nullptr) {
             uint32_t rs[16];
             ptx::tmem_ld_32x16(tlane + BN, rs);
@@ -363,14 +374,22 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
         // fp32 rows are 128 B (8 x 16-B pieces, SWIZZLE_128B), bf16 rows 64 B (4 pieces, SWIZZLE_64B)
         if (HAS_AUX) {
           if (p.dbg) w0 = clock64();
-          ptx::mbar_wait(&abar[b], (cnt / N_STG) & 1, p.err_flag, 5);
+          ptx::mbar_wait(&abar[b], (aux_phase >> b) & 1, p.err_flag, 5);
+          aux_phase ^= 1u << b;
           if (p.dbg) e_aux += clock64() - w0;
           if (EPI == T_RESID) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float4* slot = reinterpret_cast<float4*>(stg + row * 128 + (((hf * 4 + j) ^ (row & 7)) << 4));
               const float4 a = *slot;
-              *slot = make_float4(v[4 * j] + a.x, v[4 * j + 1] + a.y, v[4 * j + 2] + a.z, v[4 * j + 3] + a.w);
+              v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+              *slot = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (LN) {     // row statistics, and the finished row back into TMEM for the normalisation pass
+              uint32_t xr[16];
+#pragma unroll
+              for (int k = 0; k < 16; ++k) { ln_s1 += v[k]; ln_s2 = fmaf(v[k], v[k], ln_s2); xr[k] = __float_as_uint(v[k]); }
+              ptx::tmem_st_32x16(tlane + c * CHUNK + hf * 16, xr);
             }
           } else {
 #pragma unroll
@@ -431,6 +450,60 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
           ptx::tma_commit_group();
           if (N_STG == 3) ptx::tma_wait_group_read<1>();   // store of chunk cnt-1 has left its buffer
           if (HAS_AUX) issue_aux(cnt + 2);                 // ... which is the buffer of chunk cnt+2
+        }
+      }
+      if (EPI == T_RESID && LN) {
+        // ---- fused LayerNorm over the finished 192-wide row (two threads per row: exchange partial sums) ----
+        ptx::tmem_st_wait();
+        ln_part[(ge * 2 + hf) * BM + row] = make_float2(ln_s1, ln_s2);
+        ptx::bar_sync(bar_id, 256);
+        const float2 other = ln_part[(ge * 2 + (hf ^ 1)) * BM + row];
+        const float mean = (ln_s1 + other.x) * (1.0f / BN);
+        const float var = fmaxf((ln_s2 + other.y) * (1.0f / BN) - mean * mean, 0.f);
+        const float rstd = 1.0f / sqrtf(var + LN_EPS);
+        if (hf == 0 && m0 + row < p.M && p.ln_mean[g] != nullptr) {
+          p.ln_mean[g][m0 + row] = mean;
+          p.ln_rstd[g][m0 + row] = rstd;
+        }
+        const float* gam = p.ln_gamma[g];
+        const float* bet = p.ln_beta[g];
+#pragma unroll 1
+        for (int c = 0; c < N_CHUNKS; ++c, ++cnt) {
+          const int colh = c * CHUNK + hf * 16;
+          const int b = cnt % N_STG;
+          uint8_t* stg = stg_base + b * STG_BYTES;
+          uint32_t r[16];
+          ptx::tmem_ld_32x16(tlane + colh, r);
+          ptx::tmem_ld_wait();
+          if (c == N_CHUNKS - 1) {                  // accumulator (now holding the row) fully read
+            ptx::tc_fence_before();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[ge]);
+          }
+          float v[16];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 gg = __ldg(reinterpret_cast<const float4*>(gam + colh) + k);
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bet + colh) + k);
+            v[4 * k] = (__uint_as_float(r[4 * k]) - mean) * rstd * gg.x + bb.x;
+            v[4 * k + 1] = (__uint_as_float(r[4 * k + 1]) - mean) * rstd * gg.y + bb.y;
+            v[4 * k + 2] = (__uint_as_float(r[4 * k + 2]) - mean) * rstd * gg.z + bb.z;
+            v[4 * k + 3] = (__uint_as_float(r[4 * k + 3]) - mean) * rstd * gg.w + bb.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {             // bf16 chunk: 64-byte rows, SWIZZLE_64B, first 8 KB of the buffer
+            uint4 o;
+            o.x = pack_bf16(v[8 * j], v[8 * j + 1]); o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+            o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+            *reinterpret_cast<uint4*>(stg + row * 64 + (((hf * 2 + j) ^ ((row >> 1) & 3)) << 4)) = o;
+          }
+          ptx::fence_proxy_async();
+          ptx::bar_sync(bar_id, 256);
+          if (issuer) {
+            ptx::tma_store_2d(&p.tmOut2[g], stg, c * CHUNK, m0);
+            ptx::tma_commit_group();
+            ptx::tma_wait_group_read<1>();
+            issue_aux(cnt + 2);
+          }
         }
       }
     }
@@ -690,6 +763,12 @@ int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t strea
     if (epi == T_DGELU) V2S_TRY(get_map(&p.tmAux[g], d.aux[g], d.N, d.M, d.ldc, CHUNK, BM, true, CU_TENSOR_MAP_SWIZZLE_64B));
     p.bias[g] = (epi == T_ACCUM || epi == T_DGELU) ? nullptr : d.bias[g];
     p.rowsum[g] = (epi == T_ACCUM) ? d.rowsum_out[g] : nullptr;
+    if (epi == T_RESID && d.ln_out[g] != nullptr) {
+      if (d.N != BN || d.ldc != BN) { set_error("gemm_tc: fused LayerNorm needs N == 192"); return 1; }
+      V2S_TRY(get_map(&p.tmOut2[g], d.ln_out[g], d.N, d.M, d.ldc, CHUNK, BM, true, CU_TENSOR_MAP_SWIZZLE_64B));
+      p.ln_gamma[g] = d.ln_gamma[g]; p.ln_beta[g] = d.ln_beta[g]; p.ln_mean[g] = d.ln_mean[g]; p.ln_rstd[g] = d.ln_rstd[g];
+      p.ln = 1;
+    }
   }
   int rc;
   switch (epi) {
