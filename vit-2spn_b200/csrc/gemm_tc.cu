@@ -1,17 +1,24 @@
-// tcgen05 / TMEM / TMA GEMM for sm_100a: persistent, warp-specialised, grouped (up to 4 backbones
-// per launch), bf16 operands with fp32 accumulation in tensor memory, fused epilogues staged through
-// shared memory and written with TMA (plain store or reduce-add).
+// tcgen05 / TMEM / TMA GEMM for sm_100a: persistent, warp-specialised, grouped (up to 4 backbones per
+// launch), bf16 operands with fp32 accumulation in tensor memory, fused epilogues staged through shared
+// memory and written with TMA (plain store or reduce-add).
 //
 //   C[M,N] (+)= A[M,K] * B[N,K]^T        A, B: K-major or MN-major (UMMA descriptor major bits)
 //
-// CTA = 640 threads: warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warp 2 TMEM allocator,
-// warps 4..19 epilogue: two groups of eight warps (warps w, w+4 of a group read TMEM lane quarter w%4 and
-// take the two 16-column halves of a chunk); group g drains accumulator stage g, i.e. the CTA's even /
-// odd tiles, so two epilogues and the MMAs of a third tile overlap.  Each group walks its 128x192 accumulator in six 32-column chunks through a
-// ring of three 16 KB staging buffers: [TMA-load the auxiliary operand (residual / pre-GELU) into
-// the buffer] -> thread-per-row math in place -> TMA store (or reduce-add) out of the same buffer.
-// Tile = 128 x 192 x 64; 3-stage smem ring (A 16 KB + B 24 KB per stage); 2 accumulator stages in
-// TMEM (2 x 192 of 512 columns).
+// CTA = 640 threads, one CTA per SM, tile 128 x 192 x 64:
+//   warp 0      TMA producer: operand ring in smem (depth chosen per variant from the 227 KB budget;
+//               "B-stationary" when K <= 192: the [192 x K] weight tile is loaded once per CTA)
+//   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16 128x192x16, accumulators double-buffered in
+//               TMEM (2 x 192 of 512 columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
+//               wgrad adds an N=16 MMA against a constant ones tile: bias gradient in columns [192,208)
+//   warps 2,3   store warps of the two epilogue groups: own every TMA store / reduce-add and the prefetch of the
+//               auxiliary operand (residual, pre-GELU activation) into the staging ring (warp 2 also owns TMEM)
+//   warps 4-19  epilogue: two groups of eight warps; group g drains accumulator stage g (the CTA's even / odd
+//               tiles).  Warps w, w+4 of a group read TMEM lane quarter w%4 (tcgen05.ld 32x32b) and take the
+//               two 16-column halves of each 32-column chunk: thread = one row x 16 columns.  Epilogues: bias,
+//               bias + residual (fp32 stream, updated in place in the staging buffer) with optional fused
+//               LayerNorm (row parked in TMEM, second pass writes the normalised bf16 row), bias + erf-GELU
+//               (writes u and gelu(u)), x gelu'(u), fp32 reduce-add (split-K wgrad).
+// Staging ring protocol: see the epilogue.  Every mbarrier wait is bounded (ptx::mbar_wait).
 #include <string.h>
 
 #include <unordered_map>
@@ -48,7 +55,7 @@ enum TcEpi : int {
 // auxiliary operand (prefetched two chunks ahead into the ring) and the plain bf16 store use 3 buffers;
 // bf16 chunks are 8 KB (SWIZZLE_64B), fp32 chunks and the GELU pair (u | h) 16 KB.
 template <int EPI, bool OUT_BF16> struct Cfg {
-  static constexpr int NSTG = (EPI == T_RESID || EPI == T_DGELU || (EPI == T_STORE && OUT_BF16)) ? 3 : 2;
+  static constexpr int NSTG = (EPI == T_ACCUM || (EPI == T_STORE && !OUT_BF16)) ? 2 : 3;
   static constexpr int STG = (OUT_BF16 && EPI != T_GELU) ? 8192 : 16384;
   static constexpr int STAGING_BYTES = 2 * NSTG * STG;
 };
@@ -115,7 +122,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
   uint64_t* tempty_bar = tfull_bar + 2;          // [2] accumulator drained
   uint64_t* aux_bar = tempty_bar + 2;            // [2][3] per epilogue group and staging buffer: aux chunk landed
   uint64_t* bres_bar = aux_bar + 6;              // B-stationary tile landed
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
+  uint64_t* sfull_bar = bres_bar + 1;            // [2][3] staging buffer written by the 256 epilogue threads of a group
+  uint64_t* sfree_bar = sfull_bar + 6;           // [2][3] staging buffer released by the group's store warp
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sfree_bar + 6);
   uint8_t* ones_tile = reinterpret_cast<uint8_t*>(full_bar) + 1024;
   float2* ln_part = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(full_bar) + 3072);   // [2 groups][2 halves][128 rows]   // [16 rows x 128 B] K-major: row 0 = 1.0, rows 1..15 = 0
 
@@ -133,7 +142,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], 8); }
-    for (int s = 0; s < 6; ++s) ptx::mbar_init(&aux_bar[s], 1);
+    for (int s = 0; s < 6; ++s) { ptx::mbar_init(&aux_bar[s], 1); ptx::mbar_init(&sfull_bar[s], 256); ptx::mbar_init(&sfree_bar[s], 1); }
     ptx::mbar_init(bres_bar, 1);
     ptx::fence_barrier_init();
   }
@@ -283,6 +292,69 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[2] = w_full; p.dbg[3] = w_tempty; p.dbg[4] = clock64() - mma_t0; p.dbg[5] = ntiles; }
+  } else if (warp == 2 || warp == 3) {
+    // ================= store warp of epilogue group ge (whole warp walks the loop; one elected lane issues) ====
+    const int ge = warp - 2;
+    uint8_t* stg_base = smem + p.op_bytes + ge * N_STG * STG_BYTES;
+    uint64_t* abar = aux_bar + ge * 3;
+    uint64_t* sfull = sfull_bar + ge * 3;
+    uint64_t* sfree = sfree_bar + ge * 3;
+    constexpr bool HAS_AUX = (EPI == T_RESID || EPI == T_DGELU);
+    constexpr int AUX_BYTES = (EPI == T_RESID) ? BM * CHUNK * 4 : BM * CHUNK * 2;
+    const bool LN = (EPI == T_RESID) && p.ln != 0;
+    const int RPT = LN ? 2 * N_CHUNKS : N_CHUNKS;
+    // slot n becomes reusable: prefetch the auxiliary operand of its next user into the buffer, or release it
+    auto recycle = [&](int n) {
+      const int next = n + N_STG, c = next % RPT, b = next % N_STG;
+      int g, m_tile, split, n_tile;
+      if (!tile_at(ge + 2 * (next / RPT), g, m_tile, split, n_tile)) return;     // no further user
+      if (HAS_AUX && c < N_CHUNKS) {
+        ptx::mbar_arrive_expect_tx(&abar[b], AUX_BYTES);
+        ptx::tma_load_2d(stg_base + b * STG_BYTES, &p.tmAux[g], &abar[b], n_tile * BN + c * CHUNK, m_tile * BM);
+      } else {
+        ptx::mbar_arrive(&sfree[b]);
+      }
+    };
+    if (HAS_AUX && ptx::elect_one()) {
+      for (int n = -N_STG; n < 0; ++n) recycle(n);     // all buffers start free: prefetch for slots 0..N_STG-1
+    }
+    __syncwarp();
+    uint32_t full_par = 0;
+    int n = 0;
+    int g, m_tile, split, n_tile;
+    for (int i = ge; tile_at(i, g, m_tile, split, n_tile); i += 2) {
+      const int m0 = m_tile * BM, n0 = n_tile * BN;
+      const bool write_u = (EPI == T_GELU) && ((p.out2_mask >> g) & 1) && !(p.dbg_flags & 8);
+#pragma unroll 1
+      for (int c = 0; c < RPT; ++c, ++n) {
+        const int b = n % N_STG;
+        ptx::mbar_wait(&sfull[b], (full_par >> b) & 1, p.err_flag, 8);
+        full_par ^= 1u << b;
+        if (ptx::elect_one()) {
+          uint8_t* stg = stg_base + b * STG_BYTES;
+          if (!(p.dbg_flags & 4)) {
+            if (c < N_CHUNKS) {
+              const int col0 = n0 + c * CHUNK;
+              if (col0 < p.N) {
+                if (EPI == T_ACCUM) ptx::tma_reduce_add_2d(&p.tmOut[g], stg, col0, m0);
+                else ptx::tma_store_2d(&p.tmOut[g], stg, col0, m0);
+                if (write_u) ptx::tma_store_2d(&p.tmOut2[g], stg + 8192, col0, m0);
+              }
+            } else {
+              ptx::tma_store_2d(&p.tmOut2[g], stg, (c - N_CHUNKS) * CHUNK, m0);   // normalised row chunk
+            }
+          }
+          ptx::tma_commit_group();
+          if (n >= 1) {
+            ptx::tma_wait_group_read<1>();             // the store of slot n-1 has left its buffer
+            recycle(n - 1);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (ptx::elect_one()) ptx::tma_wait_group<0>();
+    __syncwarp();
   } else if (warp >= 4) {
     // ================= epilogue =================
     // 16 warps = 2 groups of 8.  Group ge drains accumulator stage ge.  Inside a group, warps w and w+4 share
@@ -291,32 +363,39 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     const int q = warp & 3;                         // TMEM lane quarter
     const int hf = ((warp - 4) >> 2) & 1;           // column half of the chunk
     const int row = q * 32 + lane;                  // row within the 128-row tile
-    const bool issuer = (warp == 4 + 8 * ge) && lane == 0;   // owns the group's bulk-async (TMA store) groups
     uint8_t* stg_base = smem + p.op_bytes + ge * N_STG * STG_BYTES;
     uint64_t* abar = aux_bar + ge * 3;
+    uint64_t* sfull = sfull_bar + ge * 3;
+    uint64_t* sfree = sfree_bar + ge * 3;
     const int bar_id = 1 + ge;
     constexpr bool HAS_AUX = (EPI == T_RESID || EPI == T_DGELU);
-    constexpr int AUX_BYTES = (EPI == T_RESID) ? BM * CHUNK * 4 : BM * CHUNK * 2;
-
     // With the fused LayerNorm every tile takes 12 ring slots: 6 residual chunks (pass 1) + 6 normalised chunks.
     const bool LN = (EPI == T_RESID) && p.ln != 0;
     const int RPT = LN ? 2 * N_CHUNKS : N_CHUNKS;      // ring slots per tile
-    // auxiliary operand of ring slot n of this group (slots are numbered across the group's tiles)
-    auto issue_aux = [&](int n) {
-      const int c = n % RPT;
-      if (c >= N_CHUNKS) return;                       // a pass-2 slot: nothing to prefetch
-      int g, m_tile, split, n_tile;
-      if (!tile_at(ge + 2 * (n / RPT), g, m_tile, split, n_tile)) return;
+    // Staging ring protocol (slot n uses buffer n % N_STG).  The group's store warp (warp 2 + ge) owns all TMA
+    // traffic of the ring: it stores a slot once the 256 epilogue threads have arrived on sfull, and when an
+    // older store has left its buffer it either prefetches the next auxiliary operand into it (arrival on
+    // abar) or releases it (arrival on sfree).  The epilogue threads never wait for a store of their own.
+    uint32_t aux_par = 0, free_par = 0;                // per-buffer parities of the next abar / sfree completion
+    auto acquire_slot = [&](int n) {
       const int b = n % N_STG;
-      ptx::mbar_arrive_expect_tx(&abar[b], AUX_BYTES);
-      ptx::tma_load_2d(stg_base + b * STG_BYTES, &p.tmAux[g], &abar[b], n_tile * BN + c * CHUNK, m_tile * BM);
+      if (HAS_AUX && (n % RPT) < N_CHUNKS) {
+        ptx::mbar_wait(&abar[b], (aux_par >> b) & 1, p.err_flag, 5);
+        aux_par ^= 1u << b;
+      } else if (n >= N_STG) {
+        ptx::mbar_wait(&sfree[b], (free_par >> b) & 1, p.err_flag, 7);
+        free_par ^= 1u << b;
+      }
     };
-    if (HAS_AUX && issuer) { issue_aux(0); issue_aux(1); }
-    uint32_t aux_phase = 0;                            // bit b: parity of the next aux arrival on ring buffer b
+    auto publish_slot = [&](int n) {
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(&sfull[n % N_STG]);
+    };
 
     uint32_t acc_phase = 0;
     int cnt = 0;                                    // running chunk counter of this group
     long long e_tfull = 0, e_aux = 0, e_bar = 0, e_ld = 0; const long long epi_t0 = clock64();
+    (void)bar_id;
     int g, m_tile, split, n_tile;
     for (int i = ge; tile_at(i, g, m_tile, split, n_tile); i += 2) {
       const int m0 = m_tile * BM, n0 = n_tile * BN;
@@ -325,7 +404,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
       if (p.dbg) e_tfull += clock64() - w0;
       acc_phase ^= 1;
       ptx::tc_fence_after();
-      const bool write_u = (EPI == T_GELU) && ((p.out2_mask >> g) & 1);
+      const bool write_u = (EPI == T_GELU) && ((p.out2_mask >> g) & 1) && !(p.dbg_flags & 8);
       const float* bias = (EPI != T_ACCUM && EPI != T_DGELU) ? p.bias[g] : nullptr;
       const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + ge * ACC_STRIDE;
       float ln_s1 = 0.f, ln_s2 = 0.f;
@@ -355,7 +434,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
           ptx::tc_fence_before();
           if (lane == 0) ptx::mbar_arrive(&tempty_bar[ge]);
         }
-        if (p.dbg_flags & 4) continue;
         float v[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]);
@@ -368,15 +446,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
             v[4 * k] += bb.x; v[4 * k + 1] += bb.y; v[4 * k + 2] += bb.z; v[4 * k + 3] += bb.w;
           }
         }
-        // Buffer b is free here.  3-buffer rings: its previous store (chunk cnt-3) was retired by the
-        // issuer's wait_group.read<1> after the store of chunk cnt-2, which precedes the barrier of chunk
-        // cnt-1.  2-buffer rings: the issuer drains all stores before each barrier.
         // fp32 rows are 128 B (8 x 16-B pieces, SWIZZLE_128B), bf16 rows 64 B (4 pieces, SWIZZLE_64B)
+        if (p.dbg) w0 = clock64();
+        acquire_slot(cnt);                           // buffer b is ours (and holds the auxiliary operand, if any)
+        if (p.dbg) e_aux += clock64() - w0;
+        if (p.dbg_flags & 4) { publish_slot(cnt); continue; }
         if (HAS_AUX) {
-          if (p.dbg) w0 = clock64();
-          ptx::mbar_wait(&abar[b], (aux_phase >> b) & 1, p.err_flag, 5);
-          aux_phase ^= 1u << b;
-          if (p.dbg) e_aux += clock64() - w0;
           if (EPI == T_RESID) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -434,23 +509,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
             *reinterpret_cast<float4*>(stg + row * 128 + (((hf * 4 + j) ^ (row & 7)) << 4)) =
                 make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
-        ptx::fence_proxy_async();
-        // two-buffer rings: the store of chunk cnt-1 must have left its buffer before anyone passes this
-        // barrier and starts writing chunk cnt+1 into it
-        if (N_STG == 2 && issuer) ptx::tma_wait_group_read<0>();
-        if (p.dbg) w0 = clock64();
-        ptx::bar_sync(bar_id, 256);
-        if (p.dbg) e_bar += clock64() - w0;
-        if (issuer) {
-          if (col0 < p.N) {
-            if (EPI == T_ACCUM) ptx::tma_reduce_add_2d(&p.tmOut[g], stg, col0, m0);
-            else ptx::tma_store_2d(&p.tmOut[g], stg, col0, m0);
-            if (write_u) ptx::tma_store_2d(&p.tmOut2[g], stg + 8192, col0, m0);
-          }
-          ptx::tma_commit_group();
-          if (N_STG == 3) ptx::tma_wait_group_read<1>();   // store of chunk cnt-1 has left its buffer
-          if (HAS_AUX) issue_aux(cnt + 2);                 // ... which is the buffer of chunk cnt+2
-        }
+        publish_slot(cnt);
       }
       if (EPI == T_RESID && LN) {
         // ---- fused LayerNorm over the finished 192-wide row (two threads per row: exchange partial sums) ----
@@ -475,6 +534,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
           uint32_t r[16];
           ptx::tmem_ld_32x16(tlane + colh, r);
           ptx::tmem_ld_wait();
+          acquire_slot(cnt);
           if (c == N_CHUNKS - 1) {                  // accumulator (now holding the row) fully read
             ptx::tc_fence_before();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[ge]);
@@ -496,18 +556,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
             o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
             *reinterpret_cast<uint4*>(stg + row * 64 + (((hf * 2 + j) ^ ((row >> 1) & 3)) << 4)) = o;
           }
-          ptx::fence_proxy_async();
-          ptx::bar_sync(bar_id, 256);
-          if (issuer) {
-            ptx::tma_store_2d(&p.tmOut2[g], stg, c * CHUNK, m0);
-            ptx::tma_commit_group();
-            ptx::tma_wait_group_read<1>();
-            issue_aux(cnt + 2);
-          }
+          publish_slot(cnt);
         }
       }
     }
-    if (issuer) ptx::tma_wait_group<0>();
     if (p.dbg && blockIdx.x == 0 && (threadIdx.x == 128 || threadIdx.x == 384 + 37)) {
       long long* d = p.dbg + 8 + (threadIdx.x == 128 ? 0 : 8);
       d[0] = e_tfull; d[1] = e_aux; d[2] = e_bar; d[3] = e_ld; d[4] = clock64() - epi_t0; d[5] = cnt;
