@@ -267,19 +267,38 @@ def main():
         step(x1, x2)
     rep = _lib.prof_report()
     _lib.prof_enable(False)
-    classes = {k: {"launches": n // nprof, "ms_per_step": ms / nprof,
-                   "work_per_step": w / nprof} for k, (n, ms, w) in rep.items()}
+    classes = {k: {"launches": n // nprof, "ms_per_step": ms / nprof, "work_per_step": w / nprof,
+                   "bytes_per_step": nb / nprof} for k, (n, ms, w, nb) in rep.items()}
     tensor_classes = [k for k in classes if k.startswith("gemm") or k.startswith("attn")]
     roofline = None
+    try:
+        ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_r01_traffic.json")))
+    except Exception:
+        ncu_traffic = {}
     if tensor_classes:
+        # dominant kernel class by device time; its bound is whichever roofline time is larger for its
+        # ALGORITHMIC flops / bytes (operands and outputs once); burst peaks do not apply inside a step
         dom = max(tensor_classes, key=lambda k: classes[k]["ms_per_step"])
         c = classes[dom]
-        ach = c["work_per_step"] / (c["ms_per_step"] * 1e-3) / 1e12
-        peak = pk["bf16_tflops_sustained"]
-        roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": f"bf16_tflops_sustained ({pk_src})",
-                    "launches_per_step": c["launches"], "ms_per_step": c["ms_per_step"],
-                    "share_of_step": c["ms_per_step"] / ms_per_step}
+        t_tensor = c["work_per_step"] / (pk["bf16_tflops_sustained"] * 1e12)
+        t_hbm = c["bytes_per_step"] / (pk["hbm_gbs"] * 1e9)
+        sec = c["ms_per_step"] * 1e-3
+        tr = ncu_traffic.get(dom, {}).get("dram_bytes_per_launch")
+        if t_hbm >= t_tensor:
+            ach = c["bytes_per_step"] / sec / 1e9
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": ach / pk["hbm_gbs"], "traffic": tr, "peak_source": f"hbm_gbs ({pk_src})"}
+        else:
+            ach = c["work_per_step"] / sec / 1e12
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"],
+                        "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"], "traffic": tr,
+                        "peak_source": f"bf16_tflops_sustained ({pk_src})"}
+        roofline.update({"launches_per_step": c["launches"], "ms_per_step": c["ms_per_step"],
+                         "share_of_step": c["ms_per_step"] / ms_per_step,
+                         "algorithmic_bytes_per_launch": c["bytes_per_step"] / max(c["launches"], 1),
+                         "algorithmic_flops_per_launch": c["work_per_step"] / max(c["launches"], 1),
+                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, "
+                                           "profiles/ncu_r01_traffic.json (cold-cache capture)"})
     step_tflops = value / world * FLOP_PER_PAIR / 1e12
 
     cpu_baseline = None

@@ -36,7 +36,7 @@ def run(which, m, n, k, label):
     tf = 2.0 * m * n * k / (us * 1e-6) / 1e12
     print(f"{label:26s} {m}x{n}x{k}: {us:7.1f} us  {tf:6.1f} TF/s | producer wait_empty {d[0]} / total {d[1]} | "
           f"mma wait_full {d[2]} wait_tempty {d[3]} total {d[4]} tiles {d[5]} | "
-          f"epi0 wait_tfull {d[8]} wait_aux {d[9]} bar {d[10]} tmem_ld {d[11]} total {d[12]} chunks {d[13]} | "
+          f"epi0 wait_tfull {d[8]} acquire {d[9]} publish {d[10]} tmem_ld {d[11]} total {d[12]} chunks {d[13]} | "
           f"epi1 wait_tfull {d[16]} bar {d[18]} tmem_ld {d[19]} total {d[20]} chunks {d[21]}")
 
 

@@ -114,13 +114,13 @@ def prof_enable(on: bool) -> None:
 
 
 def prof_report():
-    """{class: (launches, total_ms, work)} since prof_enable(True); synchronises the device."""
+    """{class: (launches, total_ms, work, algorithmic_bytes)} since prof_enable(True); synchronises the device."""
     buf = C.create_string_buffer(8192)
     check(lib.v2s_prof_report(buf, 8192), "prof_report")
     out = {}
     for line in buf.value.decode().splitlines():
-        name, n, ms, work = line.split()
-        out[name] = (int(n), float(ms), float(work))
+        name, n, ms, work, nbytes = line.split()
+        out[name] = (int(n), float(ms), float(work), float(nbytes))
     return out
 
 

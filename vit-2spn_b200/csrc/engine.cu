@@ -26,7 +26,7 @@ void set_error(const char* fmt, ...) {
 // ---- optional per-kernel-class device timing (bench.py roofline; off by default) -------------
 namespace prof {
 constexpr int MAX_REC = 8192;
-struct Rec { int cls; double work; cudaEvent_t a, b; };
+struct Rec { int cls; double work; double bytes; cudaEvent_t a, b; };
 static bool enabled = false;
 static Rec recs[MAX_REC];
 static int n_recs = 0;
@@ -38,11 +38,11 @@ enum { C_PATCH, C_QKV, C_PROJ, C_FC1, C_FC2, C_DGRAD, C_WGRAD, C_ATTN_F, C_ATTN_
 struct Scope {
   int idx = -1;
   cudaStream_t st;
-  Scope(int cls, double work, cudaStream_t s) : st(s) {
+  Scope(int cls, double work, cudaStream_t s, double bytes = 0.0) : st(s) {
     if (!enabled || n_recs >= MAX_REC) return;
     idx = n_recs++;
     if (idx >= n_events) { cudaEventCreate(&recs[idx].a); cudaEventCreate(&recs[idx].b); n_events = idx + 1; }
-    recs[idx].cls = cls; recs[idx].work = work;
+    recs[idx].cls = cls; recs[idx].work = work; recs[idx].bytes = bytes;
     cudaEventRecord(recs[idx].a, st);
   }
   ~Scope() { if (idx >= 0) cudaEventRecord(recs[idx].b, st); }
@@ -165,7 +165,12 @@ int max_slot(const v2s_group_t* g, int n) {
 }
 
 int run_gemm(const GemmDesc& d, int ta, int tb, int to, cudaStream_t s, int cls = prof::C_MISC) {
-  prof::Scope scope(cls, 2.0 * d.M * d.N * (double)d.K * d.groups, s);
+  // algorithmic HBM bytes: both operands and the output once (+ residual / auxiliary operand, second output)
+  const double ea = ta ? 2.0 : 4.0, eb = tb ? 2.0 : 4.0, eo = to ? 2.0 : 4.0;
+  double bytes = (double)d.M * d.K * ea + (double)d.N * d.K * eb + (double)d.M * d.N * eo;
+  if (d.epi == EPI_BIAS_RESID) bytes += (double)d.M * d.N * 4.0 + (d.ln_out[0] ? (double)d.M * d.N * 2.0 : 0.0);
+  if (d.epi == EPI_DGELU || (d.epi == EPI_BIAS_GELU && d.out[0])) bytes += (double)d.M * d.N * 2.0;
+  prof::Scope scope(cls, 2.0 * d.M * d.N * (double)d.K * d.groups, s, bytes * d.groups);
   int handled = 0;
   V2S_TRY(launch_gemm_tc(d, ta, tb, to, s, &handled));
   if (handled) return 0;
@@ -179,13 +184,13 @@ inline const void* weight_ptr(const v2s_group_t& g, int at, int64_t off) {
 
 int launch_attention_fwd(const void* const* qkv, void* const* ctx, float* const* lse, int groups, int B, int at,
                          cudaStream_t s) {
-  prof::Scope scope(prof::C_ATTN_F, 4.0 * B * NH * (double)NT * NT * DH * groups, s);
+  prof::Scope scope(prof::C_ATTN_F, 4.0 * B * NH * (double)NT * NT * DH * groups, s, (double)B * NT * 4 * D * 2.0 * groups);
   if (at == 1 && tc_enabled()) return launch_attn_fwd_tc(qkv, ctx, lse, groups, B, s);
   return launch_attn_fwd_simt(qkv, ctx, lse, groups, B, at, s);
 }
 int launch_attention_bwd(const void* const* qkv, const void* const* ctx, const float* const* lse,
                          const void* const* dctx, void* const* dqkv, int groups, int B, int at, cudaStream_t s) {
-  prof::Scope scope(prof::C_ATTN_B, 8.0 * B * NH * (double)NT * NT * DH * groups, s);
+  prof::Scope scope(prof::C_ATTN_B, 10.0 * B * NH * (double)NT * NT * DH * groups, s, (double)B * NT * 8 * D * 2.0 * groups);
   if (at == 1 && tc_enabled()) return launch_attn_bwd_tc(qkv, ctx, lse, dctx, dqkv, groups, B, s);
   return launch_attn_bwd_simt(qkv, ctx, lse, dctx, dqkv, groups, B, at, s);
 }
@@ -787,23 +792,24 @@ int v2s_prof_enable(int on) {
   return 0;
 }
 
-// writes one line per kernel class: "<name> <launches> <total_ms> <work>" (work = FLOPs for
-// GEMM/attention classes, bytes for the memory-bound ones); synchronises the device.
+// writes one line per kernel class: "<name> <launches> <total_ms> <work> <bytes>" (work = FLOPs for
+// GEMM/attention classes, bytes for the memory-bound ones; bytes = algorithmic HBM bytes); synchronises.
 int v2s_prof_report(char* host_buf, int64_t buf_bytes) {
   if (!host_buf || buf_bytes < 64) { set_error("prof_report: buffer too small"); return 1; }
   V2S_CUDA_OK(cudaDeviceSynchronize());
-  double ms[prof::C_COUNT] = {0}, work[prof::C_COUNT] = {0};
+  double ms[prof::C_COUNT] = {0}, work[prof::C_COUNT] = {0}, byt[prof::C_COUNT] = {0};
   int cnt[prof::C_COUNT] = {0};
   for (int i = 0; i < prof::n_recs; ++i) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, prof::recs[i].a, prof::recs[i].b) != cudaSuccess) continue;
     ms[prof::recs[i].cls] += t; work[prof::recs[i].cls] += prof::recs[i].work; cnt[prof::recs[i].cls]++;
+    byt[prof::recs[i].cls] += prof::recs[i].bytes > 0 ? prof::recs[i].bytes : prof::recs[i].work;
   }
   int64_t off = 0;
   host_buf[0] = 0;
   for (int c = 0; c < prof::C_COUNT; ++c) {
     if (!cnt[c]) continue;
-    int n = snprintf(host_buf + off, (size_t)(buf_bytes - off), "%s %d %.6f %.6e\n", prof::names[c], cnt[c], ms[c], work[c]);
+    int n = snprintf(host_buf + off, (size_t)(buf_bytes - off), "%s %d %.6f %.6e %.6e\n", prof::names[c], cnt[c], ms[c], work[c], byt[c]);
     if (n < 0 || off + n >= buf_bytes) break;
     off += n;
   }

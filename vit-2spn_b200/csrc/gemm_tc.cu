@@ -77,7 +77,7 @@ struct alignas(64) TcParams {
   int op_bytes;       // bytes of the operand region (staging ring starts here)
   int* err_flag;
   long long* dbg;     // optional per-role cycle counters of CTA 0 (V2S_GEMM_DEBUG=1)
-  int dbg_flags;      // experiments (V2S_GEMM_DEBUG=<n>): bit1 skip TMEM loads, bit2 skip staging + stores
+  int dbg_flags;      // experiments (V2S_GEMM_DEBUG=<n>): 2 skip TMEM loads, 4 skip epilogue math + stores, 8 skip the u store, 16 skip TMA stores only
 };
 
 // fast erf-GELU for the bf16 path: Abramowitz-Stegun 7.1.26, |erf error| < 1.5e-7 (far below bf16
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
         full_par ^= 1u << b;
         if (ptx::elect_one()) {
           uint8_t* stg = stg_base + b * STG_BYTES;
-          if (!(p.dbg_flags & 4)) {
+          if (!(p.dbg_flags & (4 | 16))) {
             if (c < N_CHUNKS) {
               const int col0 = n0 + c * CHUNK;
               if (col0 < p.N) {
@@ -387,14 +387,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
         free_par ^= 1u << b;
       }
     };
+    long long e_pub = 0;
     auto publish_slot = [&](int n) {
+      const long long t0 = p.dbg ? clock64() : 0;
       ptx::fence_proxy_async();
       ptx::mbar_arrive(&sfull[n % N_STG]);
+      if (p.dbg) e_pub += clock64() - t0;
     };
 
     uint32_t acc_phase = 0;
     int cnt = 0;                                    // running chunk counter of this group
-    long long e_tfull = 0, e_aux = 0, e_bar = 0, e_ld = 0; const long long epi_t0 = clock64();
+    long long e_tfull = 0, e_aux = 0, e_ld = 0; const long long epi_t0 = clock64();
     (void)bar_id;
     int g, m_tile, split, n_tile;
     for (int i = ge; tile_at(i, g, m_tile, split, n_tile); i += 2) {
@@ -562,7 +565,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     }
     if (p.dbg && blockIdx.x == 0 && (threadIdx.x == 128 || threadIdx.x == 384 + 37)) {
       long long* d = p.dbg + 8 + (threadIdx.x == 128 ? 0 : 8);
-      d[0] = e_tfull; d[1] = e_aux; d[2] = e_bar; d[3] = e_ld; d[4] = clock64() - epi_t0; d[5] = cnt;
+      d[0] = e_tfull; d[1] = e_aux; d[2] = e_pub; d[3] = e_ld; d[4] = clock64() - epi_t0; d[5] = cnt;
     }
   }
 
