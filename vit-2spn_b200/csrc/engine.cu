@@ -539,7 +539,7 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
 // =============================================================================================
 namespace {
 struct HeadsBufs {
-  float *a1, *y1, *a1t, *y1t, *dy1, *z, *y2, *pr, *zt, *dp, *dy2, *dz, *y2b;
+  float *a1, *y1, *a1t, *y1t, *dy1, *z, *y2, *pr, *zt, *dp, *dy2, *dz, *y2b, *part;
 };
 int heads_bufs(void* ws, int64_t ws_bytes, int B, HeadsBufs* hb) {
   const int64_t need = (int64_t)B * 8192 * 4;
@@ -562,6 +562,7 @@ int heads_bufs(void* ws, int64_t ws_bytes, int B, HeadsBufs* hb) {
   hb->dy2 = w; w += (int64_t)B * PO;
   hb->dz = w;  w += (int64_t)B * PO;
   hb->y2b = w; w += (int64_t)B * PO;
+  hb->part = w; w += (int64_t)B * PO * 8;   // split-K partial slabs
   return 0;
 }
 }  // namespace
@@ -581,12 +582,22 @@ static int heads_forward_impl(const float* hp, const float* fo, const float* ft,
     d.A[0] = x; d.B[0] = hp + woff; d.bias[0] = hp + boff; d.out[0] = out; d.out2[0] = out2; d.mask[0] = mask;
     return launch_gemm_simt(d, 0, 0, 0, st);
   };
+  // K = 1024 with a [B,128] output: too few tiles for a serial K loop → 8 K-splits into partial slabs, then a
+  // fixed-order reduction that also adds the bias (deterministic, unlike atomics)
+  auto linear_splitk = [&](const float* x, int k, int64_t woff, int64_t boff, int n, float* out) -> int {
+    GemmDesc d = make_gemm_desc();
+    d.M = B; d.N = n; d.K = k; d.a_rs = k; d.a_cs = 1; d.b_rs = 1; d.b_cs = k; d.epi = EPI_STORE; d.ldc = n;
+    d.split_k = 8; d.split_stride = (int64_t)B * n;
+    d.A[0] = x; d.B[0] = hp + woff; d.out[0] = hb.part;
+    V2S_TRY(launch_gemm_simt(d, 0, 0, 0, st));
+    return launch_splitk_reduce(out, hb.part, hp + boff, B, n, 8, st);
+  };
   V2S_TRY(linear(fo, PI, H_W1, H_B1, PH, EPI_BIAS_RELU_MASK, hb.a1, hb.y1, mo));
-  V2S_TRY(linear(hb.y1, PH, H_W2, H_B2, PO, EPI_STORE, hb.z, nullptr, nullptr));
+  V2S_TRY(linear_splitk(hb.y1, PH, H_W2, H_B2, PO, hb.z));
   V2S_TRY(linear(hb.z, PO, H_W3, H_B3, PO, EPI_BIAS_RELU_MASK, hb.y2, hb.y2b, nullptr));
   V2S_TRY(linear(hb.y2, PO, H_W4, H_B4, PO, EPI_STORE, hb.pr, nullptr, nullptr));
   V2S_TRY(linear(ft, PI, H_W1, H_B1, PH, EPI_BIAS_RELU_MASK, hb.a1t, hb.y1t, mt));
-  V2S_TRY(linear(hb.y1t, PH, H_W2, H_B2, PO, EPI_STORE, hb.zt, nullptr, nullptr));
+  V2S_TRY(linear_splitk(hb.y1t, PH, H_W2, H_B2, PO, hb.zt));
   if (pred_out) V2S_CUDA_OK(cudaMemcpyAsync(pred_out, hb.pr, (size_t)B * PO * 4, cudaMemcpyDeviceToDevice, st));
   if (tgt_out) V2S_CUDA_OK(cudaMemcpyAsync(tgt_out, hb.zt, (size_t)B * PO * 4, cudaMemcpyDeviceToDevice, st));
   return 0;
@@ -628,7 +639,13 @@ static int heads_backward_impl(const float* hp, float* hg, const float* fo, cons
   V2S_TRY(dgrad(hb.dz, PO, H_W2, PH, hb.dy1, EPI_DRELU_MASK, hb.a1, mo));
   V2S_TRY(wgrad(hb.dy1, PH, fo, PI, H_W1));
   V2S_TRY(bgrad(hb.dy1, PH, H_B1));
-  V2S_TRY(dgrad(hb.dy1, PH, H_W1, PI, dfo, EPI_STORE, nullptr, nullptr));
+  {   // d feat = dy1 W1: K = 1024 → split-K accumulate into the zeroed [B,384] output
+    V2S_CUDA_OK(cudaMemsetAsync(dfo, 0, (size_t)B * PI * sizeof(float), st));
+    GemmDesc d = make_gemm_desc();
+    d.M = B; d.N = PI; d.K = PH; d.a_rs = PH; d.a_cs = 1; d.b_rs = PI; d.b_cs = 1; d.epi = EPI_ACCUM; d.ldc = PI; d.split_k = 8;
+    d.A[0] = hb.dy1; d.B[0] = hp + H_W1; d.out[0] = dfo;
+    V2S_TRY(launch_gemm_simt(d, 0, 0, 0, st));
+  }
   return 0;
 }
 

@@ -7,12 +7,13 @@ namespace v2s {
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;
+constexpr int BK = 16, PAD = 4;   // tile = (16*TM) x (16*TM) x 16, 256 threads, TM x TM outputs per thread
 
 __device__ __forceinline__ int64_t remap_row(int64_t r) { return r + r / NP + 1; }
 
-template <typename TA, typename TB, typename TO>
+template <typename TA, typename TB, typename TO, int TM>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
+  constexpr int BM = 16 * TM, BN = 16 * TM;
   __shared__ float As[BK][BM + PAD];
   __shared__ float Bs[BK][BN + PAD];
   const int g = blockIdx.z;
@@ -29,20 +30,20 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
     k_end = min(d.K, k_begin + chunk);
   }
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
-  float acc[4][4];
+  float acc[TM][TM];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TM; ++j) acc[i][j] = 0.f;
 
   const bool a_kfast = (d.a_cs == 1);
   const bool b_kfast = (d.b_rs == 1);
 
   // register-prefetch double buffering: the global loads of tile k+1 are in flight while tile k is multiplied
-  float ra[4], rb[4];
+  float ra[TM], rb[TM];
   auto load_tile = [&](int k0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < TM; ++i) {
       const int e = tid + i * 256;
       int kk, mm;
       if (a_kfast) { kk = e % BK; mm = e / BK; } else { mm = e % BM; kk = e / BM; }
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
       ra[i] = v;
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < TM; ++i) {
       const int e = tid + i * 256;
       int kk, nn;
       if (b_kfast) { kk = e % BK; nn = e / BK; } else { nn = e % BN; kk = e / BN; }
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
   };
   auto store_tile = [&]() {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < TM; ++i) {
       const int e = tid + i * 256;
       if (a_kfast) As[e % BK][e / BK] = ra[i]; else As[e / BM][e % BM] = ra[i];
       if (b_kfast) Bs[e % BK][e / BK] = rb[i]; else Bs[e / BN][e % BN] = rb[i];
@@ -84,14 +85,13 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
     if (has_next) load_tile(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+      float a[TM], b[TM];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TM; ++i) { a[i] = As[kk][ty * TM + i]; b[i] = Bs[kk][tx * TM + i]; }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TM; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
     if (has_next) { store_tile(); __syncthreads(); }
@@ -104,17 +104,18 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
   TO* __restrict__ out = static_cast<TO*>(d.out[g]);
   TO* __restrict__ out2 = static_cast<TO*>(d.out2[g]);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
     if (m >= d.M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+    for (int j = 0; j < TM; ++j) {
+      const int n = n0 + tx * TM + j;
       if (n >= d.N) continue;
       float v = acc[i][j] * d.alpha;
       const int64_t idx = (int64_t)m * d.ldc + n;
       switch (d.epi) {
         case EPI_STORE:
+          if (d.split_k > 1) { out[idx + (int64_t)split * d.split_stride] = from_f<TO>(v); break; }   // partial slab
           if (bias) v += bias[n];
           out[idx] = from_f<TO>(v);
           break;
@@ -159,9 +160,15 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
 
 template <typename TA, typename TB, typename TO>
 int launch_t(const GemmDesc& d, cudaStream_t stream) {
-  const int tiles_m = (d.M + BM - 1) / BM, tiles_n = (d.N + BN - 1) / BN;
-  dim3 grid(tiles_m, tiles_n * (d.split_k > 1 ? d.split_k : 1), d.groups);
-  gemm_simt_kernel<TA, TB, TO><<<grid, 256, 0, stream>>>(d);
+  const int sk = d.split_k > 1 ? d.split_k : 1;
+  const int t64 = ((d.M + 63) / 64) * ((d.N + 63) / 64) * sk * d.groups;
+  if (t64 < 120) {       // small problem (the heads): 32x32 tiles put 4x more CTAs on the machine
+    dim3 grid((d.M + 31) / 32, ((d.N + 31) / 32) * sk, d.groups);
+    gemm_simt_kernel<TA, TB, TO, 2><<<grid, 256, 0, stream>>>(d);
+  } else {
+    dim3 grid((d.M + 63) / 64, ((d.N + 63) / 64) * sk, d.groups);
+    gemm_simt_kernel<TA, TB, TO, 4><<<grid, 256, 0, stream>>>(d);
+  }
   V2S_LAUNCH_CHECK();
   return 0;
 }
@@ -170,8 +177,8 @@ int launch_t(const GemmDesc& d, cudaStream_t stream) {
 
 int launch_gemm_simt(const GemmDesc& d, int ta, int tb, int to, cudaStream_t stream) {
   if (d.M <= 0 || d.N <= 0 || d.K <= 0) return 0;
-  if (d.split_k > 1 && d.epi != EPI_ACCUM) {
-    set_error("gemm_simt: split_k requires EPI_ACCUM");
+  if (d.split_k > 1 && d.epi != EPI_ACCUM && !(d.epi == EPI_STORE && d.split_stride > 0)) {
+    set_error("gemm_simt: split_k requires EPI_ACCUM, or EPI_STORE with a split_stride");
     return 1;
   }
   if (ta == 0 && tb == 0 && to == 0) return launch_t<float, float, float>(d, stream);

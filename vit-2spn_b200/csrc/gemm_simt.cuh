@@ -22,7 +22,8 @@ struct GemmDesc {
   int64_t b_rs, b_cs;  // B(k,n) = B[k*b_rs + n*b_cs]
   int a_remap;         // patch index b*196+p -> token row b*197+1+p: 1 = on A's m index, 2 = on A's k index
   int b_remap;         // same for the K index of B (wgrad of the patch embedding)
-  int split_k;         // number of K splits (EPI_ACCUM only)
+  int split_k;         // number of K splits: EPI_ACCUM (atomic adds), or EPI_STORE with split_stride > 0
+  int64_t split_stride; // EPI_STORE + split_k: split s writes its partial result at out + s * split_stride (no bias)
   int groups;
   const void* A[MAXG];
   const void* B[MAXG];

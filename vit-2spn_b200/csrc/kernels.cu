@@ -865,6 +865,22 @@ int launch_preprocess_u8(const uint8_t* src, float* dst, int B, cudaStream_t s) 
   return 0;
 }
 
+__global__ void splitk_reduce_kernel(float* __restrict__ out, const float* __restrict__ part,
+                                     const float* __restrict__ bias, int MN, int N, int splits) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < MN; i += gridDim.x * blockDim.x) {
+    float v = bias ? bias[i % N] : 0.f;
+    for (int s = 0; s < splits; ++s) v += part[(int64_t)s * MN + i];      // fixed order: deterministic
+    out[i] = v;
+  }
+}
+
+// out[m,n] = bias[n] + sum_s part[s][m][n]: deterministic second pass of a split-K GEMM
+int launch_splitk_reduce(float* out, const float* part, const float* bias, int M, int N, int splits, cudaStream_t s) {
+  splitk_reduce_kernel<<<grid_for((int64_t)M * N, 256, 148), 256, 0, s>>>(out, part, bias, M * N, N, splits);
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_zero(void* p, int64_t bytes, cudaStream_t s) {
   V2S_CUDA_OK(cudaMemsetAsync(p, 0, (size_t)bytes, s));
   return 0;

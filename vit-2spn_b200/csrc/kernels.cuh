@@ -52,5 +52,6 @@ int launch_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t s);
 int launch_dropout_mask(float* mask, int64_t n, float p, uint64_t seed, uint64_t offset, cudaStream_t s);
 int launch_preprocess_u8(const uint8_t* src, float* dst, int B, cudaStream_t s);
 int launch_zero(void* p, int64_t bytes, cudaStream_t s);
+int launch_splitk_reduce(float* out, const float* part, const float* bias, int M, int N, int splits, cudaStream_t s);
 
 }  // namespace v2s
