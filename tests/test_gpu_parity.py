@@ -154,6 +154,8 @@ def test_fused_ssp_step_equals_autograd_path(golden, dev, mode):
     g3 = {n: p.grad.cpu() for n, p in m2.named_parameters() if p.grad is not None}
     # (atomic accumulation order differs between runs, and in bf16 that noise is re-rounded: compare in rel-L2)
     for k in list(g2)[:40]:
+        if k.endswith("key.bias"):
+            continue        # d loss / d key-bias is exactly 0 (softmax is shift invariant): pure rounding noise
         err = float((g3[k] - 2 * g2[k]).norm() / (2 * g2[k]).norm().clamp_min(1e-12))
         assert err <= (1e-4 if mode == "fp32" else 5e-2), (k, err)
 
