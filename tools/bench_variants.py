@@ -1,0 +1,153 @@
+#!/usr/bin/env python
+"""Secondary timings named by SURVEY.md §8(d) / §8(f) that bench.py's single line does not carry.
+
+    python tools/bench_variants.py [--batch 128] [--iters 30] > profiles/variants_rNN.json
+
+* ssp_micro_step      — forward + backward only, gradients accumulated (no optimizer / EMA)
+* ssp_accum8          — the reference recipe: 8 micro-steps + 1 Adam + 1 EMA (ref:ssp_vit2spn_tiny.py:205-219)
+* ssp_accum1          — accumulation_steps = 1 (bench.py's step)
+* adam / ema          — the two optimiser-side kernels alone, with their algorithmic HBM bytes
+* single_stream_step  — SingleStreamNetwork (ref:dsn_ssn/ssp_single.py:103-138) full step
+* finetune_step       — FineTunedModel(4) fwd + weighted CE + bwd + Adam(L2 1e-4), fp32 and bf16 backbone
+                        (ref:octmnist_ft_vit2spn.py:95-104,187-192)
+* eval_forward_b1024  — no_grad eval forward at batch 1024 (ref:octmnist_ft_vit2spn.py:129-137)
+
+All device-timed with CUDA events on the current stream after warm-up, inputs resident in HBM.
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+import torch.nn as nn
+
+import vit2spn
+
+
+def timed(fn, iters, warmup=5):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def timed_queued(fn, iters, dev):
+    """Device time of a short kernel sequence whose host enqueue cost exceeds its run time: queue the calls
+    behind a long blocker kernel so the GPU never waits for the host."""
+    blocker = torch.randn(12288, 12288, device=dev)
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        torch.mm(blocker, blocker)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--iters", type=int, default=30)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    B = args.batch
+    out = {"batch": B, "device": torch.cuda.get_device_name(0)}
+    g = torch.Generator(device="cpu").manual_seed(0)
+    x = torch.randn(2, B, 3, 224, 224, generator=g).to(dev)
+
+    vit2spn.set_compute_mode("bf16")
+    torch.manual_seed(42)
+    model = vit2spn.DualStreamNetwork().to(dev).train()
+    opt = vit2spn.FusedAdam(model.parameters(), lr=1e-4)
+    opt.zero_grad()
+
+    def micro(accum):
+        return model.ssp_step(x[0], x[1], accumulation_steps=accum)
+
+    def full(accum):
+        for _ in range(accum):
+            micro(accum)
+        opt.step()
+        opt.zero_grad()
+        model.update_target_network()
+
+    ms = timed(lambda: micro(8), args.iters)
+    out["ssp_micro_step"] = {"ms": ms, "pairs_per_s": B / ms * 1e3}
+    opt.zero_grad()
+    ms = timed(lambda: full(8), max(args.iters // 4, 3), warmup=2)
+    out["ssp_accum8"] = {"ms_per_optimizer_step": ms, "pairs_per_s": 8 * B / ms * 1e3}
+    ms = timed(lambda: full(1), args.iters)
+    out["ssp_accum1"] = {"ms": ms, "pairs_per_s": B / ms * 1e3}
+
+    micro(1)
+    ms = timed_queued(opt.step, args.iters, dev)
+    nbytes = 11606528 * 28                                # p,g,m,v read + p,m,v written
+    out["adam"] = {"ms": ms, "algorithmic_bytes": nbytes, "GBps": nbytes / ms / 1e6}
+    ms = timed_queued(model.update_target_network, args.iters, dev)
+    nbytes = 11122944 * 12
+    out["ema"] = {"ms": ms, "algorithmic_bytes": nbytes, "GBps": nbytes / ms / 1e6}
+    del model, opt
+
+    torch.manual_seed(42)
+    single = vit2spn.SingleStreamNetwork().to(dev).train()
+    sopt = vit2spn.FusedAdam(single.parameters(), lr=1e-4)
+    crit = nn.CosineSimilarity(dim=1)
+
+    def single_step():
+        p, z = single(x[0], x[1])
+        loss = -torch.mean(crit(p, z))
+        loss.backward()
+        sopt.step()
+        sopt.zero_grad()
+        single.update_target_network()
+    ms = timed(single_step, args.iters)
+    out["single_stream_step"] = {"ms": ms, "pairs_per_s": B / ms * 1e3}
+    del single, sopt
+
+    labels = torch.randint(0, 4, (B,), generator=g).to(dev)
+    weights = torch.tensor([1.0, 2.0, 3.0, 0.5], device=dev)
+    for mode in ("fp32", "bf16"):
+        vit2spn.set_compute_mode(mode)
+        torch.manual_seed(42)
+        ft = vit2spn.FineTunedModel(4).to(dev).train()
+        fopt = vit2spn.FusedAdam(ft.parameters(), lr=1e-4, weight_decay=1e-4)
+        ce = nn.CrossEntropyLoss(weight=weights)
+
+        def ft_step():
+            loss = ce(ft(x[0]), labels)
+            loss.backward()
+            fopt.step()
+            fopt.zero_grad()
+        ms = timed(ft_step, args.iters)
+        out[f"finetune_step_{mode}"] = {"ms": ms, "images_per_s": B / ms * 1e3,
+                                        "tflops": B * 7.463e9 / ms / 1e9}
+        if mode == "bf16":
+            ft.eval()
+            xe = torch.randn(1024, 3, 224, 224, generator=g).to(dev)
+
+            def ev():
+                with torch.no_grad():
+                    return torch.softmax(ft(xe), dim=1)
+            ms = timed(ev, 10, warmup=3)
+            out["eval_forward_b1024"] = {"ms": ms, "images_per_s": 1024 / ms * 1e3,
+                                         "tflops": 1024 * 2.507e9 / ms / 1e9}
+        del ft, fopt
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()

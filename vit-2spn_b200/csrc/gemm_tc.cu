@@ -74,34 +74,38 @@ struct alignas(64) TcParams {
   int b_stationary;   // K <= 192: the CTA keeps its [192 x K] B tile in smem and walks m-tiles only
   int ctas_per_combo; // b_stationary: CTAs sharing one (group, n_tile)
   int stages;         // smem ring depth: [A|B] slots when streaming, A-only slots when B-stationary
-  int op_bytes;       // bytes of the operand region (staging ring starts here)
+  int op_bytes;       // bytes of the operand region
+  int stg_off;        // offset of the epilogue staging ring (after the operands; 0 = overlaid on them, see launch_kernel)
+  int bar_off;        // offset of the barrier / constant block
   int* err_flag;
   long long* dbg;     // optional per-role cycle counters of CTA 0 (V2S_GEMM_DEBUG=1)
   int dbg_flags;      // experiments (V2S_GEMM_DEBUG=<n>): 2 skip TMEM loads, 4 skip epilogue math + stores, 8 skip the u store, 16 skip TMA stores only
 };
 
 // fast erf-GELU for the bf16 path: Abramowitz-Stegun 7.1.26, |erf error| < 1.5e-7 (far below bf16
-// resolution); shares exp(-x^2/2) between gelu and gelu'.
-__device__ __forceinline__ void gelu_core(float x, float& cdf, float& pdf_e) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = ptx::rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  const float e = ptx::ex2_approx(-0.72134752044448170f * x * x);   // exp(-x^2/2)
+// resolution); one MUFU.RCP + one MUFU.EX2 per element, the rest FMA-pipe work.
+__device__ __forceinline__ float gelu_fast(float x) {
+  // 0.5 x (1 + erf(x/sqrt2)) = x/2 + |x/2| erf(|x|/sqrt2): no sign transfer, constants folded (13 FP + 2 MUFU)
+  const float t = ptx::rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.0f));
+  const float e = ptx::ex2_approx((-0.72134752044448170f * x) * x);   // exp(-x^2/2)
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = 1.0f - poly * t * e;
-  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
-  pdf_e = e;
-}
-__device__ __forceinline__ float gelu_fast(float x) {
-  float cdf, e;
-  gelu_core(x, cdf, e);
-  return x * cdf;
+  const float erf_abs = fmaf(-(poly * t), e, 1.0f);
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), erf_abs, hx);
 }
 __device__ __forceinline__ float gelu_grad_fast(float x) {
-  float cdf, e;
-  gelu_core(x, cdf, e);
+  // cdf(x) + x pdf(x), cdf = 1/2 + copysign(erf(|x|/sqrt2)/2, x); the 1/2 is folded into the polynomial
+  const float t = ptx::rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.0f));
+  const float e = ptx::ex2_approx((-0.72134752044448170f * x) * x);   // exp(-x^2/2)
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  const float half_erf = fmaf(-(poly * t), e, 0.5f);
+  const float cdf = 0.5f + copysignf(half_erf, x);
   return fmaf(x * 0.39894228040143268f, e, cdf);
 }
 
@@ -116,7 +120,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int N_STG = Cfg<EPI, OUT_BF16>::NSTG, STG_BYTES = Cfg<EPI, OUT_BF16>::STG;
   const int STAGES = p.stages;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.op_bytes + Cfg<EPI, OUT_BF16>::STAGING_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.bar_off);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + MAX_STAGES;  // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;          // [2] accumulator drained
@@ -276,7 +280,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
           ptx::umma_bf16_lohi(d_tmem, a_lo + a_step, b_lo + b_step, ptx::DESC_HI_SW128_SBO1024, idesc, 1u);
           ptx::umma_bf16_lohi(d_tmem, a_lo + 2 * a_step, b_lo + 2 * b_step, ptx::DESC_HI_SW128_SBO1024, idesc, 1u);
           ptx::umma_bf16_lohi(d_tmem, a_lo + 3 * a_step, b_lo + 3 * b_step, ptx::DESC_HI_SW128_SBO1024, idesc, 1u);
-          if (EPI == T_ACCUM && n_tile == 0 && p.rowsum[g] != nullptr) {
+          if (EPI == T_ACCUM && n_tile == 0 && p.rowsum[g] != nullptr && !(p.dbg_flags & 32)) {
             // row sums of A (= bias gradient in a wgrad) into accumulator columns [192,208): A x ones
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -295,7 +299,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
   } else if (warp == 2 || warp == 3) {
     // ================= store warp of epilogue group ge (whole warp walks the loop; one elected lane issues) ====
     const int ge = warp - 2;
-    uint8_t* stg_base = smem + p.op_bytes + ge * N_STG * STG_BYTES;
+    uint8_t* stg_base = smem + p.stg_off + ge * N_STG * STG_BYTES;
     uint64_t* abar = aux_bar + ge * 3;
     uint64_t* sfull = sfull_bar + ge * 3;
     uint64_t* sfree = sfree_bar + ge * 3;
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     const int q = warp & 3;                         // TMEM lane quarter
     const int hf = ((warp - 4) >> 2) & 1;           // column half of the chunk
     const int row = q * 32 + lane;                  // row within the 128-row tile
-    uint8_t* stg_base = smem + p.op_bytes + ge * N_STG * STG_BYTES;
+    uint8_t* stg_base = smem + p.stg_off + ge * N_STG * STG_BYTES;
     uint64_t* abar = aux_bar + ge * 3;
     uint64_t* sfull = sfull_bar + ge * 3;
     uint64_t* sfree = sfree_bar + ge * 3;
@@ -696,8 +700,22 @@ int launch_kernel(TcParams& p, cudaStream_t stream) {
     p.stages = st;
     p.op_bytes = st * STAGE_BYTES;
   }
+  p.stg_off = p.op_bytes;
+  p.bar_off = p.op_bytes + Cfg<EPI, OUT_BF16>::STAGING_BYTES;
+  if (EPI == T_ACCUM && !p.b_stationary && p.total_tiles <= g_num_sms) {
+    // one tile per CTA (the one-wave split-K wgrad): its epilogue starts after the last MMA has retired, when
+    // the operand ring is dead, so the staging buffers overlay the ring and the ring gets their 64 KB
+    int st = (SMEM_LIMIT - 1024 - SMEM_BAR_BYTES) / STAGE_BYTES;
+    if (st > MAX_STAGES) st = MAX_STAGES;
+    if (st * STAGE_BYTES >= Cfg<EPI, OUT_BF16>::STAGING_BYTES) {
+      p.stages = st;
+      p.op_bytes = st * STAGE_BYTES;
+      p.stg_off = 0;
+      p.bar_off = p.op_bytes;
+    }
+  }
   if (p.stages < 2) { set_error("gemm_tc: shared-memory budget leaves %d pipeline stages", p.stages); return 1; }
-  const int SMEM_TOTAL = p.op_bytes + Cfg<EPI, OUT_BF16>::STAGING_BYTES + SMEM_BAR_BYTES + 1024;
+  const int SMEM_TOTAL = p.bar_off + SMEM_BAR_BYTES + 1024;
   int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   if (p.b_stationary) grid = p.groups * p.tiles_n * p.ctas_per_combo;
   V2S_CUDA_OK(launch_pdl(gemm_tc_kernel<EPI, OUT_BF16>, dim3(grid), dim3(N_THREADS), (size_t)SMEM_TOTAL, stream, p));
@@ -850,7 +868,11 @@ int gemm_tc_test(int which, const void* a, const void* b, void* c, int m, int n,
   else if (which == 1) { d.a_rs = k; d.a_cs = 1; d.b_rs = n; d.b_cs = 1; d.epi = EPI_STORE; }
   else if (which == 2) { d.a_rs = 1; d.a_cs = m; d.b_rs = n; d.b_cs = 1; d.epi = EPI_ACCUM; to = 0; d.split_k = 1; }
   else if (which == 3) { d.a_rs = k; d.a_cs = 1; d.b_rs = 1; d.b_cs = k; d.epi = EPI_STORE; to = 0; }   // NT, fp32 out
-  else { set_error("gemm_tc_test: which must be 0..3"); return 1; }
+  else if (which == 4 || which == 5) {   // NT with the erf-GELU epilogue: h -> c, and (which 5) pre-activation u -> c + m*n
+    d.a_rs = k; d.a_cs = 1; d.b_rs = 1; d.b_cs = k; d.epi = EPI_BIAS_GELU;
+    d.out2[0] = c; d.out[0] = (which == 5) ? static_cast<bf16*>(c) + (size_t)m * n : nullptr;
+  }
+  else { set_error("gemm_tc_test: which must be 0..5"); return 1; }
   if (variant == 1) return launch_gemm_simt(d, 1, 1, to, stream);
   int handled = 0;
   V2S_TRY(launch_gemm_tc(d, 1, 1, to, stream, &handled));
