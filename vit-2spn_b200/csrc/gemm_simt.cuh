@@ -43,6 +43,10 @@ struct GemmDesc {
   float* rowsum_out[MAXG];  // EPI_ACCUM, tensor-core path only: rowsum_out[m] += sum_k A(m,k) (bias gradient for free)
   int64_t ldc;
   float alpha;
+  // tensor-core path, programmatic dependent launch: every input of this GEMM was produced at least two kernels
+  // back in the stream and the immediate predecessor is a wgrad (which releases its dependents only after its own
+  // wait) -> start without draining the predecessor, wait for it just before exiting (see gemm_tc.cu)
+  int late_wait;
 };
 
 inline GemmDesc make_gemm_desc() {

@@ -77,6 +77,7 @@ struct alignas(64) TcParams {
   int op_bytes;       // bytes of the operand region
   int stg_off;        // offset of the epilogue staging ring (after the operands; 0 = overlaid on them, see launch_kernel)
   int bar_off;        // offset of the barrier / constant block
+  int late_wait;      // see GemmDesc::late_wait
   int* err_flag;
   long long* dbg;     // optional per-role cycle counters of CTA 0 (V2S_GEMM_DEBUG=1)
   int dbg_flags;      // experiments (V2S_GEMM_DEBUG=<n>): 2 skip TMEM loads, 4 skip epilogue math + stores, 8 skip the u store, 16 skip TMA stores only
@@ -160,12 +161,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
       reinterpret_cast<uint32_t*>(ones_tile)[i] = (i < 32) ? 0x3F803F80u : 0u;
     ptx::fence_proxy_async();
   }
-  ptx::pdl_launch_dependents();     // the next kernel may start its own prologue while this one runs
+  // Programmatic dependent launch.  Ordinary kernels release their dependents right away (the successor's
+  // prologue overlaps this kernel) and wait for the predecessor before touching global memory.  A wgrad
+  // (T_ACCUM) releases its dependents only AFTER its own wait: a successor that starts therefore knows that
+  // everything up to the wgrad's predecessor is complete, and one flagged late_wait (the dgrad that follows a
+  // wgrad and reads the same, older, inputs) starts its CTAs as SMs free up instead of draining the wgrad; it
+  // waits just before exiting so that "this kernel complete" still implies "all earlier kernels complete".
+  if (EPI != T_ACCUM && !p.late_wait) ptx::pdl_launch_dependents();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
-  ptx::pdl_wait();                  // everything above overlapped the predecessor's tail; its outputs are visible now
+  if (!p.late_wait) ptx::pdl_wait();   // everything above overlapped the predecessor's tail; its outputs are visible now
+  if (EPI == T_ACCUM) ptx::pdl_launch_dependents();
 
   const int tiles_per_group = p.tiles_m * p.splits * p.tiles_n;
   // i-th tile of this CTA (same sequence for every warp role); false when the CTA is done
@@ -573,6 +581,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     }
   }
 
+  if (p.late_wait) { ptx::pdl_wait(); ptx::pdl_launch_dependents(); }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -817,6 +826,7 @@ int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t strea
     p.b_stationary = 1;
     p.ctas_per_combo = cpc;
   }
+  p.late_wait = (d.late_wait && epi != T_ACCUM && !getenv("V2S_NO_LATE_WAIT")) ? 1 : 0;
   p.err_flag = g_err_flag;
   p.dbg = g_dbg;
   p.dbg_flags = g_dbg_flags;
