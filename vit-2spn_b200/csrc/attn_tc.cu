@@ -41,6 +41,7 @@ constexpr int F_OFF_KP = F_OFF_V + KV_TILE_BYTES;           // 43008: K (26 KB),
 constexpr int F_OFF_BAR = F_OFF_KP + P_TILE_BYTES;          // 108544
 constexpr int F_SMEM = F_OFF_BAR + 128 + 1024;
 constexpr int F_THREADS = 160;
+constexpr int F_TM_O = 128;                                 // TMEM: S [0,208) -> P bf16x2 [0,104), O [128,192)
 static_assert(F_OFF_KP % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 
 struct alignas(64) AttnFwdParams {
@@ -113,8 +114,9 @@ __global__ void __launch_bounds__(F_THREADS, 2) attn_fwd_tc_kernel(const __grid_
     ptx::tc_fence_after();
     if (ptx::elect_one()) {
 #pragma unroll
-      for (int j = 0; j < KPAD / 16; ++j)
-        mma(tmem_base, skp + (j >> 2) * (QT * 128) + (j & 3) * 32, 16, sv + j * 2048, 8192, idesc_o, j > 0);
+      for (int j = 0; j < KPAD / 16; ++j)     // O (columns [128,192)) = P (tensor memory, 8 columns per K-step) x V
+        ptx::umma_bf16_ts(tmem_base + F_TM_O, tmem_base + j * 8, ptx::desc_lo(sv + j * 2048, 8192),
+                          ptx::DESC_HI_SW128_SBO1024, idesc_o, j > 0 ? 1u : 0u);
       ptx::umma_commit(bar_o);
     }
     __syncwarp();
@@ -140,42 +142,38 @@ __global__ void __launch_bounds__(F_THREADS, 2) attn_fwd_tc_kernel(const __grid_
     ptx::tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < NT - 192; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-    // pass 2: p = exp2((s - max) * scale * log2e), row sum, bf16 P into the swizzled operand tile
+    // pass 2: p = exp2((s - max) * scale * log2e), row sum; bf16 P goes back into tensor memory over the
+    // scores already consumed (two keys per 32-bit column, the A-operand layout of the P V UMMA)
     const float moff = mx * SCALE_LOG2E;
     float sum = 0.f;
 #pragma unroll 1
     for (int c = 0; c < 6; ++c) {
       ptx::tmem_ld_32x32(taddr + c * 32, r);
       ptx::tmem_ld_wait();
-      float e[32];
+      uint32_t pw[16];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { e[i] = ptx::ex2_approx(fmaf(__uint_as_float(r[i]), SCALE_LOG2E, -moff)); sum += e[i]; }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 v;
-        v.x = pack2(e[8 * j], e[8 * j + 1]); v.y = pack2(e[8 * j + 2], e[8 * j + 3]);
-        v.z = pack2(e[8 * j + 4], e[8 * j + 5]); v.w = pack2(e[8 * j + 6], e[8 * j + 7]);
-        store_p_chunk(ptile, row, c * 4 + j, v);
+      for (int i = 0; i < 16; ++i) {
+        const float e0 = ptx::ex2_approx(fmaf(__uint_as_float(r[2 * i]), SCALE_LOG2E, -moff));
+        const float e1 = ptx::ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), SCALE_LOG2E, -moff));
+        sum += e0 + e1;
+        pw[i] = pack2(e0, e1);
       }
+      ptx::tmem_st_32x16(taddr + c * 16, pw);
     }
     {
       ptx::tmem_ld_32x16(taddr + 192, r);
       ptx::tmem_ld_wait();
-      float e[16];
+      uint32_t pw[8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        e[i] = (192 + i < NT) ? ptx::ex2_approx(fmaf(__uint_as_float(r[i]), SCALE_LOG2E, -moff)) : 0.f;
-        sum += e[i];
+      for (int i = 0; i < 8; ++i) {
+        const float e0 = (192 + 2 * i < NT) ? ptx::ex2_approx(fmaf(__uint_as_float(r[2 * i]), SCALE_LOG2E, -moff)) : 0.f;
+        const float e1 = (193 + 2 * i < NT) ? ptx::ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), SCALE_LOG2E, -moff)) : 0.f;
+        sum += e0 + e1;
+        pw[i] = pack2(e0, e1);
       }
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        uint4 v;
-        v.x = pack2(e[8 * j], e[8 * j + 1]); v.y = pack2(e[8 * j + 2], e[8 * j + 3]);
-        v.z = pack2(e[8 * j + 4], e[8 * j + 5]); v.w = pack2(e[8 * j + 6], e[8 * j + 7]);
-        store_p_chunk(ptile, row, 24 + j, v);
-      }
+      ptx::tmem_st_32x8(taddr + 96, pw);
     }
-    ptx::fence_proxy_async();
+    ptx::tmem_st_wait();
     ptx::tc_fence_before();
     ptx::mbar_arrive(bar_p);
     if (qrow < NT && p.lse[g]) p.lse[g][((int64_t)b * NH + h) * NT + qrow] = mx * SCALE + __logf(sum);
@@ -185,7 +183,7 @@ __global__ void __launch_bounds__(F_THREADS, 2) attn_fwd_tc_kernel(const __grid_
     uint8_t* stg = smem + F_OFF_Q;              // the Q tile is dead once S is complete
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      ptx::tmem_ld_32x32(taddr + c * 32, r);
+      ptx::tmem_ld_32x32(taddr + F_TM_O + c * 32, r);
       ptx::tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
