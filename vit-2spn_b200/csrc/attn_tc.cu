@@ -1,10 +1,12 @@
-// tcgen05 attention for the 197-token ViT-Tiny blocks (3 heads x 64): one CTA per (head, image,
-// backbone).  All 197 keys fit one tile (padded to 208), so the softmax is a plain two-pass row
-// softmax over a 128 x 208 fp32 score tile held in tensor memory - no online rescaling.
+// tcgen05 attention for the 197-token ViT-Tiny blocks (3 heads x 64).  All 197 keys fit one tile (padded to
+// 208), so the softmax is a plain two-pass row softmax over a 128 x 208 fp32 score tile held in tensor
+// memory - no online rescaling.
 //
-//   forward:  S = Q K^T (UMMA 128x208x64, both K-major)  ->  P = softmax(S/8) (thread per row,
-//             TMEM -> registers -> bf16 P in swizzled smem)  ->  O = P V (UMMA 128x64x208, V MN-major)
-//             -> O / rowsum -> bf16 -> TMA store; log-sum-exp saved for the backward.
+//   forward:  S = Q K^T (UMMA 128x208x64, both K-major)  ->  P = softmax(S/8) (TMEM -> registers -> bf16
+//             pairs back into TMEM over the consumed scores)  ->  O = P V (UMMA 128x64x208, A = P from
+//             tensor memory, V MN-major)  -> O / rowsum -> bf16 -> TMA store; log-sum-exp saved for the
+//             backward.  attn_fwd_persist_kernel (default): persistent CTAs, two jobs in flight;
+//             attn_fwd_tc_kernel (V2S_ATTN_FWD=v1): one CTA per job, two CTAs per SM.
 //   backward: see attn_bwd_tc_kernel.
 #include <string.h>
 
@@ -208,6 +210,290 @@ __global__ void __launch_bounds__(F_THREADS, 2) attn_fwd_tc_kernel(const __grid_
   if (warp == 0) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ---- forward, persistent ----------------------------------------------------------------------
+// One CTA per SM walks the (query tile, head, image, backbone) jobs.  Three shared-memory stages [Q | K | V]
+// are filled by a TMA producer warp ahead of use; a store warp owns the output staging tile; two tensor-memory slots (256 columns each) hold the scores of
+// two jobs in flight, each served by its own eight softmax warps (two threads per query row: keys [0,112) and
+// [112,208)), so the softmax of one job overlaps the UMMAs and the epilogue of the other.
+//   TMEM slot: S [0,208) fp32 -> P bf16x2 in place ([0,56) and [112,160): each thread packs over scores it has
+//   already consumed itself) -> O accumulator [160,224).
+constexpr int PF_STAGES = 3;
+constexpr int PF_STAGE_BYTES = Q_TILE_BYTES + 2 * KV_TILE_BYTES;   // 69632
+constexpr int PF_OFF_STG = PF_STAGES * PF_STAGE_BYTES;             // 208896: O staging tile (16 KB)
+constexpr int PF_OFF_XCH = PF_OFF_STG + Q_TILE_BYTES;              // 225280: row max / row sum exchange (4 KB)
+constexpr int PF_OFF_BAR = PF_OFF_XCH + 4096;                      // 229376
+constexpr int PF_SMEM = PF_OFF_BAR + 256 + 1024;                   // 230656
+constexpr int PF_THREADS = 96 + 2 * 256;                          // producer, UMMA, store warps + 2 x 8 softmax warps
+constexpr int PF_KSPLIT = 112;                                     // keys [0,112) | [112,208)
+constexpr int PF_TM_PB = 112;                                      // P columns of the second key half
+constexpr int PF_TM_O = 160;
+static_assert(PF_STAGE_BYTES % 1024 == 0 && PF_SMEM <= 232448, "persistent attention smem map");
+
+struct alignas(64) AttnFwdPParams {
+  CUtensorMap tmQ[MAXG], tmKV[MAXG], tmCtx[MAXG];
+  float* lse[MAXG];
+  int B, total_jobs;
+  int* err_flag;
+  long long* dbg;   // optional cycle counters of CTA 0 (V2S_GEMM_DEBUG): [0..3] UMMA warp waits, [8..15] softmax thread phases
+};
+
+__global__ void __launch_bounds__(PF_THREADS, 1) attn_fwd_persist_kernel(const __grid_constant__ AttnFwdPParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + PF_OFF_BAR);   // [3] stage filled
+  uint64_t* bar_sfree = bar_load + 3;                                    // [3] stage consumed (P V retired)
+  uint64_t* bar_s = bar_sfree + 3;                                       // [2] scores ready
+  uint64_t* bar_p = bar_s + 2;                                           // [2] P written (256 threads)
+  uint64_t* bar_o = bar_p + 2;                                           // [2] O ready
+  uint64_t* bar_tfree = bar_o + 2;                                       // [2] O read out: slot reusable
+  uint64_t* bar_full = bar_tfree + 2;                                    // [2] output tile staged (256 threads)
+  uint64_t* bar_stgfree = bar_full + 2;                                  // [2] staging tile free for this slot's next job
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_stgfree + 2);
+  float* xch = reinterpret_cast<float*>(smem + PF_OFF_XCH);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 3; ++i) { ptx::mbar_init(&bar_load[i], 1); ptx::mbar_init(&bar_sfree[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bar_s[i], 1); ptx::mbar_init(&bar_p[i], 256); ptx::mbar_init(&bar_o[i], 1); ptx::mbar_init(&bar_tfree[i], 256);
+      ptx::mbar_init(&bar_full[i], 256); ptx::mbar_init(&bar_stgfree[i], 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::pdl_launch_dependents();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+  ptx::pdl_wait();
+
+  const int njobs = ((int)blockIdx.x < p.total_jobs) ? (p.total_jobs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  auto decode = [&](int n, int& t, int& h, int& b, int& g) {
+    const int J = blockIdx.x + n * gridDim.x;
+    t = J & 1;
+    int r = J >> 1;
+    h = r % NH; r /= NH;
+    b = r % p.B; g = r / p.B;
+  };
+
+  if (warp == 0) {
+    // ---- TMA producer ----
+    for (int n = 0; n < njobs; ++n) {
+      const int st = n % PF_STAGES;
+      if (n >= PF_STAGES) ptx::mbar_wait(&bar_sfree[st], ((n / PF_STAGES) - 1) & 1, p.err_flag, 31);
+      int t, h, b, g;
+      decode(n, t, h, b, g);
+      if (ptx::elect_one()) {
+        uint8_t* stage = smem + st * PF_STAGE_BYTES;
+        ptx::mbar_arrive_expect_tx(&bar_load[st], PF_STAGE_BYTES);
+        ptx::tma_load_3d(stage, &p.tmQ[g], &bar_load[st], h * DH, t * QT, b);
+        ptx::tma_load_3d(stage + Q_TILE_BYTES, &p.tmKV[g], &bar_load[st], D + h * DH, 0, b);
+        ptx::tma_load_3d(stage + Q_TILE_BYTES + KV_TILE_BYTES, &p.tmKV[g], &bar_load[st], 2 * D + h * DH, 0, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ---- UMMA issuer: S(n) as soon as its stage and slot are ready, then P V of job n-1 ----
+    const uint32_t idesc_s = ptx::make_idesc_bf16(QT, KPAD, 0, 0);
+    const uint32_t idesc_o = ptx::make_idesc_bf16(QT, DH, 0, 1);
+    const uint32_t sbase = ptx::smem_u32(smem);
+    long long w_load = 0, w_tfree = 0, w_p = 0; const long long t_mma0 = clock64();
+    for (int n = 0; n <= njobs; ++n) {
+      if (n < njobs) {
+        const int st = n % PF_STAGES, sl = n & 1;
+        long long w0 = p.dbg ? clock64() : 0;
+        ptx::mbar_wait(&bar_load[st], (n / PF_STAGES) & 1, p.err_flag, 32);
+        if (p.dbg) { const long long w1 = clock64(); w_load += w1 - w0; w0 = w1; }
+        if (n >= 2) ptx::mbar_wait(&bar_tfree[sl], ((n >> 1) - 1) & 1, p.err_flag, 33);
+        if (p.dbg) w_tfree += clock64() - w0;
+        ptx::tc_fence_after();
+        const uint32_t sq = sbase + st * PF_STAGE_BYTES, sk = sq + Q_TILE_BYTES;
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) mma(tmem_base + sl * 256, sq + k * 32, 16, sk + k * 32, 16, idesc_s, k > 0);
+          ptx::umma_commit(&bar_s[sl]);
+        }
+        __syncwarp();
+      }
+      if (n >= 1) {
+        const int m = n - 1, st = m % PF_STAGES, sl = m & 1;
+        const long long w0 = p.dbg ? clock64() : 0;
+        ptx::mbar_wait(&bar_p[sl], (m >> 1) & 1, p.err_flag, 34);
+        if (p.dbg) w_p += clock64() - w0;
+        ptx::tc_fence_after();
+        const uint32_t sv = sbase + st * PF_STAGE_BYTES + Q_TILE_BYTES + KV_TILE_BYTES;
+        const uint32_t tslot = tmem_base + sl * 256;
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int j = 0; j < KPAD / 16; ++j) {
+            const uint32_t a = tslot + (j < PF_KSPLIT / 16 ? 8 * j : PF_TM_PB + 8 * (j - PF_KSPLIT / 16));
+            ptx::umma_bf16_ts(tslot + PF_TM_O, a, ptx::desc_lo(sv + j * 2048, 8192), ptx::DESC_HI_SW128_SBO1024, idesc_o,
+                              j > 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&bar_o[sl]);
+          ptx::umma_commit(&bar_sfree[st]);
+        }
+        __syncwarp();
+      }
+    }
+    if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[0] = w_load; p.dbg[1] = w_tfree; p.dbg[2] = w_p; p.dbg[3] = clock64() - t_mma0; p.dbg[4] = njobs; }
+  } else if (warp == 2) {
+    // ---- store warp: staging tile -> global.  Jobs use the single staging tile in job order; its release is
+    // signalled to the slot of the NEXT job, so every slot sees its own completions in order. ----
+    if (ptx::elect_one()) ptx::mbar_arrive(&bar_stgfree[0]);       // free for job 0
+    __syncwarp();
+    for (int n = 0; n < njobs; ++n) {
+      const int sl = n & 1;
+      ptx::mbar_wait(&bar_full[sl], (n >> 1) & 1, p.err_flag, 38);
+      int t, h, b, g;
+      decode(n, t, h, b, g);
+      if (ptx::elect_one()) {
+        ptx::tma_store_3d(&p.tmCtx[g], smem + PF_OFF_STG, h * DH, t * QT, b);   // rows >= 197 are clipped by TMA
+        ptx::tma_commit_group();
+        ptx::tma_wait_group_read<0>();
+        ptx::mbar_arrive(&bar_stgfree[sl ^ 1]);
+      }
+      __syncwarp();
+    }
+    if (ptx::elect_one()) ptx::tma_wait_group<0>();
+    __syncwarp();
+  } else {
+    // ---- softmax + epilogue warps: slot sl, TMEM lane quarter q, key half hf ----
+    const int sw = warp - 3, sl = sw >> 3, hf = (sw & 7) >> 2, q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + sl * 256;
+    float* xmax = xch + sl * 512;
+    float* xsum = xmax + 256;
+    const int bar_id = 1 + sl;
+    const int key0 = hf ? PF_KSPLIT : 0;
+    const int pcol0 = hf ? PF_TM_PB : 0;
+    uint32_t r[32], r2[32];
+    long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = 0; 2 * j + sl < njobs; ++j) {
+      const int n = 2 * j + sl;
+      int t, h, b, g;
+      decode(n, t, h, b, g);
+      const int qrow = t * QT + row;
+      long long c0 = p.dbg ? clock64() : 0, c1;
+#define V2S_TICK(k) if (p.dbg) { c1 = clock64(); tk[k] += c1 - c0; c0 = c1; }
+      ptx::mbar_wait(&bar_s[sl], j & 1, p.err_flag, 35);
+      V2S_TICK(0)
+      ptx::tc_fence_after();
+      // pass 1: maximum over this thread's keys, then over the row.  Tensor-memory loads are issued one chunk
+      // ahead of the arithmetic (two register buffers) in both passes.
+      float mx = -INFINITY;
+      auto max32 = [&](const uint32_t* v, int kbase) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (kbase + i < NT) mx = fmaxf(mx, __uint_as_float(v[i]));
+      };
+      ptx::tmem_ld_32x32(taddr + key0, r);
+      ptx::tmem_ld_wait();
+      ptx::tmem_ld_32x32(taddr + key0 + 32, r2);
+      max32(r, key0);
+      ptx::tmem_ld_wait();
+      ptx::tmem_ld_32x32(taddr + key0 + 64, r);
+      max32(r2, key0 + 32);
+      ptx::tmem_ld_wait();
+      if (hf == 0) ptx::tmem_ld_32x16(taddr + 96, r2);
+      max32(r, key0 + 64);
+      if (hf == 0) {
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(r2[i]));
+      }
+      xmax[hf * 128 + row] = mx;
+      ptx::tmem_ld_32x32(taddr + key0, r);           // first chunk of pass 2, in flight across the exchange
+      V2S_TICK(1)
+      ptx::bar_sync(bar_id, 256);
+      V2S_TICK(2)
+      mx = fmaxf(mx, xmax[(hf ^ 1) * 128 + row]);
+      // pass 2: p = exp2((s - max) * scale * log2e); bf16 pairs back into tensor memory
+      const float moff = mx * SCALE_LOG2E;
+      float sum = 0.f;
+      auto exp32 = [&](const uint32_t* v, int kbase, int pcol) {
+        uint32_t pw[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int key = kbase + 2 * i;
+          const float e0 = (key < NT) ? ptx::ex2_approx(fmaf(__uint_as_float(v[2 * i]), SCALE_LOG2E, -moff)) : 0.f;
+          const float e1 = (key + 1 < NT) ? ptx::ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), SCALE_LOG2E, -moff)) : 0.f;
+          sum += e0 + e1;
+          pw[i] = pack2(e0, e1);
+        }
+        ptx::tmem_st_32x16(taddr + pcol, pw);
+      };
+      ptx::tmem_ld_wait();
+      ptx::tmem_ld_32x32(taddr + key0 + 32, r2);
+      exp32(r, key0, pcol0);
+      ptx::tmem_ld_wait();
+      ptx::tmem_ld_32x32(taddr + key0 + 64, r);
+      exp32(r2, key0 + 32, pcol0 + 16);
+      ptx::tmem_ld_wait();
+      if (hf == 0) ptx::tmem_ld_32x16(taddr + 96, r2);
+      exp32(r, key0 + 64, pcol0 + 32);
+      if (hf == 0) {
+        ptx::tmem_ld_wait();
+        uint32_t pw[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float e0 = ptx::ex2_approx(fmaf(__uint_as_float(r2[2 * i]), SCALE_LOG2E, -moff));
+          const float e1 = ptx::ex2_approx(fmaf(__uint_as_float(r2[2 * i + 1]), SCALE_LOG2E, -moff));
+          sum += e0 + e1;
+          pw[i] = pack2(e0, e1);
+        }
+        ptx::tmem_st_32x8(taddr + 48, pw);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bar_p[sl]);
+      xsum[hf * 128 + row] = sum;
+      V2S_TICK(3)
+      ptx::bar_sync(bar_id, 256);
+      V2S_TICK(4)
+      sum += xsum[(hf ^ 1) * 128 + row];
+      if (hf == 0 && qrow < NT && p.lse[g]) p.lse[g][((int64_t)b * NH + h) * NT + qrow] = mx * SCALE + __logf(sum);
+      const float inv = 1.0f / sum;
+      // epilogue: this thread's 32 output columns -> bf16 -> staging tile -> TMA store
+      ptx::mbar_wait(&bar_o[sl], j & 1, p.err_flag, 36);
+      V2S_TICK(5)
+      ptx::tc_fence_after();
+      ptx::tmem_ld_32x32(taddr + PF_TM_O + hf * 32, r);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bar_tfree[sl]);
+      uint8_t* stg = smem + PF_OFF_STG;
+      ptx::mbar_wait(&bar_stgfree[sl], j & 1, p.err_flag, 37);    // the previous job's store has read the tile
+      V2S_TICK(6)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        uint4 v;
+        v.x = pack2(__uint_as_float(r[8 * jj]) * inv, __uint_as_float(r[8 * jj + 1]) * inv);
+        v.y = pack2(__uint_as_float(r[8 * jj + 2]) * inv, __uint_as_float(r[8 * jj + 3]) * inv);
+        v.z = pack2(__uint_as_float(r[8 * jj + 4]) * inv, __uint_as_float(r[8 * jj + 5]) * inv);
+        v.w = pack2(__uint_as_float(r[8 * jj + 6]) * inv, __uint_as_float(r[8 * jj + 7]) * inv);
+        *reinterpret_cast<uint4*>(stg + row * 128 + (((hf * 4 + jj) ^ (row & 7)) << 4)) = v;
+      }
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(&bar_full[sl]);
+      V2S_TICK(7)
+    }
+#undef V2S_TICK
+    if (p.dbg && blockIdx.x == 0 && sw == 0 && lane == 0)
+      for (int k = 0; k < 8; ++k) p.dbg[8 + k] = tk[k];
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -548,12 +834,31 @@ int launch_attn_fwd_tc(const void* const* qkv, void* const* ctx, float* const* l
     V2S_TRY(tmap_get_3d(&p.tmCtx[g], ctx[g], D, NT, B, D * 2, (uint64_t)NT * D * 2, DH, QT, true, 128));
     p.lse[g] = lse ? lse[g] : nullptr;
   }
-  static bool attr = false;
-  if (!attr) {
-    V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
-    attr = true;
+  static const bool legacy = getenv("V2S_ATTN_FWD") && strcmp(getenv("V2S_ATTN_FWD"), "v1") == 0;
+  if (legacy) {      // one CTA per job, two CTAs per SM (kept for A/B measurements)
+    static bool attr = false;
+    if (!attr) {
+      V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+      attr = true;
+    }
+    V2S_CUDA_OK(launch_pdl(attn_fwd_tc_kernel, dim3(NH * 2, B, groups), dim3(F_THREADS), (size_t)F_SMEM, s, p));
+    V2S_LAUNCH_CHECK();
+    return 0;
   }
-  V2S_CUDA_OK(launch_pdl(attn_fwd_tc_kernel, dim3(NH * 2, B, groups), dim3(F_THREADS), (size_t)F_SMEM, s, p));
+  AttnFwdPParams pp;
+  memset(&pp, 0, sizeof(pp));
+  memcpy(pp.tmQ, p.tmQ, sizeof(p.tmQ)); memcpy(pp.tmKV, p.tmKV, sizeof(p.tmKV)); memcpy(pp.tmCtx, p.tmCtx, sizeof(p.tmCtx));
+  for (int g = 0; g < groups; ++g) pp.lse[g] = p.lse[g];
+  pp.B = B; pp.total_jobs = 2 * NH * B * groups; pp.err_flag = p.err_flag; pp.dbg = tc_dbg_counters();
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    V2S_CUDA_OK(cudaGetDevice(&dev));
+    V2S_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+  }
+  const int grid = pp.total_jobs < num_sms ? pp.total_jobs : num_sms;
+  V2S_CUDA_OK(launch_pdl(attn_fwd_persist_kernel, dim3(grid), dim3(PF_THREADS), (size_t)PF_SMEM, s, pp));
   V2S_LAUNCH_CHECK();
   return 0;
 }

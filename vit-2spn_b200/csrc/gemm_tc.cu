@@ -684,6 +684,7 @@ int tmap_get_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uin
   return 0;
 }
 int* tc_err_flag() { return g_err_flag; }
+long long* tc_dbg_counters() { return g_dbg; }
 bool tc_enabled() { return g_encode != nullptr && !g_disabled; }
 
 namespace {

@@ -16,6 +16,7 @@ int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t strea
 int tmap_get_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
                 uint64_t s2_bytes, uint32_t b0, uint32_t b1, bool is_bf16, int swizzle_bytes);
 int* tc_err_flag();
+long long* tc_dbg_counters();   // 32 device counters when V2S_GEMM_DEBUG is set, else NULL
 bool tc_enabled();
 int gemm_tc_debug_counters(long long* host32);
 // reads and clears the device-side protocol error flag (0 = none); synchronises
