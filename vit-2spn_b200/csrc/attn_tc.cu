@@ -522,6 +522,7 @@ struct alignas(64) AttnBwdParams {
   const bf16* ctx[MAXG];
   const float* lse[MAXG];
   int* err_flag;
+  long long* dbg;   // optional phase cycle counters of CTA 0 (V2S_GEMM_DEBUG): [16..27]
 };
 
 __device__ __forceinline__ uint4 load_p_chunk(const uint8_t* tile, int r, int c8) {
@@ -649,12 +650,44 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
     uint8_t* dstile = smem + B_OFF_DS;
     const int col0 = half ? 112 : 0;
     uint32_t r[32];
+    long long tk[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long c0 = clock64(), c1;
+    const long long t_begin = c0;
+#define V2S_TICK(k) if (p.dbg) { c1 = clock64(); tk[k] += c1 - c0; c0 = c1; }
     for (int t = 0; t < 2; ++t) {
       const int qrow = t * QT + row;
       const bool valid = qrow < NT;
       const float lse2 = valid ? p.lse[g][((int64_t)b * NH + h) * NT + qrow] * LOG2E : 0.f;
+      // the O row comes from global memory: issue its loads before waiting for the TMA tiles, so that both
+      // latencies overlap; D is then computed while the S = Q K^T UMMAs run
+      uint4 ov[8];
+      if (valid) {
+        const uint4* orow = reinterpret_cast<const uint4*>(p.ctx[g] + ((int64_t)b * NT + qrow) * D + h * DH);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) ov[c] = __ldg(orow + c);
+      }
+      ptx::mbar_wait(&bar_load[t], 0, p.err_flag, 30);
+      V2S_TICK(2)
+      // ---- D = rowsum(dO * O) (both halves compute it) ----
+      float Dr = 0.f;
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 dv = *reinterpret_cast<const uint4*>(smem + B_OFF_DO + row * 128 + ((c ^ (row & 7)) << 4));
+          const uint32_t ow[4] = {ov[c].x, ov[c].y, ov[c].z, ov[c].w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 o2 = *reinterpret_cast<const __nv_bfloat162*>(&ow[e]);
+            const __nv_bfloat162 d2 = *reinterpret_cast<const __nv_bfloat162*>(&dw[e]);
+            Dr = fmaf(__low2float(o2), __low2float(d2), Dr);
+            Dr = fmaf(__high2float(o2), __high2float(d2), Dr);
+          }
+        }
+      }
+      V2S_TICK(9)
       // ---- P = exp(S/8 - lse) ----
       ptx::mbar_wait(&bar_s[t], 0, p.err_flag, 26);
+      V2S_TICK(0)
       ptx::tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < 3; ++c) {
@@ -690,26 +723,10 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bar_p[t]);
-      // ---- D = rowsum(dO * O) (both halves compute it; dO from smem, O from global) ----
-      float Dr = 0.f;
-      if (valid) {
-        const uint4* orow = reinterpret_cast<const uint4*>(p.ctx[g] + ((int64_t)b * NT + qrow) * D + h * DH);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 ov = __ldg(orow + c);
-          const uint4 dv = *reinterpret_cast<const uint4*>(smem + B_OFF_DO + row * 128 + ((c ^ (row & 7)) << 4));
-          const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const __nv_bfloat162 o2 = *reinterpret_cast<const __nv_bfloat162*>(&ow[e]);
-            const __nv_bfloat162 d2 = *reinterpret_cast<const __nv_bfloat162*>(&dw[e]);
-            Dr = fmaf(__low2float(o2), __low2float(d2), Dr);
-            Dr = fmaf(__high2float(o2), __high2float(d2), Dr);
-          }
-        }
-      }
+      V2S_TICK(1)
       // ---- dS = P * (dP - D) / 8 ----
       ptx::mbar_wait(&bar_dp[t], 0, p.err_flag, 27);
+      V2S_TICK(3)
       ptx::tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < 3; ++c) {
@@ -754,8 +771,10 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bar_ds[t]);
+      V2S_TICK(4)
       // ---- dQ_t: TMEM [0,64) → bf16 → staged in the (dead) dO buffer → TMA store ----
       ptx::mbar_wait(&bar_dq[t], 0, p.err_flag, 28);
+      V2S_TICK(5)
       ptx::tc_fence_after();
       ptx::tmem_ld_32x32(tlane + half * 32, r);
       ptx::tmem_ld_wait();
@@ -780,9 +799,11 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
         ptx::tma_wait_group_read<0>();
       }
       if (t == 0) ptx::mbar_arrive(bar_free);
+      V2S_TICK(6)
     }
     // ---- dK, dV: TMEM → bf16 → staged in the P buffer → TMA store (rows = keys) ----
     ptx::mbar_wait(&bar_kv[1], 0, p.err_flag, 29);       // every MMA has retired
+    V2S_TICK(7)
     ptx::tc_fence_after();
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {          // 0: dK, 1: dV
@@ -811,6 +832,13 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
                             (1 + which) * D + h * DH, mt * QT, b);
       ptx::tma_commit_group();
       ptx::tma_wait_group<0>();
+    }
+    V2S_TICK(8)
+#undef V2S_TICK
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 32) {
+      for (int k = 0; k < 9; ++k) p.dbg[16 + k] = tk[k];
+      p.dbg[25] = clock64() - t_begin;
+      p.dbg[26] = tk[9];
     }
   }
   ptx::tc_fence_before();
@@ -880,6 +908,7 @@ int launch_attn_bwd_tc(const void* const* qkv, const void* const* ctx, const flo
     p.ctx[g] = static_cast<const bf16*>(ctx[g]);
     p.lse[g] = lse[g];
   }
+  p.dbg = tc_dbg_counters();
   static bool attr = false;
   if (!attr) {
     V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
