@@ -133,11 +133,29 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_STDOUT_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner at
+    communicator creation, for one) is sent to stderr instead."""
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_STDOUT_FD if _STDOUT_FD is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 def main():
     args = parse()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -328,7 +346,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "kernel_classes": classes, "debug_flag": flag, "host_enqueue_ms_per_step": host_ms,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
