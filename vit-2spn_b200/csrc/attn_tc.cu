@@ -84,12 +84,12 @@ __global__ void __launch_bounds__(F_THREADS, 2) attn_fwd_tc_kernel(const __grid_
     ptx::tmem_alloc(tmem_ptr, 256);
     ptx::tmem_relinquish();
   }
-  ptx::pdl_launch_dependents();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
   ptx::pdl_wait();                  // prologue above overlapped the predecessor's tail
+  ptx::pdl_launch_dependents();     // after the wait: see the dependent-launch note in gemm_tc.cu
 
   if (warp == 0) {
     // control warp: every lane walks the same path and waits on the barriers; one elected lane issues
@@ -267,12 +267,12 @@ __global__ void __launch_bounds__(PF_THREADS, 1) attn_fwd_persist_kernel(const _
     ptx::tmem_alloc(tmem_ptr, 512);
     ptx::tmem_relinquish();
   }
-  ptx::pdl_launch_dependents();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
   ptx::pdl_wait();
+  ptx::pdl_launch_dependents();     // after the wait: see the dependent-launch note in gemm_tc.cu
 
   const int njobs = ((int)blockIdx.x < p.total_jobs) ? (p.total_jobs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   auto decode = [&](int n, int& t, int& h, int& b, int& g) {
@@ -569,12 +569,12 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
     }
     ptx::fence_proxy_async();
   }
-  ptx::pdl_launch_dependents();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
   ptx::pdl_wait();                  // prologue above overlapped the predecessor's tail
+  ptx::pdl_launch_dependents();     // after the wait: see the dependent-launch note in gemm_tc.cu
 
   if (warp == 0) {
     // control warp: every lane walks the same path and waits on the barriers; one elected lane issues

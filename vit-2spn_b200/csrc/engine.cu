@@ -444,14 +444,14 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
     return run_gemm(d, at, at, 0, st, prof::C_WGRAD);
   };
   // dX[M, K_in] = dY[M, N_out] * W[N_out, K_in]
-  // after_wgrad: the kernel launched just before this one is a wgrad and neither it nor this GEMM's output
-  // buffer overlaps (GemmDesc::late_wait)
+  // late: the kernel launched just before this one is a wgrad whose inputs this GEMM shares, and nothing the wgrad
+  // touches is written here (GemmDesc::late_wait)
   auto dgrad = [&](void* const* dy, int n_out, int64_t woff, int k_in, void* const* out, int epi,
-                   void* const* aux, bool after_wgrad) -> int {
+                   void* const* aux, bool late = false) -> int {
     GemmDesc d = make_gemm_desc();
     d.M = (int)M; d.N = k_in; d.K = n_out; d.groups = G;
     d.a_rs = n_out; d.a_cs = 1; d.b_rs = k_in; d.b_cs = 1;
-    d.epi = epi; d.ldc = k_in; d.late_wait = after_wgrad ? 1 : 0;
+    d.epi = epi; d.ldc = k_in; d.late_wait = late ? 1 : 0;
     for (int g = 0; g < G; ++g) {
       d.A[g] = dy[g]; d.B[g] = weight_ptr(gs[g], at, woff); d.out[g] = out[g];
       d.aux[g] = aux ? aux[g] : nullptr;
@@ -473,12 +473,16 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
       u[g] = sb(g, s.u); h[g] = sb(g, s.h); xn2[g] = sb(g, s.xn2);
       ctx[g] = sb(g, s.ctx); qkv[g] = sb(g, s.qkv); xn1[g] = sb(g, s.xn1);
     }
+    // Order: the backward chain is dgrad(W2) -> dgrad(W1) -> LN2' -> dgrad(Wo) -> attention' -> dgrad(Wqkv) -> LN1';
+    // the wgrads are leaves.  Each dgrad is launched right after the wgrad that reads the same (older) gradient and
+    // runs "late" (GemmDesc::late_wait): it does not drain that wgrad.  The mirrored order (wgrads late after the
+    // chain kernels, dWo filling the attention kernel's partial last wave) measured the same or slightly slower.
     // ---- MLP ----
     V2S_TRY(wgrad(dxlp, D, h, DF, lo + L_W2, false));                      // dW2 [192,768]
     if (l == NL - 1) V2S_TRY(bias_grad(dxlp, D, lo + L_B2));               // lower blocks: fused into LN1-bwd above
-    V2S_TRY(dgrad(dxlp, D, lo + L_W2, DF, big, EPI_DGELU, u, l != NL - 1));             // du = (dx W2) * gelu'(u)
+    V2S_TRY(dgrad(dxlp, D, lo + L_W2, DF, big, EPI_DGELU, u, l != NL - 1));   // du = (dx W2) * gelu'(u)
     V2S_TRY(wgrad(big, DF, xn2, D, lo + L_W1, false, lo + L_B1));          // dW1 [768,192] and d b1
-    V2S_TRY(dgrad(big, DF, lo + L_W1, D, tmp, EPI_STORE, nullptr, true));        // d xn2
+    V2S_TRY(dgrad(big, DF, lo + L_W1, D, tmp, EPI_STORE, nullptr, true));  // d xn2
     {
       const void* dy[MAXG]; const float *x[MAXG], *mu[MAXG], *rs[MAXG], *gm[MAXG];
       float *dg[MAXG], *db[MAXG], *cs[MAXG]; void* lp[MAXG];
@@ -493,7 +497,7 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
     }
     // ---- attention ----
     V2S_TRY(wgrad(dxlp, D, ctx, D, lo + L_WO, false));                     // dWo (d b_o: fused into LN2-bwd)
-    V2S_TRY(dgrad(dxlp, D, lo + L_WO, D, tmp, EPI_STORE, nullptr, true));        // d ctx
+    V2S_TRY(dgrad(dxlp, D, lo + L_WO, D, tmp, EPI_STORE, nullptr, true));  // d ctx
     {
       const void *cq[MAXG], *cc[MAXG], *cd[MAXG]; const float* ls[MAXG];
       for (int g = 0; g < G; ++g) { cq[g] = qkv[g]; cc[g] = ctx[g]; cd[g] = tmp[g]; ls[g] = (const float*)sb(g, s.lse); }

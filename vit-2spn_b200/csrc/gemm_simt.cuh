@@ -44,8 +44,8 @@ struct GemmDesc {
   int64_t ldc;
   float alpha;
   // tensor-core path, programmatic dependent launch: every input of this GEMM was produced at least two kernels
-  // back in the stream and the immediate predecessor is a wgrad (which releases its dependents only after its own
-  // wait) -> start without draining the predecessor, wait for it just before exiting (see gemm_tc.cu)
+  // back in the stream and its output is not touched by the kernel launched just before it -> start without
+  // draining that kernel, wait for it just before exiting (see gemm_tc.cu)
   int late_wait;
 };
 

@@ -163,19 +163,21 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
       reinterpret_cast<uint32_t*>(ones_tile)[i] = (i < 32) ? 0x3F803F80u : 0u;
     ptx::fence_proxy_async();
   }
-  // Programmatic dependent launch.  Ordinary kernels release their dependents right away (the successor's
-  // prologue overlaps this kernel) and wait for the predecessor before touching global memory.  A wgrad
-  // (T_ACCUM) releases its dependents only AFTER its own wait: a successor that starts therefore knows that
-  // everything up to the wgrad's predecessor is complete, and one flagged late_wait (the dgrad that follows a
-  // wgrad and reads the same, older, inputs) starts its CTAs as SMs free up instead of draining the wgrad; it
-  // waits just before exiting so that "this kernel complete" still implies "all earlier kernels complete".
-  if (EPI != T_ACCUM && !p.late_wait) ptx::pdl_launch_dependents();
+  // Programmatic dependent launch.  Every kernel of this library waits for its predecessor and only THEN
+  // releases its successor (the successor's CTAs cannot become resident before ours exit anyway: shared memory).
+  // So when a kernel starts, everything up to its predecessor's predecessor is complete.  A kernel flagged
+  // late_wait (the dgrad launched right after the wgrad that shares its inputs: all of them at least two kernels
+  // old) uses that: it skips the wait, starts its CTAs as the predecessor's CTAs exit instead of draining it, and
+  // waits just before exiting, so that "this kernel complete" still implies "all earlier kernels complete" for
+  // whoever follows.
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
-  if (!p.late_wait) ptx::pdl_wait();   // everything above overlapped the predecessor's tail; its outputs are visible now
-  if (EPI == T_ACCUM) ptx::pdl_launch_dependents();
+  if (!p.late_wait) {
+    ptx::pdl_wait();                // everything above overlapped the predecessor's tail; its outputs are visible now
+    ptx::pdl_launch_dependents();
+  }
 
   const int tiles_per_group = p.tiles_m * p.splits * p.tiles_n;
   // i-th tile of this CTA (same sequence for every warp role); false when the CTA is done
@@ -829,7 +831,7 @@ int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t strea
     p.b_stationary = 1;
     p.ctas_per_combo = cpc;
   }
-  p.late_wait = (d.late_wait && epi != T_ACCUM && !getenv("V2S_NO_LATE_WAIT")) ? 1 : 0;
+  p.late_wait = (d.late_wait && !getenv("V2S_NO_LATE_WAIT")) ? 1 : 0;
   p.err_flag = g_err_flag;
   p.dbg = g_dbg;
   p.dbg_flags = g_dbg_flags;

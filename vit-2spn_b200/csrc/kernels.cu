@@ -114,8 +114,10 @@ template <> __device__ __forceinline__ float4 load4<bf16>(const bf16* src) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const __grid_constant__ LnFwdP p) {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // wait for the predecessor, THEN release the successor: a successor flagged "late wait" (gemm_tc.cu) relies on
+  // everything before its predecessor being complete when it starts
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int g = blockIdx.y;
   const int hw = threadIdx.x >> 4, l = threadIdx.x & 15;
   const unsigned hmask = 0xffffu << (16 * (hw & 1));
@@ -163,8 +165,10 @@ struct LnBwdP {
 template <typename T>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const __grid_constant__ LnBwdP p) {
   __shared__ float red[16][3 * D];          // 36 KB
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // wait for the predecessor, THEN release the successor: a successor flagged "late wait" (gemm_tc.cu) relies on
+  // everything before its predecessor being complete when it starts
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int g = blockIdx.y;
   const int hw = threadIdx.x >> 4, l = threadIdx.x & 15;
   const unsigned hmask = 0xffffu << (16 * (hw & 1));
