@@ -204,12 +204,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, finish=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
+        if finish is not None:
+            finish()
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -255,27 +257,46 @@ def main():
                 bufs[i][1].copy_(host[1], non_blocking=True)
                 ready[i].record(copy_stream)
 
-        state = {"i": 0}
+        # the loss of every step is read on the host (ref:220 `loss.item()`), through a pinned buffer and an event,
+        # one step behind: step k's value is fetched after step k+1 has been enqueued, so the host-side enqueue
+        # cost of a step never leaves the GPU idle; the last value is fetched before the timed region closes
+        loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_ev = [torch.cuda.Event() for _ in range(2)]
+        state = {"i": 0, "pending": None, "last": None}
         for d in done:
             d.record()
+
+        def fetch():
+            j = state["pending"]
+            if j is not None:
+                loss_ev[j].synchronize()
+                state["last"] = float(loss_host[j])
+                state["pending"] = None
 
         def e2e_step():
             i = state["i"]
             torch.cuda.current_stream().wait_event(ready[i])
             loss = step(bufs[i][0], bufs[i][1])
+            loss_host[i].copy_(loss.detach().reshape(()), non_blocking=True)   # D2H of the step's result, every step
+            loss_ev[i].record()
             done[i].record()
             upload(i)                      # refill this buffer for step i+2 while step i+1 computes
+            fetch()                        # previous step's loss
+            state["pending"] = i
             state["i"] = i ^ 1
-            return loss.item()             # D2H read of the step's result, every step (ref:220)
 
         upload(0); upload(1)
         for _ in range(3):
             e2e_step()
-        ms_e2e = timed(e2e_step, args.steps)
+        fetch()
+        ms_e2e = timed(e2e_step, args.steps, finish=fetch)
+        if state["last"] is None or state["last"] != state["last"]:
+            raise RuntimeError("e2e: loss readback failed")
         e2e = {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s",
                "h2d_bytes_per_step": int(2 * B * 3 * 224 * 224 * 4), "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e / args.steps,
-               "input": "fp32 views [2,B,3,224,224] in pinned host memory, double-buffered H2D on a copy stream"}
+               "input": "fp32 views [2,B,3,224,224] in pinned host memory, double-buffered H2D on a copy stream",
+               "result": "loss of every step copied to pinned host memory and read there, one step behind the enqueue"}
 
     # ---- per-kernel-class device timing (CUDA events on the launching stream) → roofline ---------
     pk, pk_src = peaks()
