@@ -158,6 +158,16 @@ int v2s_cast_bf16(const float* src, void* dst, int64_t numel, void* stream);
  * uint8 [batch,1,28,28] → bilinear 224x224 → 3 channels → ImageNet normalise → fp32 NCHW */
 int v2s_preprocess_u8(const uint8_t* src, float* dst, int batch, void* stream);
 
+/* GPU half of the reference's augmentation pipeline, from `transforms.Resize((224, 224))` on
+ * (ref:ssp_vit2spn_tiny.py:90-95): Pillow-exact BILINEAR resize of the 8-bit view (coefficient tables from the
+ * host: bounds [224,2] = first source index and tap count, coefs [224,ksize] in 22-bit fixed point) -> ToTensor
+ * -> GaussianBlur 3x3 with per-view taps k1d [n,3] (NULL / taps {0,1,0}: none) -> RandomErasing rectangle
+ * erase [n,4] = top, left, height, width set to 0 (NULL / height <= 0: none) -> Normalize with host_mean3 /
+ * host_std3, written to all 3 channels.  src: uint8 [n, in_size, in_size] (in_size <= 64), dst: fp32 [n,3,224,224]. */
+int v2s_augment_finish_u8(const uint8_t* src, int n, int in_size, const int32_t* bounds, const int32_t* coefs, int ksize,
+                          const float* k1d, const int32_t* erase, const float* host_mean3, const float* host_std3,
+                          float* dst, void* stream);
+
 /* test hooks: individual operators, used by tests/ to localise a parity failure */
 int v2s_test_gemm(int which, const void* a, const void* b, void* c, int m, int n, int k,
                   int variant, void* stream);

@@ -11,6 +11,8 @@
 * finetune_step       — FineTunedModel(4) fwd + weighted CE + bwd + Adam(L2 1e-4), fp32 and bf16 backbone
                         (ref:octmnist_ft_vit2spn.py:95-104,187-192)
 * eval_forward_b1024  — no_grad eval forward at batch 1024 (ref:octmnist_ft_vit2spn.py:129-137)
+* augment_*           — input pipeline split (ref:ssp_vit2spn_tiny.py:84-96): GPU finish kernel for 2x128 views, host half per
+                        image, and the reference's full CPU transform per image for comparison
 
 All device-timed with CUDA events on the current stream after warm-up, inputs resident in HBM.
 """
@@ -146,6 +148,45 @@ def main():
             out["eval_forward_b1024"] = {"ms": ms, "images_per_s": 1024 / ms * 1e3,
                                          "tflops": 1024 * 2.507e9 / ms / 1e9}
         del ft, fopt
+    # ---- input pipeline ----
+    try:
+        import time
+        import numpy as np
+        from PIL import Image
+        from torchvision import transforms
+        from vit2spn import augment
+        compose = transforms.Compose([
+            transforms.Grayscale(num_output_channels=3), transforms.RandomHorizontalFlip(p=0.5),
+            transforms.RandomVerticalFlip(p=0.3), transforms.RandomRotation(degrees=30),
+            transforms.RandomAffine(degrees=15, translate=(0.1, 0.1), scale=(0.8, 1.2), shear=10),
+            transforms.ColorJitter(brightness=0.3, contrast=0.3, saturation=0.3, hue=0.1),
+            transforms.Resize((224, 224)), transforms.ToTensor(),
+            transforms.GaussianBlur(kernel_size=3, sigma=(0.1, 2.0)),
+            transforms.RandomErasing(p=0.5, scale=(0.02, 0.2), ratio=(0.3, 3.3)),
+            transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+        split = augment.SplitAugment(compose)
+        rng = np.random.default_rng(0)
+        pil = [Image.fromarray(rng.integers(0, 256, size=(28, 28), dtype=np.uint8), mode="L") for _ in range(64)]
+        t0 = time.perf_counter()
+        recs = [split(im) for im in pil for _ in range(2)]
+        host_ms = (time.perf_counter() - t0) / len(recs) * 1e3
+        t0 = time.perf_counter()
+        for im in pil[:16]:
+            compose(im); compose(im)
+        ref_ms = (time.perf_counter() - t0) / 32 * 1e3
+        n = 2 * B
+        u8 = torch.stack([recs[i % len(recs)][0] for i in range(n)]).to(dev)
+        k1d = torch.stack([recs[i % len(recs)][1] for i in range(n)]).to(dev)
+        er = torch.stack([recs[i % len(recs)][2] for i in range(n)]).to(dev)
+        buf = torch.empty(n, 3, 224, 224, device=dev)
+        ms = timed_queued(lambda: augment.finish_views(u8, k1d, er, split.mean, split.std, dev, out=buf), args.iters, dev)
+        nbytes = n * 3 * 224 * 224 * 4
+        out["augment_finish_gpu"] = {"views": n, "ms": ms, "algorithmic_bytes": nbytes, "GBps": nbytes / ms / 1e6}
+        out["augment_host_half_per_view_ms"] = host_ms
+        out["augment_reference_cpu_per_view_ms"] = ref_ms
+        out["augment_h2d_bytes_per_step"] = {"split": int(n * (784 + 12 + 16)), "reference": int(nbytes)}
+    except Exception as e:      # torchvision / PIL missing
+        out["augment"] = f"skipped: {e}"
     print(json.dumps(out, indent=1))
 
 

@@ -62,6 +62,7 @@ _SIGS = {
     "v2s_ema_update": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i, _i64, _d, _vp]),
     "v2s_cast_bf16": (C.c_int, [_vp, _vp, _i64, _vp]),
     "v2s_preprocess_u8": (C.c_int, [_vp, _vp, _i, _vp]),
+    "v2s_augment_finish_u8": (C.c_int, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "v2s_test_gemm": (C.c_int, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "v2s_test_attention": (C.c_int, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "v2s_launch_count": (_i64, []),

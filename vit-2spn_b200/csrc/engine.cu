@@ -807,6 +807,14 @@ int v2s_preprocess_u8(const uint8_t* src, float* dst, int batch, void* stream) {
   return launch_preprocess_u8(src, dst, batch, (cudaStream_t)stream);
 }
 
+int v2s_augment_finish_u8(const uint8_t* src, int n, int in_size, const int32_t* bounds, const int32_t* coefs, int ksize,
+                          const float* k1d, const int32_t* erase, const float* host_mean3, const float* host_std3,
+                          float* dst, void* stream) {
+  if (!src || !bounds || !coefs || !host_mean3 || !host_std3 || !dst || n < 1) { set_error("augment: bad argument"); return 1; }
+  return launch_augment_finish(src, n, in_size, bounds, coefs, ksize, k1d, erase, host_mean3, host_std3, dst,
+                               (cudaStream_t)stream);
+}
+
 int64_t v2s_launch_count(void) { return g_launch_count; }
 
 int v2s_prof_enable(int on) {
