@@ -185,8 +185,49 @@ def main():
         out["augment_host_half_per_view_ms"] = host_ms
         out["augment_reference_cpu_per_view_ms"] = ref_ms
         out["augment_h2d_bytes_per_step"] = {"split": int(n * (784 + 12 + 16)), "reference": int(nbytes)}
+        # ---- the real input path end to end: synthetic OCTMNIST-shaped dataset -> DataLoader workers -> SSP step ----
+        import importlib.util
+        from torch.utils.data import DataLoader
+        d = os.path.join(ROOT, "vit-2spn_b200", "compat", "medmnist")
+        spec = importlib.util.spec_from_file_location("_v2s_medmnist", os.path.join(d, "__init__.py"),
+                                                      submodule_search_locations=[d])
+        mm = importlib.util.module_from_spec(spec); sys.modules["_v2s_medmnist"] = mm; spec.loader.exec_module(mm)
+        os.environ["V2S_SHIM_DATASET_SIZE"] = str(B * 24)
+        workers = min(16, os.cpu_count() or 4)
+        vit2spn.set_compute_mode("bf16")
+        torch.manual_seed(42)
+        model = vit2spn.DualStreamNetwork().to(dev).train()
+        opt = vit2spn.FusedAdam(model.parameters(), lr=1e-4)
+        opt.zero_grad()
+
+        def run(loader, to_dev):
+            n, t0 = 0, None
+            for i, (views, _) in enumerate(loader):
+                if i == 4:                      # workers warmed up
+                    torch.cuda.synchronize(); t0 = time.perf_counter(); n = 0
+                v1, v2 = views
+                if to_dev:
+                    v1, v2 = v1.to(dev, non_blocking=True), v2.to(dev, non_blocking=True)
+                model.ssp_step(v1, v2, accumulation_steps=1)
+                opt.step(); opt.zero_grad(); model.update_target_network()
+                n += v1.shape[0]
+            torch.cuda.synchronize()
+            return n / (time.perf_counter() - t0)
+
+        class Dual:
+            def __init__(self, t): self.t = t
+            def __call__(self, x): return self.t(x), self.t(x)
+
+        ours = augment.gpu_dual_view_loader(mm.OCTMNIST(split="train", download=True), compose, batch_size=B, device=dev,
+                                            shuffle=True, num_workers=workers, pin_memory=True, persistent_workers=True,
+                                            drop_last=True)
+        out["real_input_pipeline_gpu_split"] = {"pairs_per_s": run(ours, False), "workers": workers}
+        del ours
+        ref = DataLoader(mm.OCTMNIST(split="train", transform=Dual(compose), download=True), batch_size=B, shuffle=True,
+                         num_workers=workers, pin_memory=True, persistent_workers=True, drop_last=True)
+        out["real_input_pipeline_reference_loader"] = {"pairs_per_s": run(ref, True), "workers": workers}
     except Exception as e:      # torchvision / PIL missing
-        out["augment"] = f"skipped: {e}"
+        out["augment"] = f"skipped: {type(e).__name__}: {e}"
     print(json.dumps(out, indent=1))
 
 
