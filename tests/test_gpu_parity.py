@@ -423,3 +423,35 @@ def test_single_stream_variant_step(dev):
     o0 = m.online_network.vit.embeddings.position_embeddings.detach().clone()
     m.update_target_network()                      # default momentum 0.99, as the reference's signature
     assert torch.equal(0.99 * t0 + (1 - 0.99) * o0, m.target_network.vit.embeddings.position_embeddings.detach())
+
+
+def test_repeatability_under_overlapped_launches(dev):
+    """The step overlaps kernels (programmatic dependent launch with late waits, persistent attention CTAs with
+    several jobs in flight): a missing dependency would show up as run-to-run differences.  The forward has no
+    atomics, so the loss must be bit-identical over many repetitions; gradients accumulate split-K partial sums
+    (and LayerNorm / bias column sums) with fp32 reduce-add in arbitrary order, so they agree only to
+    summation-order noise: measured 5-6e-5 rel-L2 (dominated by the patch-embedding and first-block weight
+    gradients, whose partial sums cancel heavily), identical with the overlap switched off (V2S_NO_LATE_WAIT=1) and
+    on the SIMT path (tools/repeat_probe.py).  A missed dependency corrupts whole tiles and lands orders of
+    magnitude above the 5e-4 bound used here."""
+    from oracle import vit2spn_oracle as orc
+    state = orc.init_state(3, 0.02)
+    x1, x2 = orc.synthetic_views(48, seed=5)
+    x1, x2 = x1.to(dev), x2.to(dev)
+    model = _build(state, dev, "bf16")
+    losses, first = [], None
+    for it in range(60):
+        for p in model.parameters():
+            p.grad = None
+        loss = model.ssp_step(x1, x2, accumulation_steps=1)
+        losses.append(loss.item())
+        if it % 20 == 0:
+            g = torch.cat([p.grad.flatten() for p in model.parameters() if p.grad is not None]).clone()
+            if first is None:
+                first = g
+            else:
+                rel = ((g - first).norm() / first.norm()).item()
+                assert rel <= 5e-4, rel
+    assert len(set(losses)) == 1, sorted(set(losses))
+    from vit2spn import _lib
+    assert _lib.lib.v2s_debug_flag() == 0
