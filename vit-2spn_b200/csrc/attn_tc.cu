@@ -240,6 +240,7 @@ struct alignas(64) AttnFwdPParams {
   long long* dbg;   // optional cycle counters of CTA 0 (V2S_GEMM_DEBUG): [0..3] UMMA warp waits, [8..15] softmax thread phases
 };
 
+template <bool DBG>   // DBG: instrumented build (phase cycle counters), launched only when V2S_GEMM_DEBUG is set
 __global__ void __launch_bounds__(PF_THREADS, 1) attn_fwd_persist_kernel(const __grid_constant__ AttnFwdPParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -308,11 +309,11 @@ __global__ void __launch_bounds__(PF_THREADS, 1) attn_fwd_persist_kernel(const _
     for (int n = 0; n <= njobs; ++n) {
       if (n < njobs) {
         const int st = n % PF_STAGES, sl = n & 1;
-        long long w0 = p.dbg ? clock64() : 0;
+        long long w0 = DBG ? clock64() : 0;
         ptx::mbar_wait(&bar_load[st], (n / PF_STAGES) & 1, p.err_flag, 32);
-        if (p.dbg) { const long long w1 = clock64(); w_load += w1 - w0; w0 = w1; }
+        if (DBG) { const long long w1 = clock64(); w_load += w1 - w0; w0 = w1; }
         if (n >= 2) ptx::mbar_wait(&bar_tfree[sl], ((n >> 1) - 1) & 1, p.err_flag, 33);
-        if (p.dbg) w_tfree += clock64() - w0;
+        if (DBG) w_tfree += clock64() - w0;
         ptx::tc_fence_after();
         const uint32_t sq = sbase + st * PF_STAGE_BYTES, sk = sq + Q_TILE_BYTES;
         if (ptx::elect_one()) {
@@ -324,9 +325,9 @@ __global__ void __launch_bounds__(PF_THREADS, 1) attn_fwd_persist_kernel(const _
       }
       if (n >= 1) {
         const int m = n - 1, st = m % PF_STAGES, sl = m & 1;
-        const long long w0 = p.dbg ? clock64() : 0;
+        const long long w0 = DBG ? clock64() : 0;
         ptx::mbar_wait(&bar_p[sl], (m >> 1) & 1, p.err_flag, 34);
-        if (p.dbg) w_p += clock64() - w0;
+        if (DBG) w_p += clock64() - w0;
         ptx::tc_fence_after();
         const uint32_t sv = sbase + st * PF_STAGE_BYTES + Q_TILE_BYTES + KV_TILE_BYTES;
         const uint32_t tslot = tmem_base + sl * 256;
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) attn_fwd_persist_kernel(const _
         __syncwarp();
       }
     }
-    if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[0] = w_load; p.dbg[1] = w_tfree; p.dbg[2] = w_p; p.dbg[3] = clock64() - t_mma0; p.dbg[4] = njobs; }
+    if (DBG && blockIdx.x == 0 && lane == 0) { p.dbg[0] = w_load; p.dbg[1] = w_tfree; p.dbg[2] = w_p; p.dbg[3] = clock64() - t_mma0; p.dbg[4] = njobs; }
   } else if (warp == 2) {
     // ---- store warp: staging tile -> global.  Jobs use the single staging tile in job order; its release is
     // signalled to the slot of the NEXT job, so every slot sees its own completions in order. ----
@@ -381,8 +382,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) attn_fwd_persist_kernel(const _
       int t, h, b, g;
       decode(n, t, h, b, g);
       const int qrow = t * QT + row;
-      long long c0 = p.dbg ? clock64() : 0, c1;
-#define V2S_TICK(k) if (p.dbg) { c1 = clock64(); tk[k] += c1 - c0; c0 = c1; }
+      long long c0 = DBG ? clock64() : 0, c1;
+#define V2S_TICK(k) if (DBG) { c1 = clock64(); tk[k] += c1 - c0; c0 = c1; }
       ptx::mbar_wait(&bar_s[sl], j & 1, p.err_flag, 35);
       V2S_TICK(0)
       ptx::tc_fence_after();
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) attn_fwd_persist_kernel(const _
       V2S_TICK(7)
     }
 #undef V2S_TICK
-    if (p.dbg && blockIdx.x == 0 && sw == 0 && lane == 0)
+    if (DBG && blockIdx.x == 0 && sw == 0 && lane == 0)
       for (int k = 0; k < 8; ++k) p.dbg[8 + k] = tk[k];
   }
   ptx::tc_fence_before();
@@ -530,6 +531,7 @@ __device__ __forceinline__ uint4 load_p_chunk(const uint8_t* tile, int r, int c8
   return *reinterpret_cast<const uint4*>(tile + block * (QT * 128) + r * 128 + ((chunk ^ (r & 7)) << 4));
 }
 
+template <bool DBG>
 __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -651,9 +653,9 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
     const int col0 = half ? 112 : 0;
     uint32_t r[32];
     long long tk[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    long long c0 = clock64(), c1;
+    long long c0 = DBG ? clock64() : 0, c1;
     const long long t_begin = c0;
-#define V2S_TICK(k) if (p.dbg) { c1 = clock64(); tk[k] += c1 - c0; c0 = c1; }
+#define V2S_TICK(k) if (DBG) { c1 = clock64(); tk[k] += c1 - c0; c0 = c1; }
     for (int t = 0; t < 2; ++t) {
       const int qrow = t * QT + row;
       const bool valid = qrow < NT;
@@ -835,7 +837,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
     }
     V2S_TICK(8)
 #undef V2S_TICK
-    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 32) {
+    if (DBG && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 32) {
       for (int k = 0; k < 9; ++k) p.dbg[16 + k] = tk[k];
       p.dbg[25] = clock64() - t_begin;
       p.dbg[26] = tk[9];
@@ -883,10 +885,12 @@ int launch_attn_fwd_tc(const void* const* qkv, void* const* ctx, float* const* l
     int dev = 0;
     V2S_CUDA_OK(cudaGetDevice(&dev));
     V2S_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
   }
   const int grid = pp.total_jobs < num_sms ? pp.total_jobs : num_sms;
-  V2S_CUDA_OK(launch_pdl(attn_fwd_persist_kernel, dim3(grid), dim3(PF_THREADS), (size_t)PF_SMEM, s, pp));
+  if (pp.dbg) V2S_CUDA_OK(launch_pdl(attn_fwd_persist_kernel<true>, dim3(grid), dim3(PF_THREADS), (size_t)PF_SMEM, s, pp));
+  else V2S_CUDA_OK(launch_pdl(attn_fwd_persist_kernel<false>, dim3(grid), dim3(PF_THREADS), (size_t)PF_SMEM, s, pp));
   V2S_LAUNCH_CHECK();
   return 0;
 }
@@ -911,10 +915,12 @@ int launch_attn_bwd_tc(const void* const* qkv, const void* const* ctx, const flo
   p.dbg = tc_dbg_counters();
   static bool attr = false;
   if (!attr) {
-    V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
     attr = true;
   }
-  V2S_CUDA_OK(launch_pdl(attn_bwd_tc_kernel, dim3(NH, B, groups), dim3(B_THREADS), (size_t)B_SMEM, s, p));
+  if (p.dbg) V2S_CUDA_OK(launch_pdl(attn_bwd_tc_kernel<true>, dim3(NH, B, groups), dim3(B_THREADS), (size_t)B_SMEM, s, p));
+  else V2S_CUDA_OK(launch_pdl(attn_bwd_tc_kernel<false>, dim3(NH, B, groups), dim3(B_THREADS), (size_t)B_SMEM, s, p));
   V2S_LAUNCH_CHECK();
   return 0;
 }

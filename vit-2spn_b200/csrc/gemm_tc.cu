@@ -117,7 +117,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int EPI, bool OUT_BF16>
+// DBG: the instrumented build of the kernel (per-role cycle counters, ablation switches), launched only when
+// V2S_GEMM_DEBUG is set: even predicated-off clock reads cost issue slots in the issue-bound epilogues.
+template <int EPI, bool OUT_BF16, bool DBG>
 __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -227,9 +229,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
-        const long long w0 = p.dbg ? clock64() : 0;
+        const long long w0 = DBG ? clock64() : 0;
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
-        if (p.dbg) prod_wait += clock64() - w0;
+        if (DBG) prod_wait += clock64() - w0;
         if (ptx::elect_one()) {
           uint8_t* sa = p.b_stationary ? aring + stage * A_STAGE_BYTES : smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-    if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[0] = prod_wait; p.dbg[1] = clock64() - prod_t0; }
+    if (DBG && blockIdx.x == 0 && lane == 0) { p.dbg[0] = prod_wait; p.dbg[1] = clock64() - prod_t0; }
   } else if (warp == 1) {
     // ================= MMA issuer (whole warp walks the loop; one elected lane issues) =================
     const uint32_t idesc = ptx::make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
@@ -275,15 +277,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     for (int i = 0; tile_at(i, g, m_tile, split, n_tile); ++i) {
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-      long long w0 = p.dbg ? clock64() : 0;
+      long long w0 = DBG ? clock64() : 0;
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 2);
-      if (p.dbg) { w_tempty += clock64() - w0; ++ntiles; }
+      if (DBG) { w_tempty += clock64() - w0; ++ntiles; }
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
       for (int kb = kb0; kb < kb1; ++kb) {
-        if (p.dbg) w0 = clock64();
+        if (DBG) w0 = clock64();
         ptx::mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
-        if (p.dbg) w_full += clock64() - w0;
+        if (DBG) w_full += clock64() - w0;
         ptx::tc_fence_after();
         const uint32_t a_lo = a_lo0 + ((stage * a_slot_stride) >> 4);
         const uint32_t b_lo = b_lo0 + (((p.b_stationary ? kb : stage) * b_slot_stride) >> 4);
@@ -292,7 +294,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
           ptx::umma_bf16_lohi(d_tmem, a_lo + a_step, b_lo + b_step, ptx::DESC_HI_SW128_SBO1024, idesc, 1u);
           ptx::umma_bf16_lohi(d_tmem, a_lo + 2 * a_step, b_lo + 2 * b_step, ptx::DESC_HI_SW128_SBO1024, idesc, 1u);
           ptx::umma_bf16_lohi(d_tmem, a_lo + 3 * a_step, b_lo + 3 * b_step, ptx::DESC_HI_SW128_SBO1024, idesc, 1u);
-          if (EPI == T_ACCUM && n_tile == 0 && p.rowsum[g] != nullptr && !(p.dbg_flags & 32)) {
+          if (EPI == T_ACCUM && n_tile == 0 && p.rowsum[g] != nullptr && !(DBG && (p.dbg_flags & 32))) {
             // row sums of A (= bias gradient in a wgrad) into accumulator columns [192,208): A x ones
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[2] = w_full; p.dbg[3] = w_tempty; p.dbg[4] = clock64() - mma_t0; p.dbg[5] = ntiles; }
+    if (DBG && blockIdx.x == 0 && lane == 0) { p.dbg[2] = w_full; p.dbg[3] = w_tempty; p.dbg[4] = clock64() - mma_t0; p.dbg[5] = ntiles; }
   } else if (warp == 2 || warp == 3) {
     // ================= store warp of epilogue group ge (whole warp walks the loop; one elected lane issues) ====
     const int ge = warp - 2;
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     int g, m_tile, split, n_tile;
     for (int i = ge; tile_at(i, g, m_tile, split, n_tile); i += 2) {
       const int m0 = m_tile * BM, n0 = n_tile * BN;
-      const bool write_u = (EPI == T_GELU) && ((p.out2_mask >> g) & 1) && !(p.dbg_flags & 8);
+      const bool write_u = (EPI == T_GELU) && ((p.out2_mask >> g) & 1) && !(DBG && (p.dbg_flags & 8));
 #pragma unroll 1
       for (int c = 0; c < RPT; ++c, ++n) {
         const int b = n % N_STG;
@@ -348,7 +350,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
         full_par ^= 1u << b;
         if (ptx::elect_one()) {
           uint8_t* stg = stg_base + b * STG_BYTES;
-          if (!(p.dbg_flags & (4 | 16))) {
+          if (!(DBG && (p.dbg_flags & (4 | 16)))) {
             if (c < N_CHUNKS) {
               const int col0 = n0 + c * CHUNK;
               if (col0 < p.N) {
@@ -405,10 +407,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     };
     long long e_pub = 0;
     auto publish_slot = [&](int n) {
-      const long long t0 = p.dbg ? clock64() : 0;
+      const long long t0 = DBG ? clock64() : 0;
       ptx::fence_proxy_async();
       ptx::mbar_arrive(&sfull[n % N_STG]);
-      if (p.dbg) e_pub += clock64() - t0;
+      if (DBG) e_pub += clock64() - t0;
     };
 
     uint32_t acc_phase = 0;
@@ -418,12 +420,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     int g, m_tile, split, n_tile;
     for (int i = ge; tile_at(i, g, m_tile, split, n_tile); i += 2) {
       const int m0 = m_tile * BM, n0 = n_tile * BN;
-      long long w0 = p.dbg ? clock64() : 0;
+      long long w0 = DBG ? clock64() : 0;
       ptx::mbar_wait(&tfull_bar[ge], acc_phase, p.err_flag, 4);
-      if (p.dbg) e_tfull += clock64() - w0;
+      if (DBG) e_tfull += clock64() - w0;
       acc_phase ^= 1;
       ptx::tc_fence_after();
-      const bool write_u = (EPI == T_GELU) && ((p.out2_mask >> g) & 1) && !(p.dbg_flags & 8);
+      const bool write_u = (EPI == T_GELU) && ((p.out2_mask >> g) & 1) && !(DBG && (p.dbg_flags & 8));
       const float* bias = (EPI != T_ACCUM && EPI != T_DGELU) ? p.bias[g] : nullptr;
       const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + ge * ACC_STRIDE;
       float ln_s1 = 0.f, ln_s2 = 0.f;
@@ -434,15 +436,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
         const int b = cnt % N_STG;
         uint8_t* stg = stg_base + b * STG_BYTES;
         uint32_t r[16];
-        if (p.dbg) w0 = clock64();
-        if (!(p.dbg_flags & 2)) {
+        if (DBG) w0 = clock64();
+        if (!(DBG && (p.dbg_flags & 2))) {
           ptx::tmem_ld_32x16(tlane + c * CHUNK + hf * 16, r);
           ptx::tmem_ld_wait();
         } else {
 #pragma unroll
           for (int k = 0; k < 16; ++k) r[k] = 0;
         }
-        if (p.dbg) e_ld += clock64() - w0;
+        if (DBG) e_ld += clock64() - w0;
         if (c == N_CHUNKS - 1 && !LN) {             // accumulator fully read: hand the stage back to the MMA warp
           if (EPI == T_ACCUM && hf == 0 && n_tile == 0 && p.rowsum[g] != nullptr) {
             uint32_t rs[16];
@@ -466,10 +468,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
           }
         }
         // fp32 rows are 128 B (8 x 16-B pieces, SWIZZLE_128B), bf16 rows 64 B (4 pieces, SWIZZLE_64B)
-        if (p.dbg) w0 = clock64();
+        if (DBG) w0 = clock64();
         acquire_slot(cnt);                           // buffer b is ours (and holds the auxiliary operand, if any)
-        if (p.dbg) e_aux += clock64() - w0;
-        if (p.dbg_flags & 4) { publish_slot(cnt); continue; }
+        if (DBG) e_aux += clock64() - w0;
+        if (DBG && (p.dbg_flags & 4)) { publish_slot(cnt); continue; }
         if (HAS_AUX) {
           if (EPI == T_RESID) {
 #pragma unroll
@@ -579,7 +581,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
         }
       }
     }
-    if (p.dbg && blockIdx.x == 0 && (threadIdx.x == 128 || threadIdx.x == 384 + 37)) {
+    if (DBG && blockIdx.x == 0 && (threadIdx.x == 128 || threadIdx.x == 384 + 37)) {
       long long* d = p.dbg + 8 + (threadIdx.x == 128 ? 0 : 8);
       d[0] = e_tfull; d[1] = e_aux; d[2] = e_pub; d[3] = e_ld; d[4] = clock64() - epi_t0; d[5] = cnt;
     }
@@ -693,11 +695,11 @@ bool tc_enabled() { return g_encode != nullptr && !g_disabled; }
 
 namespace {
 
-template <int EPI, bool OUT_BF16>
-int launch_kernel(TcParams& p, cudaStream_t stream) {
+template <int EPI, bool OUT_BF16, bool DBG>
+int launch_kernel_impl(TcParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    V2S_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI, OUT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    V2S_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI, OUT_BF16, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set = true;
   }
   // split the 227 KB between the operand ring and the epilogue staging ring of this variant
@@ -732,9 +734,14 @@ int launch_kernel(TcParams& p, cudaStream_t stream) {
   const int SMEM_TOTAL = p.bar_off + SMEM_BAR_BYTES + 1024;
   int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   if (p.b_stationary) grid = p.groups * p.tiles_n * p.ctas_per_combo;
-  V2S_CUDA_OK(launch_pdl(gemm_tc_kernel<EPI, OUT_BF16>, dim3(grid), dim3(N_THREADS), (size_t)SMEM_TOTAL, stream, p));
+  V2S_CUDA_OK(launch_pdl(gemm_tc_kernel<EPI, OUT_BF16, DBG>, dim3(grid), dim3(N_THREADS), (size_t)SMEM_TOTAL, stream, p));
   V2S_LAUNCH_CHECK();
   return 0;
+}
+
+template <int EPI, bool OUT_BF16>
+int launch_kernel(TcParams& p, cudaStream_t stream) {
+  return p.dbg ? launch_kernel_impl<EPI, OUT_BF16, true>(p, stream) : launch_kernel_impl<EPI, OUT_BF16, false>(p, stream);
 }
 
 }  // namespace
