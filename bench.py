@@ -55,40 +55,57 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Started well before the timed region (nvidia-smi takes a while to come up); samples are time-stamped on
+        arrival and only those inside [mark_begin, mark_end] are used."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "25", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx = float(f[2])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+
+        def parse(rows):
+            sm, mx, reasons = [], None, set()
+            for _, ln in rows:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx = float(f[2])
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+
+        inside = [r for r in self.lines if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or r[0]) + 0.03]
+        scope = "timed region"
+        if not inside:                       # region shorter than the sampling period: nearest samples under load
+            inside, scope = self.lines[-3:], "nearest samples (timed region shorter than the sampling period)"
+        sm, mx, reasons = parse(inside)
         sm.sort()
-        # median over the samples under load (upper half: idle samples at the edges pull it down)
         med = sm[len(sm) // 2] if sm else None
-        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
 def cpu_reference_step_fn(batch):
@@ -174,6 +191,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     vit2spn.set_compute_mode(args.mode)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
 
     # ---- model, optimizer, synthetic device-resident data -------------------------------------
     torch.manual_seed(42)
@@ -222,11 +242,10 @@ def main():
     opt.zero_grad()
     for _ in range(max(args.warmup, 3)):
         step(x1, x2)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = _lib.lib.v2s_launch_count()
+    sampler.mark_begin()
     ms_total = timed(lambda: step(x1, x2), args.steps)
+    sampler.mark_end()
     launches = int(_lib.lib.v2s_launch_count() - l0)
     # host-side cost of enqueueing one step (no device wait inside): tells CPU-bound from GPU-bound
     torch.cuda.synchronize()

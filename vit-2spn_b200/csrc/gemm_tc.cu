@@ -382,6 +382,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     const int hf = ((warp - 4) >> 2) & 1;           // column half of the chunk
     const int row = q * 32 + lane;                  // row within the 128-row tile
     uint8_t* stg_base = smem + p.stg_off + ge * N_STG * STG_BYTES;
+    const uint32_t stg_s0 = ptx::smem_u32(stg_base);
+    const bool full_n = (p.N % BN) == 0;
     uint64_t* abar = aux_bar + ge * 3;
     uint64_t* sfull = sfull_bar + ge * 3;
     uint64_t* sfree = sfree_bar + ge * 3;
@@ -434,7 +436,20 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
         const int col0 = n0 + c * CHUNK;            // first column of the chunk
         const int colh = col0 + hf * 16;            // first column of this thread's half
         const int b = cnt % N_STG;
-        uint8_t* stg = stg_base + b * STG_BYTES;
+        const uint32_t stg_s = stg_s0 + b * STG_BYTES;
+        // bias first (its registers are then live across the tensor-memory load instead of being shuffled around
+        // it); the column bound is only checked when N is not a whole number of tiles
+        float4 bb[4];
+        if (bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(bias + colh);
+          if (full_n) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) bb[k] = __ldg(b4 + k);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) bb[k] = (colh + 4 * k < p.N) ? __ldg(b4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         uint32_t r[16];
         if (DBG) w0 = clock64();
         if (!(DBG && (p.dbg_flags & 2))) {
@@ -456,16 +471,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
           if (lane == 0) ptx::mbar_arrive(&tempty_bar[ge]);
         }
         float v[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]);
         if (bias != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(bias + colh);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (colh + 4 * k < p.N) bb = __ldg(b4 + k);
-            v[4 * k] += bb.x; v[4 * k + 1] += bb.y; v[4 * k + 2] += bb.z; v[4 * k + 3] += bb.w;
+            v[4 * k] = __uint_as_float(r[4 * k]) + bb[k].x; v[4 * k + 1] = __uint_as_float(r[4 * k + 1]) + bb[k].y;
+            v[4 * k + 2] = __uint_as_float(r[4 * k + 2]) + bb[k].z; v[4 * k + 3] = __uint_as_float(r[4 * k + 3]) + bb[k].w;
           }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]);
         }
         // fp32 rows are 128 B (8 x 16-B pieces, SWIZZLE_128B), bf16 rows 64 B (4 pieces, SWIZZLE_64B)
         if (DBG) w0 = clock64();
@@ -476,10 +490,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
           if (EPI == T_RESID) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              float4* slot = reinterpret_cast<float4*>(stg + row * 128 + (((hf * 4 + j) ^ (row & 7)) << 4));
-              const float4 a = *slot;
+              const uint32_t slot = stg_s + row * 128 + (((hf * 4 + j) ^ (row & 7)) << 4);
+              const float4 a = ptx::lds128f(slot);
               v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
-              *slot = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              ptx::sts128f(slot, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
             if (LN) {     // row statistics, and the finished row back into TMEM for the normalisation pass
               uint32_t xr[16];
@@ -490,8 +504,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
           } else {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-              uint4* slot = reinterpret_cast<uint4*>(stg + row * 64 + (((hf * 2 + j) ^ ((row >> 1) & 3)) << 4));
-              const uint4 a = *slot;
+              const uint32_t slot = stg_s + row * 64 + (((hf * 2 + j) ^ ((row >> 1) & 3)) << 4);
+              const uint4 a = ptx::lds128(slot);
               const uint32_t w[4] = {a.x, a.y, a.z, a.w};
               uint32_t o[4];
 #pragma unroll
@@ -500,7 +514,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
                 o[e] = pack_bf16(v[8 * j + 2 * e] * gelu_grad_fast(__low2float(u2)),
                                  v[8 * j + 2 * e + 1] * gelu_grad_fast(__high2float(u2)));
               }
-              *slot = make_uint4(o[0], o[1], o[2], o[3]);
+              ptx::sts128(slot, o[0], o[1], o[2], o[3]);
             }
           }
         } else if (OUT_BF16) {
@@ -511,7 +525,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
                 uint4 o;
                 o.x = pack_bf16(v[8 * j], v[8 * j + 1]); o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
                 o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-                *reinterpret_cast<uint4*>(stg + 8192 + row * 64 + (((hf * 2 + j) ^ ((row >> 1) & 3)) << 4)) = o;
+                ptx::sts128(stg_s + 8192 + row * 64 + (((hf * 2 + j) ^ ((row >> 1) & 3)) << 4), o.x, o.y, o.z, o.w);
               }
             }
 #pragma unroll
@@ -522,13 +536,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
             uint4 o;
             o.x = pack_bf16(v[8 * j], v[8 * j + 1]); o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
             o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-            *reinterpret_cast<uint4*>(stg + row * 64 + (((hf * 2 + j) ^ ((row >> 1) & 3)) << 4)) = o;
+            ptx::sts128(stg_s + row * 64 + (((hf * 2 + j) ^ ((row >> 1) & 3)) << 4), o.x, o.y, o.z, o.w);
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(stg + row * 128 + (((hf * 4 + j) ^ (row & 7)) << 4)) =
-                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            ptx::sts128f(stg_s + row * 128 + (((hf * 4 + j) ^ (row & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2],
+                         v[4 * j + 3]);
         }
         publish_slot(cnt);
       }
@@ -551,7 +565,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
         for (int c = 0; c < N_CHUNKS; ++c, ++cnt) {
           const int colh = c * CHUNK + hf * 16;
           const int b = cnt % N_STG;
-          uint8_t* stg = stg_base + b * STG_BYTES;
+          const uint32_t stg_s = stg_s0 + b * STG_BYTES;
           uint32_t r[16];
           ptx::tmem_ld_32x16(tlane + colh, r);
           ptx::tmem_ld_wait();
@@ -575,7 +589,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
             uint4 o;
             o.x = pack_bf16(v[8 * j], v[8 * j + 1]); o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
             o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-            *reinterpret_cast<uint4*>(stg + row * 64 + (((hf * 2 + j) ^ ((row >> 1) & 3)) << 4)) = o;
+            ptx::sts128(stg_s + row * 64 + (((hf * 2 + j) ^ ((row >> 1) & 3)) << 4), o.x, o.y, o.z, o.w);
           }
           publish_slot(cnt);
         }
