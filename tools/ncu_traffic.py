@@ -25,13 +25,13 @@ def main(rep, out):
     acc = collections.defaultdict(list)
     for r in data:
         name = r[nm]
-        if "gemm_tc_kernel<4, 0>" in name:
+        if "gemm_tc_kernel<4, 0" in name:
             backward = True
-        if "gemm_tc_kernel<4, 0>" in name: cls = "gemm_wgrad"
-        elif "gemm_tc_kernel<3, 1>" in name: cls = "gemm_dgrad"
-        elif "gemm_tc_kernel<0, 1>" in name: cls = "gemm_dgrad" if backward else "gemm_qkv"
-        elif "gemm_tc_kernel<2, 1>" in name: cls = "gemm_fc1"
-        elif "gemm_tc_kernel<1, 0>" in name: cls = "gemm_resid"          # proj and fc2 alternate
+        if "gemm_tc_kernel<4, 0" in name: cls = "gemm_wgrad"
+        elif "gemm_tc_kernel<3, 1" in name: cls = "gemm_dgrad"
+        elif "gemm_tc_kernel<0, 1" in name: cls = "gemm_dgrad" if backward else "gemm_qkv"
+        elif "gemm_tc_kernel<2, 1" in name: cls = "gemm_fc1"
+        elif "gemm_tc_kernel<1, 0" in name: cls = "gemm_resid"          # proj and fc2 alternate
         elif "attn_fwd" in name: cls = "attn_fwd"
         elif "attn_bwd" in name: cls = "attn_bwd"
         elif "ln_bwd" in name: cls = "ln_bwd"
