@@ -390,21 +390,26 @@ __global__ void __launch_bounds__(PF_THREADS, 1) attn_fwd_persist_kernel(const _
       // pass 1: maximum over this thread's keys, then over the row.  Tensor-memory loads are issued one chunk
       // ahead of the arithmetic (two register buffers) in both passes.
       float mx = -INFINITY;
-      auto max32 = [&](const uint32_t* v, int kbase) {
+      // only the last chunk of the second key half (keys 176..207) contains padding keys (>= 197): every other
+      // chunk runs the unmasked variant, so the per-element bound checks stay out of the hot loop
+      auto max32 = [&](const uint32_t* v) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (kbase + i < NT) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+      };
+      auto max32_tail = [&](const uint32_t* v) {       // keys 176 + i
+#pragma unroll
+        for (int i = 0; i < NT - 176; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
       };
       ptx::tmem_ld_32x32(taddr + key0, r);
       ptx::tmem_ld_wait();
       ptx::tmem_ld_32x32(taddr + key0 + 32, r2);
-      max32(r, key0);
+      max32(r);
       ptx::tmem_ld_wait();
       ptx::tmem_ld_32x32(taddr + key0 + 64, r);
-      max32(r2, key0 + 32);
+      max32(r2);
       ptx::tmem_ld_wait();
       if (hf == 0) ptx::tmem_ld_32x16(taddr + 96, r2);
-      max32(r, key0 + 64);
+      if (hf == 0) max32(r); else max32_tail(r);
       if (hf == 0) {
         ptx::tmem_ld_wait();
 #pragma unroll
@@ -419,13 +424,23 @@ __global__ void __launch_bounds__(PF_THREADS, 1) attn_fwd_persist_kernel(const _
       // pass 2: p = exp2((s - max) * scale * log2e); bf16 pairs back into tensor memory
       const float moff = mx * SCALE_LOG2E;
       float sum = 0.f;
-      auto exp32 = [&](const uint32_t* v, int kbase, int pcol) {
+      auto exp32 = [&](const uint32_t* v, int pcol) {
         uint32_t pw[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int key = kbase + 2 * i;
-          const float e0 = (key < NT) ? ptx::ex2_approx(fmaf(__uint_as_float(v[2 * i]), SCALE_LOG2E, -moff)) : 0.f;
-          const float e1 = (key + 1 < NT) ? ptx::ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), SCALE_LOG2E, -moff)) : 0.f;
+          const float e0 = ptx::ex2_approx(fmaf(__uint_as_float(v[2 * i]), SCALE_LOG2E, -moff));
+          const float e1 = ptx::ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), SCALE_LOG2E, -moff));
+          sum += e0 + e1;
+          pw[i] = pack2(e0, e1);
+        }
+        ptx::tmem_st_32x16(taddr + pcol, pw);
+      };
+      auto exp32_tail = [&](const uint32_t* v, int pcol) {     // keys 176 + 2i, 177 + 2i: padding keys get p = 0
+        uint32_t pw[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float e0 = (176 + 2 * i < NT) ? ptx::ex2_approx(fmaf(__uint_as_float(v[2 * i]), SCALE_LOG2E, -moff)) : 0.f;
+          const float e1 = (177 + 2 * i < NT) ? ptx::ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), SCALE_LOG2E, -moff)) : 0.f;
           sum += e0 + e1;
           pw[i] = pack2(e0, e1);
         }
@@ -433,13 +448,13 @@ __global__ void __launch_bounds__(PF_THREADS, 1) attn_fwd_persist_kernel(const _
       };
       ptx::tmem_ld_wait();
       ptx::tmem_ld_32x32(taddr + key0 + 32, r2);
-      exp32(r, key0, pcol0);
+      exp32(r, pcol0);
       ptx::tmem_ld_wait();
       ptx::tmem_ld_32x32(taddr + key0 + 64, r);
-      exp32(r2, key0 + 32, pcol0 + 16);
+      exp32(r2, pcol0 + 16);
       ptx::tmem_ld_wait();
       if (hf == 0) ptx::tmem_ld_32x16(taddr + 96, r2);
-      exp32(r, key0 + 64, pcol0 + 32);
+      if (hf == 0) exp32(r, pcol0 + 32); else exp32_tail(r, pcol0 + 32);
       if (hf == 0) {
         ptx::tmem_ld_wait();
         uint32_t pw[8];
@@ -659,7 +674,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
     for (int t = 0; t < 2; ++t) {
       const int qrow = t * QT + row;
       const bool valid = qrow < NT;
-      const float lse2 = valid ? p.lse[g][((int64_t)b * NH + h) * NT + qrow] * LOG2E : 0.f;
+      // padding query rows (>= 197): lse2 = +huge makes every p underflow to exactly 0, no per-element row mask needed
+      const float lse2 = valid ? p.lse[g][((int64_t)b * NH + h) * NT + qrow] * LOG2E : 3.0e38f;
       // the O row comes from global memory: issue its loads before waiting for the TMA tiles, so that both
       // latencies overlap; D is then computed while the S = Q K^T UMMAs run
       uint4 ov[8];
@@ -695,13 +711,18 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
       for (int c = 0; c < 3; ++c) {
         ptx::tmem_ld_32x32(tlane + col0 + c * 32, r);
         ptx::tmem_ld_wait();
+        // only keys 176..207 (second half, last chunk) contain padding keys: the bound check stays out of the other chunks
+        const bool tail = (half == 1) && (c == 2);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float e[8];
+          if (!tail) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int key = col0 + c * 32 + j * 8 + i;
-            e[i] = (valid && key < NT) ? ptx::ex2_approx(fmaf(__uint_as_float(r[8 * j + i]), SCALE_LOG2E, -lse2)) : 0.f;
+            for (int i = 0; i < 8; ++i) e[i] = ptx::ex2_approx(fmaf(__uint_as_float(r[8 * j + i]), SCALE_LOG2E, -lse2));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              e[i] = (176 + j * 8 + i < NT) ? ptx::ex2_approx(fmaf(__uint_as_float(r[8 * j + i]), SCALE_LOG2E, -lse2)) : 0.f;
           }
           uint4 v;
           v.x = pack2(e[0], e[1]); v.y = pack2(e[2], e[3]); v.z = pack2(e[4], e[5]); v.w = pack2(e[6], e[7]);
@@ -716,7 +737,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
           float e[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            e[i] = valid ? ptx::ex2_approx(fmaf(__uint_as_float(r[8 * j + i]), SCALE_LOG2E, -lse2)) : 0.f;
+            e[i] = ptx::ex2_approx(fmaf(__uint_as_float(r[8 * j + i]), SCALE_LOG2E, -lse2));
           uint4 v;
           v.x = pack2(e[0], e[1]); v.y = pack2(e[2], e[3]); v.z = pack2(e[4], e[5]); v.w = pack2(e[6], e[7]);
           store_p_chunk(ptile, row, 12 + j, v);
