@@ -541,6 +541,14 @@ struct alignas(64) AttnBwdParams {
   long long* dbg;   // optional phase cycle counters of CTA 0 (V2S_GEMM_DEBUG): [16..27]
 };
 
+// the same accesses through 32-bit shared addresses with the per-row part precomputed (rowbase = tile + r * 128,
+// rx = r & 7): the backward softmax threads run at two warps per scheduler, where instruction count is time
+__device__ __forceinline__ void store_p_chunk_s(uint32_t rowbase, int rx, int c8, uint4 v) {
+  ptx::sts128(rowbase + (c8 >> 3) * (QT * 128) + (((c8 & 7) ^ rx) << 4), v.x, v.y, v.z, v.w);
+}
+__device__ __forceinline__ uint4 load_p_chunk_s(uint32_t rowbase, int rx, int c8) {
+  return ptx::lds128(rowbase + (c8 >> 3) * (QT * 128) + (((c8 & 7) ^ rx) << 4));
+}
 __device__ __forceinline__ uint4 load_p_chunk(const uint8_t* tile, int r, int c8) {
   const int block = c8 >> 3, chunk = c8 & 7;
   return *reinterpret_cast<const uint4*>(tile + block * (QT * 128) + r * 128 + ((chunk ^ (r & 7)) << 4));
@@ -665,6 +673,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint8_t* ptile = smem + B_OFF_P;
     uint8_t* dstile = smem + B_OFF_DS;
+    const uint32_t prow_s = ptx::smem_u32(ptile) + row * 128, dsrow_s = ptx::smem_u32(dstile) + row * 128;
+    const int rx = row & 7;
     const int col0 = half ? 112 : 0;
     uint32_t r[32];
     long long tk[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -726,7 +736,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
           }
           uint4 v;
           v.x = pack2(e[0], e[1]); v.y = pack2(e[2], e[3]); v.z = pack2(e[4], e[5]); v.w = pack2(e[6], e[7]);
-          store_p_chunk(ptile, row, (col0 + c * 32) / 8 + j, v);
+          store_p_chunk_s(prow_s, rx, (col0 + c * 32) / 8 + j, v);
         }
       }
       if (half == 0) {      // keys 96..111
@@ -740,7 +750,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
             e[i] = ptx::ex2_approx(fmaf(__uint_as_float(r[8 * j + i]), SCALE_LOG2E, -lse2));
           uint4 v;
           v.x = pack2(e[0], e[1]); v.y = pack2(e[2], e[3]); v.z = pack2(e[4], e[5]); v.w = pack2(e[6], e[7]);
-          store_p_chunk(ptile, row, 12 + j, v);
+          store_p_chunk_s(prow_s, rx, 12 + j, v);
         }
       }
       ptx::fence_proxy_async();
@@ -748,6 +758,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
       ptx::mbar_arrive(&bar_p[t]);
       V2S_TICK(1)
       // ---- dS = P * (dP - D) / 8 ----
+      const float mDs = -Dr * SCALE;
       ptx::mbar_wait(&bar_dp[t], 0, p.err_flag, 27);
       V2S_TICK(3)
       ptx::tc_fence_after();
@@ -758,18 +769,18 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int c8 = (col0 + c * 32) / 8 + j;
-          const uint4 pv = load_p_chunk(ptile, row, c8);
+          const uint4 pv = load_p_chunk_s(prow_s, rx, c8);
           const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
           float d[8];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const __nv_bfloat162 p2 = *reinterpret_cast<const __nv_bfloat162*>(&pw[e]);
-            d[2 * e] = __low2float(p2) * (__uint_as_float(r[8 * j + 2 * e]) - Dr) * SCALE;
-            d[2 * e + 1] = __high2float(p2) * (__uint_as_float(r[8 * j + 2 * e + 1]) - Dr) * SCALE;
+            d[2 * e] = __low2float(p2) * fmaf(__uint_as_float(r[8 * j + 2 * e]), SCALE, mDs);
+            d[2 * e + 1] = __high2float(p2) * fmaf(__uint_as_float(r[8 * j + 2 * e + 1]), SCALE, mDs);
           }
           uint4 v;
           v.x = pack2(d[0], d[1]); v.y = pack2(d[2], d[3]); v.z = pack2(d[4], d[5]); v.w = pack2(d[6], d[7]);
-          store_p_chunk(dstile, row, c8, v);
+          store_p_chunk_s(dsrow_s, rx, c8, v);
         }
       }
       if (half == 0) {
@@ -777,18 +788,18 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const uint4 pv = load_p_chunk(ptile, row, 12 + j);
+          const uint4 pv = load_p_chunk_s(prow_s, rx, 12 + j);
           const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
           float d[8];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const __nv_bfloat162 p2 = *reinterpret_cast<const __nv_bfloat162*>(&pw[e]);
-            d[2 * e] = __low2float(p2) * (__uint_as_float(r[8 * j + 2 * e]) - Dr) * SCALE;
-            d[2 * e + 1] = __high2float(p2) * (__uint_as_float(r[8 * j + 2 * e + 1]) - Dr) * SCALE;
+            d[2 * e] = __low2float(p2) * fmaf(__uint_as_float(r[8 * j + 2 * e]), SCALE, mDs);
+            d[2 * e + 1] = __high2float(p2) * fmaf(__uint_as_float(r[8 * j + 2 * e + 1]), SCALE, mDs);
           }
           uint4 v;
           v.x = pack2(d[0], d[1]); v.y = pack2(d[2], d[3]); v.z = pack2(d[4], d[5]); v.w = pack2(d[6], d[7]);
-          store_p_chunk(dstile, row, 12 + j, v);
+          store_p_chunk_s(dsrow_s, rx, 12 + j, v);
         }
       }
       ptx::fence_proxy_async();
