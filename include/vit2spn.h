@@ -171,6 +171,12 @@ int v2s_augment_finish_u8(const uint8_t* src, int n, int in_size, const int32_t*
 /* test hooks: individual operators, used by tests/ to localise a parity failure */
 int v2s_test_gemm(int which, const void* a, const void* b, void* c, int m, int n, int k,
                   int variant, void* stream);
+/* fused MLP half of a block (mlp_tc.cu), one backbone: mode 0 forward (a = LN2 output [m,192]; writes optional u, h
+ * [m,768], out = x_mid + b2 + gelu(a W1^T + b1) W2^T fp32 [m,192], optional LayerNorm of out), mode 1 backward
+ * (a = d out [m,192], u in, h = du out [m,768], out = d a [m,192]); 16-bit tensors are bf16 (lp_f16 0) or fp16 (1) */
+int v2s_test_mlp(int mode, const void* a, const void* w1, const void* w2, const float* b1, const float* b2, void* u,
+                 void* h, const float* resid, void* out, void* ln_out, const float* ln_gamma, const float* ln_beta,
+                 float* ln_mean, float* ln_rstd, int m, int lp_f16, void* stream);
 int v2s_test_attention(int which, const void* qkv, void* ctx, float* lse, const void* dctx, void* dqkv,
                        int batch, int variant, void* stream);
 /* reads and clears the device-side pipeline-protocol error flag of the tcgen05 kernels (0 = ok) */

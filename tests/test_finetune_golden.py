@@ -85,7 +85,15 @@ def test_cuda_finetune_model_matches_reference_golden():
     opt.step()
     post = model.state_dict()
     norms = np.array([post[k].double().norm().item() for k in post])
-    np.testing.assert_allclose(norms, G["post_norms"], rtol=2e-6, atol=1e-7)
+    # Tensors whose gradient is analytically zero (key biases, the last block's output bias) carry pure rounding
+    # noise, and Adam's first step moves every element by +-lr whatever the gradient's magnitude: their post-step
+    # norm is only defined up to lr * sqrt(numel).  Every other tensor must match the reference to 2e-6.
+    gnorm = dict(zip(list(G["grad_names"]), G["grad_norms"]))
+    noise_floor = 1e-5 * float(G["grad_norms"].max())
+    for k, got, want in zip(post, norms, G["post_norms"]):
+        noisy = k in gnorm and float(gnorm[k]) <= noise_floor
+        atol = 2.0 * 1e-4 * post[k].numel() ** 0.5 if noisy else 1e-7
+        assert abs(got - want) <= 2e-6 * abs(want) + atol, (k, got, want, noisy)
     np.testing.assert_allclose(post["fc.0.weight"].flatten()[:mk.SLICE].cpu().numpy(), G["post_fc0_weight_slice"], rtol=0, atol=2e-6)
     np.testing.assert_allclose(post["fc.1.running_mean"].cpu().numpy(), G["post_bn_running_mean"], rtol=0, atol=2e-6)
     np.testing.assert_allclose(post["fc.1.running_var"].cpu().numpy(), G["post_bn_running_var"], rtol=0, atol=2e-6)

@@ -64,6 +64,7 @@ _SIGS = {
     "v2s_preprocess_u8": (C.c_int, [_vp, _vp, _i, _vp]),
     "v2s_augment_finish_u8": (C.c_int, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "v2s_test_gemm": (C.c_int, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "v2s_test_mlp": (C.c_int, [_i] + [_vp] * 14 + [_i, _i, _vp]),
     "v2s_test_attention": (C.c_int, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "v2s_launch_count": (_i64, []),
     "v2s_debug_flag": (C.c_int, []),

@@ -10,6 +10,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
+#include "mlp_tc.cuh"
 
 namespace v2s {
 
@@ -32,9 +33,10 @@ static Rec recs[MAX_REC];
 static int n_recs = 0;
 static int n_events = 0;   // events created so far (recs[i].a/b valid for i < n_events)
 static const char* names[] = {"gemm_patch", "gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_dgrad",
-                              "gemm_wgrad", "attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd", "colsum", "misc", "heads"};
+                              "gemm_wgrad", "attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd", "colsum", "misc", "heads", "gemm_mlp_fwd",
+                              "gemm_mlp_bwd"};
 enum { C_PATCH, C_QKV, C_PROJ, C_FC1, C_FC2, C_DGRAD, C_WGRAD, C_ATTN_F, C_ATTN_B, C_LN_F, C_LN_B, C_COLSUM, C_MISC,
-       C_HEADS, C_COUNT };
+       C_HEADS, C_MLP_F, C_MLP_B, C_COUNT };
 struct Scope {
   int idx = -1;
   cudaStream_t st;
@@ -272,6 +274,9 @@ static int backbone_forward_impl(const v2s_group_t* gs, int G, int B, int mode, 
   // On the tensor-core path every LayerNorm except the first is fused into the epilogue of the GEMM that
   // produces its input row (attention projection → LN2, fc2 → LN1 of the next block): V2S_NO_LNFUSE=1 disables.
   const bool ln_fuse = at == 1 && tc_enabled() && !getenv("V2S_NO_LNFUSE");
+  // fc1 -> GELU -> fc2 chained on chip (mlp_tc.cu): V2S_NO_MLPFUSE=1 falls back to the two separate GEMMs
+  const bool mlp_fuse = ln_fuse && !getenv("V2S_NO_MLPFUSE");
+  const int lp_f16 = 0;
   bool ln1_done = false;
   for (int l = 0; l < NL; ++l) {
     const int64_t lo = layer_off(l);
@@ -341,6 +346,34 @@ static int backbone_forward_impl(const v2s_group_t* gs, int G, int B, int mode, 
       if (!ln_fuse) {
         prof::Scope sc(prof::C_LN_F, (double)M * D * (4 + p.es) * G, st);
         V2S_TRY(launch_ln_fwd(xm, gam, bet, xn2, m2, r2, G, (int)M, at, st));
+      }
+      if (mlp_fuse) {
+        // fc1 -> GELU -> fc2 + residual (+ LN1 of the next block) as ONE chained kernel: h never leaves the chip for
+        // the EMA-target groups; the online groups still write u and h for the backward pass
+        MlpDesc d = make_mlp_desc();
+        d.mode = MLP_FWD; d.M = (int)M; d.groups = G; d.lp_f16 = lp_f16;
+        double bytes = 0.0;
+        for (int g = 0; g < G; ++g) {
+          d.a[g] = xn2[g];
+          d.w1[g] = weight_ptr(gs[g], at, lo + L_W1); d.w2[g] = weight_ptr(gs[g], at, lo + L_W2);
+          d.b1[g] = gs[g].params + lo + L_B1; d.b2[g] = gs[g].params + lo + L_B2;
+          d.u[g] = u[g]; d.h[g] = saved(g) ? h[g] : nullptr;
+          d.resid[g] = xmid[g]; d.out[g] = xout[g];
+          bytes += (double)M * D * (2 + 4 + 4) + 2.0 * D * DF * 2 + (saved(g) ? 2.0 * M * DF * 2 : 0.0);
+          if (l + 1 < NL) {     // LN1 of the next block, fused
+            const int64_t ln = layer_off(l + 1);
+            d.ln_out[g] = saved(g) ? (void*)sb(g, p.s_layer[l + 1].xn1) : (void*)fb(g, p.f_xn);
+            d.ln_gamma[g] = gs[g].params + ln + L_LN1W; d.ln_beta[g] = gs[g].params + ln + L_LN1B;
+            d.ln_mean[g] = saved(g) ? (float*)sb(g, p.s_layer[l + 1].mean1) : nullptr;
+            d.ln_rstd[g] = saved(g) ? (float*)sb(g, p.s_layer[l + 1].rstd1) : nullptr;
+            bytes += (double)M * D * 2;
+          }
+        }
+        prof::Scope scope(prof::C_MLP_F, 4.0 * M * D * (double)DF * G, st, bytes);
+        V2S_TRY(launch_mlp_tc(d, st));
+        ln1_done = l + 1 < NL;
+        for (int g = 0; g < G; ++g) x_cur[g] = xout[g];
+        continue;
       }
       GemmDesc d = make_gemm_desc();   // fc1 + GELU
       d.M = (int)M; d.N = DF; d.K = D; d.groups = G;
@@ -424,6 +457,7 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
   // bias_goff >= 0: also accumulate the bias gradient (column sums of dY) — inside the tensor-core wgrad
   // kernel (extra N=16 MMA against a ones tile), or with the column-sum kernel on the SIMT path
   const bool tc = at == 1 && tc_enabled();
+  const bool mlp_fuse = tc && !getenv("V2S_NO_MLPFUSE") && !getenv("V2S_NO_LNFUSE");
   auto wgrad = [&](void* const* dy, int n_out, void* const* x, int k_in, int64_t goff, bool remap,
                    int64_t bias_goff = -1) -> int {
     if (bias_goff >= 0 && !tc) {
@@ -480,9 +514,25 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
     // ---- MLP ----
     V2S_TRY(wgrad(dxlp, D, h, DF, lo + L_W2, false));                      // dW2 [192,768]
     if (l == NL - 1) V2S_TRY(bias_grad(dxlp, D, lo + L_B2));               // lower blocks: fused into LN1-bwd above
+    if (mlp_fuse) {
+      // du = (dx W2) * gelu'(u) and d xn2 = du W1 chained on chip (du is still written once: dW1 needs it)
+      MlpDesc d = make_mlp_desc();
+      d.mode = MLP_BWD; d.M = (int)M; d.groups = G; d.lp_f16 = 0; d.late_wait = (l != NL - 1 && !getenv("V2S_NO_LATE_WAIT")) ? 1 : 0;
+      for (int g = 0; g < G; ++g) {
+        d.a[g] = dxlp[g]; d.w1[g] = weight_ptr(gs[g], at, lo + L_W1); d.w2[g] = weight_ptr(gs[g], at, lo + L_W2);
+        d.u[g] = u[g]; d.h[g] = big[g]; d.out[g] = tmp[g];
+      }
+      {
+        prof::Scope scope(prof::C_MLP_B, 4.0 * M * D * (double)DF * G, st,
+                          ((double)M * D * 4 + (double)M * DF * 4 + 2.0 * D * DF * 2) * G);
+        V2S_TRY(launch_mlp_tc(d, st));
+      }
+      V2S_TRY(wgrad(big, DF, xn2, D, lo + L_W1, false, lo + L_B1));          // dW1 [768,192] and d b1
+    } else {
     V2S_TRY(dgrad(dxlp, D, lo + L_W2, DF, big, EPI_DGELU, u, l != NL - 1));   // du = (dx W2) * gelu'(u)
     V2S_TRY(wgrad(big, DF, xn2, D, lo + L_W1, false, lo + L_B1));          // dW1 [768,192] and d b1
     V2S_TRY(dgrad(big, DF, lo + L_W1, D, tmp, EPI_STORE, nullptr, true));  // d xn2
+    }
     {
       const void* dy[MAXG]; const float *x[MAXG], *mu[MAXG], *rs[MAXG], *gm[MAXG];
       float *dg[MAXG], *db[MAXG], *cs[MAXG]; void* lp[MAXG];
@@ -869,6 +919,17 @@ int v2s_test_attention(int which, const void* qkv, void* ctx, float* lse, const 
 
 int v2s_debug_flag(void) { return gemm_tc_error_flag(); }
 int v2s_debug_counters(int64_t* host32) { return gemm_tc_debug_counters(reinterpret_cast<long long*>(host32)); }
+
+int v2s_test_mlp(int mode, const void* a, const void* w1, const void* w2, const float* b1, const float* b2, void* u,
+                 void* h, const float* resid, void* out, void* ln_out, const float* ln_gamma, const float* ln_beta,
+                 float* ln_mean, float* ln_rstd, int m, int lp_f16, void* stream) {
+  MlpDesc d = make_mlp_desc();
+  d.mode = mode; d.M = m; d.groups = 1; d.lp_f16 = lp_f16;
+  d.a[0] = a; d.w1[0] = w1; d.w2[0] = w2; d.b1[0] = b1; d.b2[0] = b2; d.u[0] = u; d.h[0] = h; d.resid[0] = resid;
+  d.out[0] = out; d.ln_out[0] = ln_out; d.ln_gamma[0] = ln_gamma; d.ln_beta[0] = ln_beta; d.ln_mean[0] = ln_mean;
+  d.ln_rstd[0] = ln_rstd;
+  return launch_mlp_tc(d, (cudaStream_t)stream);
+}
 
 int v2s_test_gemm(int which, const void* a, const void* b, void* c, int m, int n, int k, int variant, void* stream) {
   return gemm_tc_test(which, a, b, c, m, n, k, variant, (cudaStream_t)stream);

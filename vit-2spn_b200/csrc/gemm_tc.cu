@@ -25,6 +25,7 @@
 
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
+#include "tc_math.cuh"
 
 namespace v2s {
 
@@ -82,35 +83,6 @@ struct alignas(64) TcParams {
   long long* dbg;     // optional per-role cycle counters of CTA 0 (V2S_GEMM_DEBUG=1)
   int dbg_flags;      // experiments (V2S_GEMM_DEBUG=<n>): 2 skip TMEM loads, 4 skip epilogue math + stores, 8 skip the u store, 16 skip TMA stores only
 };
-
-// fast erf-GELU for the bf16 path: Abramowitz-Stegun 7.1.26, |erf error| < 1.5e-7 (far below bf16
-// resolution); one MUFU.RCP + one MUFU.EX2 per element, the rest FMA-pipe work.  (A cheaper fitted logistic form,
-// 7 FP + 2 MUFU and 5.7e-5 abs error, was measured: fc1 1.06 -> 1.00 ms but no change of the step, so the more
-// accurate form stays.)
-__device__ __forceinline__ float gelu_fast(float x) {
-  // 0.5 x (1 + erf(x/sqrt2)) = x/2 + |x/2| erf(|x|/sqrt2): no sign transfer, constants folded (13 FP + 2 MUFU)
-  const float t = ptx::rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.0f));
-  const float e = ptx::ex2_approx((-0.72134752044448170f * x) * x);   // exp(-x^2/2)
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = fmaf(-(poly * t), e, 1.0f);
-  const float hx = 0.5f * x;
-  return fmaf(fabsf(hx), erf_abs, hx);
-}
-__device__ __forceinline__ float gelu_grad_fast(float x) {
-  // cdf(x) + x pdf(x), cdf = 1/2 + copysign(erf(|x|/sqrt2)/2, x); the 1/2 is folded into the polynomial
-  const float t = ptx::rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.0f));
-  const float e = ptx::ex2_approx((-0.72134752044448170f * x) * x);   // exp(-x^2/2)
-  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
-  poly = fmaf(poly, t, 0.5f * 1.421413741f);
-  poly = fmaf(poly, t, 0.5f * -0.284496736f);
-  poly = fmaf(poly, t, 0.5f * 0.254829592f);
-  const float half_erf = fmaf(-(poly * t), e, 0.5f);
-  const float cdf = 0.5f + copysignf(half_erf, x);
-  return fmaf(x * 0.39894228040143268f, e, cdf);
-}
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -703,6 +675,14 @@ int tmap_get_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uin
   *out = m;
   return 0;
 }
+int tmap_get_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t stride1_elems, uint32_t b0,
+                uint32_t b1, bool is_lp, int swizzle_bytes) {
+  if (!g_encode) { set_error("tensor maps not initialised (v2s_init)"); return 1; }
+  return get_map(out, ptr, d0, d1, stride1_elems, b0, b1, is_lp,
+                 swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                 : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+int tc_num_sms() { return g_num_sms; }
 int* tc_err_flag() { return g_err_flag; }
 long long* tc_dbg_counters() { return g_dbg; }
 bool tc_enabled() { return g_encode != nullptr && !g_disabled; }

@@ -15,6 +15,10 @@ int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t strea
 // shared with the attention kernels: cached rank-3 tensor map, error flag, availability
 int tmap_get_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
                 uint64_t s2_bytes, uint32_t b0, uint32_t b1, bool is_bf16, int swizzle_bytes);
+// cached rank-2 tensor map of a row-major [d1 rows, d0 cols] 16-bit (is_lp) or fp32 tensor, box b0 x b1
+int tmap_get_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t stride1_elems, uint32_t b0,
+                uint32_t b1, bool is_lp, int swizzle_bytes);
+int tc_num_sms();
 int* tc_err_flag();
 long long* tc_dbg_counters();   // 32 device counters when V2S_GEMM_DEBUG is set, else NULL
 bool tc_enabled();
