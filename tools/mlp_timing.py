@@ -66,7 +66,7 @@ def main():
         import ctypes as C
         names_mma = ["acc1_empty", "a1_full", "w_full(S1)", "acc2_empty", "a2_full", "w_full(S2)", "total", "tiles"]
         names_epi = ["e2_done", "u_full", "acc1_full", "a2_free", "u_free", "acc2_full", "rs_full", "st_free/a2_free(E2)",
-                     "acc2 drain total", "total"]
+                     "acc2 drain total", "total", "drain:acc2 wait+tmem ld", "drain:chunk loop", "drain:LN barrier"]
         for name, fn in (("fwd target", lambda: fwd(False)), ("fwd online", lambda: fwd(True)), ("bwd", bwd)):
             buf = (C.c_int64 * 32)()
             L.lib.v2s_debug_counters(buf)            # clear

@@ -44,10 +44,11 @@ constexpr int KB2 = CW / 64;               // 2 k-blocks per chunk in stage 2
 constexpr int KBLK = BM * 128;             // one [128 rows x 128 B] tile: 16384 B
 constexpr int A1_BYTES = KB1 * KBLK;       // 49152
 constexpr int W_SLOT = 24576;              // holds a stage-1 B k-block (16 KB) or a stage-2 B k-block (24 KB)
-constexpr int W_SLOTS = 4;
+constexpr int W_SLOTS = 3;
 constexpr int OFF_W = A1_BYTES;
-constexpr int OFF_EB = OFF_W + W_SLOTS * W_SLOT;       // 147456: EB0..3
-constexpr int OFF_BAR = OFF_EB + 4 * KBLK;             // 212992
+constexpr int N_EB = 6;
+constexpr int OFF_EB = OFF_W + W_SLOTS * W_SLOT;       // 122880: EB0..5
+constexpr int OFF_BAR = OFF_EB + N_EB * KBLK;          // 221184
 constexpr int OFF_LN = OFF_BAR + 1024;                 // [4 column quarters][128 rows] float2
 constexpr int SMEM_BYTES = OFF_LN + 4 * BM * 8 + 1024;
 constexpr int TM_ACC2 = 256;               // TMEM columns: acc1[0] 0..127, acc1[1] 128..255, acc2 256..447
@@ -88,10 +89,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
   uint64_t* u_free = u_full + 2;            // [2] forward: store warp (u store has read it); backward: 256 readers done
   uint64_t* acc2_full = u_free + 2;
   uint64_t* acc2_empty = acc2_full + 1;     // one arrival per epilogue warp
-  uint64_t* rs_full = acc2_empty + 1;       // [4] residual chunk landed in EB[b]
-  uint64_t* st_full = rs_full + 4;          // [4] 512 arrivals: EB[b] holds a finished output chunk
-  uint64_t* st_free = st_full + 4;          // [4] store warp: EB[b] may be overwritten (its store has read it)
-  uint64_t* e2_done = st_free + 4;          // store warp: every store of the tile's acc2 drain has read its buffer
+  uint64_t* rs_full = acc2_empty + 1;       // [6] residual chunk k landed in its buffer
+  uint64_t* st_full = rs_full + XCH;        // [6] 512 arrivals: output chunk k finished in its buffer
+  uint64_t* xn_free = st_full + XCH;        // store warp: the three buffers of the normalised row / dxn2 tiles may be overwritten
+  uint64_t* xn_full = xn_free + 1;          // 512 arrivals: those three tiles are written
+  uint64_t* e2_done = xn_full + 1;          // store warp: every store of the tile's acc2 drain has read its buffer
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(e2_done + 1);
   float2* ln_part = reinterpret_cast<float2*>(smem + OFF_LN);
 
@@ -111,8 +113,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
       ptx::mbar_init(&u_full[s], MODE == MLP_FWD ? 256 : 1); ptx::mbar_init(&u_free[s], MODE == MLP_FWD ? 1 : 256);
     }
     ptx::mbar_init(acc2_full, 1); ptx::mbar_init(acc2_empty, 16);
-    for (int s = 0; s < 4; ++s) { ptx::mbar_init(&rs_full[s], 1); ptx::mbar_init(&st_full[s], EPI_THREADS); ptx::mbar_init(&st_free[s], 1); }
-    ptx::mbar_init(e2_done, 1);
+    for (int s = 0; s < XCH; ++s) { ptx::mbar_init(&rs_full[s], 1); ptx::mbar_init(&st_full[s], EPI_THREADS); }
+    ptx::mbar_init(xn_free, 1); ptx::mbar_init(xn_full, EPI_THREADS); ptx::mbar_init(e2_done, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -185,7 +187,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
         advance();
       }
     };
-    int pg = -1, pj = 0;
+    // stage-2 operands lag two chunks behind stage-1 operands (the MMA warp's order): (g, j) of the last two chunks
+    int pg1 = -1, pj1 = 0, pg2 = -1, pj2 = 0;
     for (int i = 0; i < n_my; ++i) {
       int g, mt;
       tile_at(i, g, mt);
@@ -199,13 +202,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
 #pragma unroll 1
       for (int j = 0; j < NCH; ++j) {
         load_b1(g, j);
-        if (pg >= 0) load_b2(pg, pj);
-        pg = g; pj = j;
+        if (pg2 >= 0) load_b2(pg2, pj2);
+        pg2 = pg1; pj2 = pj1; pg1 = g; pj1 = j;
       }
     }
-    if (pg >= 0) load_b2(pg, pj);
+    if (pg2 >= 0) load_b2(pg2, pj2);
+    if (pg1 >= 0) load_b2(pg1, pj1);
   } else if (warp == 1) {
-    // ================= MMA issuer: S1(c), then S2(c-1) =================
+    // ================= MMA issuer: S1(c), then S2(c-2) =================
+    // (S1(c+1) only needs the accumulator drained by the chunk epilogue c-1, which happens at its very start; issuing
+    //  it ahead of S2(c-1), which needs that epilogue's END, has the next accumulator ready a whole chunk early)
     constexpr uint32_t b_mn = (MODE == MLP_BWD) ? 1u : 0u;
     const uint32_t idesc1 = make_idesc_lp(LP::kIdescFmt, BM, CW, 0, b_mn);
     const uint32_t idesc2 = make_idesc_lp(LP::kIdescFmt, BM, D, 0, b_mn);
@@ -262,16 +268,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
         advance();
       }
     };
-    int c = 0, pi = -1, pj = 0;
+    int c = 0, pi1 = -1, pj1 = 0, pi2 = -1, pj2 = 0;
     for (int i = 0; i < n_my; ++i) {
 #pragma unroll 1
       for (int j = 0; j < NCH; ++j, ++c) {
         stage1(i, j, c);
-        if (pi >= 0) stage2(pi, pj, c - 1);
-        pi = i; pj = j;
+        if (pi2 >= 0) stage2(pi2, pj2, c - 2);
+        pi2 = pi1; pj2 = pj1; pi1 = i; pj1 = j;
       }
     }
-    if (pi >= 0) stage2(pi, pj, c - 1);
+    if (pi2 >= 0) stage2(pi2, pj2, c - 2);
+    if (pi1 >= 0) stage2(pi1, pj1, c - 1);
     if (DBG && blockIdx.x == 0 && lane == 0) {
       for (int k = 0; k < 6; ++k) p.dbg[k] = tk[k];
       p.dbg[6] = clock64() - t_begin; p.dbg[7] = n_my;
@@ -279,8 +286,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
   } else if (warp == 2) {
     // ================= store warp: every TMA store, the epilogue-side TMA loads, buffer recycling ==============
     // (lane 0 issues: bulk async-groups are per thread)
-    uint32_t par_st = 0;                 // parity bits of the next st_full[b] completion
-    int c = 0, nu = 0;
+    int c = 0, nu = 0, nl = 0;
     if (MODE == MLP_BWD && n_my > 0 && lane == 0) {     // u tiles of the very first chunk
       int g, mt;
       tile_at(0, g, mt);
@@ -295,6 +301,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
       tile_at(i, g, mt);
       const int m0 = mt * BM;
       const bool has_h = p.has_h[g] != 0, has_u = p.has_u[g] != 0, has_ln = p.has_ln[g] != 0;
+      if (MODE == MLP_FWD && lane == 0) {
+        // residual chunks 0, 1 of this tile into their dedicated buffers EB4 / EB5, long before the drain needs them
+        for (int k = 0; k < 2; ++k) {
+          ptx::mbar_arrive_expect_tx(&rs_full[k], KBLK);
+          ptx::tma_load_2d(eb + (4 + k) * KBLK, &p.tmRes[g], &rs_full[k], k * 32, m0);
+        }
+      }
+      __syncwarp();
 #pragma unroll 1
       for (int j = 0; j < NCH; ++j, ++c) {
         if (MODE == MLP_BWD) {
@@ -342,57 +356,48 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
       // ---- acc2 drain ----
       ptx::mbar_wait(acc2_full, i & 1, p.err_flag, 56);      // all stage-2 UMMAs of the tile retired: EB0..3 are idle
       if (MODE == MLP_FWD) {
+        // chunk k lives in buffer EB[k < 2 ? 4 + k : k - 2]: six buffers for six chunks, no recycling inside a tile
         if (lane == 0) {
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 2; k < XCH; ++k) {
             ptx::mbar_arrive_expect_tx(&rs_full[k], KBLK);
-            ptx::tma_load_2d(eb + k * KBLK, &p.tmRes[g], &rs_full[k], k * 32, m0);
+            ptx::tma_load_2d(eb + (k - 2) * KBLK, &p.tmRes[g], &rs_full[k], k * 32, m0);
           }
         }
         __syncwarp();
 #pragma unroll 1
         for (int k = 0; k < XCH; ++k) {
-          const int b = k & 3;
-          ptx::mbar_wait(&st_full[b], (par_st >> b) & 1, p.err_flag, 57);
-          par_st ^= 1u << b;
+          ptx::mbar_wait(&st_full[k], i & 1, p.err_flag, 57);
           if (lane == 0) {
-            ptx::tma_store_2d(&p.tmOut[g], eb + b * KBLK, k * 32, m0);
+            ptx::tma_store_2d(&p.tmOut[g], eb + (k < 2 ? 4 + k : k - 2) * KBLK, k * 32, m0);
             ptx::tma_commit_group();
-            ptx::tma_wait_group_read<0>();
-            if (k + 4 < XCH) {
-              ptx::mbar_arrive_expect_tx(&rs_full[b], KBLK);
-              ptx::tma_load_2d(eb + b * KBLK, &p.tmRes[g], &rs_full[b], (k + 4) * 32, m0);
-            } else if (has_ln && k >= 2 && k <= 4) {
-              ptx::mbar_arrive(&st_free[b]);                 // b = 2, 3, 0: the tiles of the normalised row
-            }
           }
           __syncwarp();
         }
         if (has_ln) {
-#pragma unroll 1
-          for (int t = 0; t < 3; ++t) {
-            const int b = (XCH + t) & 3;
-            ptx::mbar_wait(&st_full[b], (par_st >> b) & 1, p.err_flag, 58);
-            par_st ^= 1u << b;
-            if (lane == 0) {
-              ptx::tma_store_2d(&p.tmXn[g], eb + b * KBLK, t * 64, m0);
-              ptx::tma_commit_group();
-            }
-            __syncwarp();
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int t = 0; t < 3; ++t) {
-          const int b = t & 1;
-          ptx::mbar_wait(&st_full[b], (par_st >> b) & 1, p.err_flag, 59);
-          par_st ^= 1u << b;
           if (lane == 0) {
-            ptx::tma_store_2d(&p.tmOut[g], eb + b * KBLK, t * 64, m0);
+            ptx::tma_wait_group_read<3>();        // the stores of chunks 0..2 have read EB4, EB5, EB0
+            ptx::mbar_arrive(xn_free);
+          }
+          __syncwarp();
+          ptx::mbar_wait(xn_full, nl & 1, p.err_flag, 58);
+          ++nl;
+          if (lane == 0) {
+            ptx::tma_store_2d(&p.tmXn[g], eb + 4 * KBLK, 0, m0);
+            ptx::tma_store_2d(&p.tmXn[g], eb + 5 * KBLK, 64, m0);
+            ptx::tma_store_2d(&p.tmXn[g], eb, 128, m0);
             ptx::tma_commit_group();
-            if (t == 0) { ptx::tma_wait_group_read<0>(); ptx::mbar_arrive(&st_free[0]); }
           }
           __syncwarp();
         }
+      } else {
+        ptx::mbar_wait(xn_full, i & 1, p.err_flag, 59);
+        if (lane == 0) {
+          ptx::tma_store_2d(&p.tmOut[g], eb + 4 * KBLK, 0, m0);
+          ptx::tma_store_2d(&p.tmOut[g], eb + 5 * KBLK, 64, m0);
+          ptx::tma_store_2d(&p.tmOut[g], eb, 128, m0);
+          ptx::tma_commit_group();
+        }
+        __syncwarp();
       }
       if (lane == 0) {
         ptx::tma_wait_group_read<0>();
@@ -411,14 +416,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
     const int rx = row & 7;
     const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t eb_row = ptx::smem_u32(eb) + row * 128;      // this thread's row in EB0
-    uint32_t par_rs = 0, par_sf = 0;
-    int c = 0, nu = 0;
+    int c = 0, nu = 0, nl = 0;
     for (int i = 0; i < n_my; ++i) {
       int g, mt;
       tile_at(i, g, mt);
       const int64_t grow = (int64_t)mt * BM + row;
       const bool has_u = p.has_u[g] != 0, has_ln = p.has_ln[g] != 0;
-      if (i > 0) V2S_WAIT(0, e2_done, (i - 1) & 1, 60);     // the previous tile's drain has left EB0..3
 #pragma unroll 1
       for (int j = 0; j < NCH; ++j, ++c) {
         const int b = c & 1;
@@ -469,6 +472,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
           }
         }
         // A operand of stage 2: k-block tile kbq of the chunk, 16-byte pieces (cq & 1) * 4 + t of this row
+        if (j == 0 && i > 0) V2S_WAIT(0, e2_done, (i - 1) & 1, 60);   // the previous tile's drain has left the buffers
         V2S_WAIT(3, &a2_free[kbq], (c & 1) ^ 1, 51);
 #pragma unroll
         for (int t = 0; t < 4; ++t)
@@ -496,16 +500,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       if (lane == 0) ptx::mbar_arrive(acc2_empty);
+      long long t_ph = DBG ? clock64() : 0;
+      if (DBG) tk[9] += t_ph - t_e2;
       if (MODE == MLP_FWD) {
         float v[48];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int k = 0; k < XCH; ++k) {
-          const int bq = k & 3;
+          const int bq = k < 2 ? 4 + k : k - 2;
           const float4 ba = __ldg(reinterpret_cast<const float4*>(p.b2[g] + k * 32 + cq * 8));
           const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2[g] + k * 32 + cq * 8 + 4));
-          V2S_WAIT(6, &rs_full[bq], (par_rs >> bq) & 1, 63);
-          par_rs ^= 1u << bq;
+          V2S_WAIT(6, &rs_full[k], i & 1, 63);
           const uint32_t s0 = eb_row + bq * KBLK + (((2 * cq) ^ rx) << 4), s1a = eb_row + bq * KBLK + (((2 * cq + 1) ^ rx) << 4);
           const float4 xa = ptx::lds128f(s0), xb = ptx::lds128f(s1a);
           float* x = v + 8 * k;
@@ -515,15 +520,20 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
           x[6] = __uint_as_float(r[8 * k + 6]) + bb.z + xb.z; x[7] = __uint_as_float(r[8 * k + 7]) + bb.w + xb.w;
           ptx::sts128f(s0, x[0], x[1], x[2], x[3]);
           ptx::sts128f(s1a, x[4], x[5], x[6], x[7]);
-          ptx::fence_proxy_async();
-          ptx::mbar_arrive(&st_full[bq]);
+          if (k & 1) {       // one proxy fence per pair of chunks
+            ptx::fence_proxy_async();
+            ptx::mbar_arrive(&st_full[k - 1]);
+            ptx::mbar_arrive(&st_full[k]);
+          }
 #pragma unroll
           for (int e = 0; e < 8; ++e) { s1 += x[e]; s2 = fmaf(x[e], x[e], s2); }
         }
+        if (DBG) { const long long t1 = clock64(); tk[10] += t1 - t_ph; t_ph = t1; }
         if (has_ln) {
           // LayerNorm over the 192-wide row: four threads per row exchange partial sums through shared memory
           ln_part[cq * BM + row] = make_float2(s1, s2);
           ptx::bar_sync(1, EPI_THREADS);
+          if (DBG) { const long long t1 = clock64(); tk[11] += t1 - t_ph; t_ph = t1; }
           s1 = 0.f; s2 = 0.f;
 #pragma unroll
           for (int k = 0; k < 4; ++k) { const float2 o2 = ln_part[k * BM + row]; s1 += o2.x; s2 += o2.y; }
@@ -531,9 +541,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
           const float var = fmaxf(s2 * (1.0f / D) - mean * mean, 0.f);
           const float rstd = 1.0f / sqrtf(var + LN_EPS);
           if (cq == 0 && grow < p.M && p.ln_mean[g] != nullptr) { p.ln_mean[g][grow] = mean; p.ln_rstd[g][grow] = rstd; }
+          V2S_WAIT(7, xn_free, nl & 1, 64);
+          ++nl;
 #pragma unroll
           for (int t = 0; t < 3; ++t) {
-            const int bq = (XCH + t) & 3;
+            const int bq = t < 2 ? 4 + t : 0;
             uint32_t w[8];
 #pragma unroll
             for (int hk = 0; hk < 2; ++hk) {
@@ -548,25 +560,18 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
               w[4 * hk + 2] = LP::pack((x[4] - mean) * rstd * gb.x + eb4.x, (x[5] - mean) * rstd * gb.y + eb4.y);
               w[4 * hk + 3] = LP::pack((x[6] - mean) * rstd * gb.z + eb4.z, (x[7] - mean) * rstd * gb.w + eb4.w);
             }
-            V2S_WAIT(7, &st_free[bq], (par_sf >> bq) & 1, 64);
-            par_sf ^= 1u << bq;
             // tile t holds columns [64 t, +64): chunk 2t -> 16-byte piece cq, chunk 2t+1 -> piece 4 + cq
             ptx::sts128(eb_row + bq * KBLK + ((cq ^ rx) << 4), w[0], w[1], w[2], w[3]);
             ptx::sts128(eb_row + bq * KBLK + (((4 + cq) ^ rx) << 4), w[4], w[5], w[6], w[7]);
-            ptx::fence_proxy_async();
-            ptx::mbar_arrive(&st_full[bq]);
           }
+          ptx::fence_proxy_async();
+          ptx::mbar_arrive(xn_full);
         }
       } else {
+        V2S_WAIT(7, &a2_free[0], (c & 1) ^ 1, 65);       // EB0: the last chunk's du store and UMMAs have read it
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-          const int bq = t & 1;
-          if (t < 2) {
-            V2S_WAIT(7, &a2_free[bq], (c & 1) ^ 1, 65);       // last chunk's du store and UMMAs have read it
-          } else {
-            V2S_WAIT(7, &st_free[0], (par_sf >> 0) & 1, 66);
-            par_sf ^= 1u;
-          }
+          const int bq = t < 2 ? 4 + t : 0;
           const uint32_t* x = r + 16 * t;
           ptx::sts128(eb_row + bq * KBLK + ((cq ^ rx) << 4), LP::pack(__uint_as_float(x[0]), __uint_as_float(x[1])),
                       LP::pack(__uint_as_float(x[2]), __uint_as_float(x[3])), LP::pack(__uint_as_float(x[4]), __uint_as_float(x[5])),
@@ -574,15 +579,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
           ptx::sts128(eb_row + bq * KBLK + (((4 + cq) ^ rx) << 4), LP::pack(__uint_as_float(x[8]), __uint_as_float(x[9])),
                       LP::pack(__uint_as_float(x[10]), __uint_as_float(x[11])), LP::pack(__uint_as_float(x[12]), __uint_as_float(x[13])),
                       LP::pack(__uint_as_float(x[14]), __uint_as_float(x[15])));
-          ptx::fence_proxy_async();
-          ptx::mbar_arrive(&st_full[bq]);
         }
+        ptx::fence_proxy_async();
+        ptx::mbar_arrive(xn_full);
       }
       if (DBG) tk[8] += clock64() - t_e2;
     }
     if (DBG && blockIdx.x == 0 && threadIdx.x == 128) {
       for (int k = 0; k < 9; ++k) p.dbg[8 + k] = tk[k];
       p.dbg[17] = clock64() - t_begin;
+      p.dbg[18] = tk[9]; p.dbg[19] = tk[10]; p.dbg[20] = tk[11];
     }
   }
 #undef V2S_WAIT
