@@ -19,6 +19,8 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# random-init ViT-Tiny weights by specification (north_star: no ImageNet checkpoint offline)
+os.environ.setdefault("V2S_ALLOW_RANDOM_INIT", "1")
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 

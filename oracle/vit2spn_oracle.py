@@ -179,6 +179,52 @@ def synthetic_views(batch: int, seed: int = 0):
 
 
 # ---------------------------------------------------------------------------------------------
+# Optional rounding model of the 16-bit compute modes
+# ---------------------------------------------------------------------------------------------
+# The fp32 restatement above is the oracle proper.  `rounding(...)` turns it into a MODEL of a 16-bit tensor-core
+# implementation: the named intermediate tensors are rounded to bf16 / fp16 (round-to-nearest-even, straight-through
+# gradient) exactly where libvit2spn stores them in 16 bits, everything else stays fp32:
+#   "w"        GEMM weight operands (the bf16 shadow of the fp32 master weights)
+#   "patches"  the im2col patch matrix
+#   "xn"       LayerNorm outputs (the A operands of the QKV and fc1 GEMMs)
+#   "qkv"      the fused QKV projection output
+#   "p"        the un-normalised softmax numerators exp(s - max) fed to P V (the row sum stays fp32)
+#   "ctx"      the attention output
+#   "h"        gelu(u) (u itself stays fp32 in the forward pass)
+# Used (a) to attribute the bf16 loss error to stages (tools/bf16_attribution.py) and (b) as the parity oracle of the
+# bf16 / fp16 modes: the CUDA path must match the fully rounded model to the north_star loss tolerance, which
+# separates "the format's rounding noise" from "a kernel bug".
+ALL_ROUNDING_STAGES = ("w", "patches", "xn", "qkv", "p", "ctx", "h")
+_ROUND = {"stages": frozenset(), "dtype": torch.bfloat16}
+
+
+class rounding:
+    """Context manager: ``with rounding(("w", "xn"), torch.bfloat16): ...``; ``rounding("all")`` enables every stage."""
+
+    def __init__(self, stages="all", dtype=torch.bfloat16):
+        self.new = {"stages": frozenset(ALL_ROUNDING_STAGES if stages == "all" else stages), "dtype": dtype}
+        unknown = self.new["stages"] - set(ALL_ROUNDING_STAGES)
+        if unknown:
+            raise ValueError(f"unknown rounding stages {sorted(unknown)}")
+
+    def __enter__(self):
+        self.old = dict(_ROUND)
+        _ROUND.update(self.new)
+        return self
+
+    def __exit__(self, *exc):
+        _ROUND.update(self.old)
+        return False
+
+
+def _rnd(x, stage):
+    """Round `x` to the 16-bit format if `stage` is enabled (identity gradient)."""
+    if stage not in _ROUND["stages"]:
+        return x
+    return x + (x.to(_ROUND["dtype"]).to(x.dtype) - x).detach()
+
+
+# ---------------------------------------------------------------------------------------------
 # Backbone forward  (HF:modeling_vit.py)
 # ---------------------------------------------------------------------------------------------
 def patch_embed(p, x):
@@ -186,8 +232,8 @@ def patch_embed(p, x):
     (K index = c*256 + ky*16 + kx), then CLS prepend + position add (HF:117-124)."""
     B = x.shape[0]
     cols = x.reshape(B, 3, GRID, PATCH, GRID, PATCH).permute(0, 2, 4, 1, 3, 5).reshape(B, GRID * GRID, 3 * PATCH * PATCH)
-    w = p["embeddings.patch_embeddings.projection.weight"].reshape(HIDDEN, -1)
-    tok = cols @ w.t() + p["embeddings.patch_embeddings.projection.bias"]
+    w = _rnd(p["embeddings.patch_embeddings.projection.weight"].reshape(HIDDEN, -1), "w")
+    tok = _rnd(cols, "patches") @ w.t() + p["embeddings.patch_embeddings.projection.bias"]
     cls = p["embeddings.cls_token"].expand(B, -1, -1)
     return torch.cat([cls, tok], dim=1) + p["embeddings.position_embeddings"]
 
@@ -210,6 +256,10 @@ def attention(q, k, v):
     k = k.view(B, N, HEADS, HEAD_DIM).transpose(1, 2)
     v = v.view(B, N, HEADS, HEAD_DIM).transpose(1, 2)
     s = (q @ k.transpose(-1, -2)) * (HEAD_DIM ** -0.5)
+    if "p" in _ROUND["stages"]:
+        # the tensor-core kernels feed the rounded numerators to P V and divide by the fp32 row sum afterwards
+        e = torch.exp(s - s.max(dim=-1, keepdim=True).values)
+        return ((_rnd(e, "p") @ v) / e.sum(dim=-1, keepdim=True)).transpose(1, 2).reshape(B, N, HIDDEN)
     a = torch.softmax(s, dim=-1)
     return (a @ v).transpose(1, 2).reshape(B, N, HIDDEN)
 
@@ -217,16 +267,16 @@ def attention(q, k, v):
 def vit_layer(p, l, h):
     """HF ViTLayer.forward :328-346 (pre-LN block)."""
     pre = f"encoder.layer.{l}."
-    x = layer_norm(h, p[pre + "layernorm_before.weight"], p[pre + "layernorm_before.bias"])
+    x = _rnd(layer_norm(h, p[pre + "layernorm_before.weight"], p[pre + "layernorm_before.bias"]), "xn")
     a = pre + "attention.attention."
-    q = x @ p[a + "query.weight"].t() + p[a + "query.bias"]
-    k = x @ p[a + "key.weight"].t() + p[a + "key.bias"]
-    v = x @ p[a + "value.weight"].t() + p[a + "value.bias"]
-    ctx = attention(q, k, v)
-    h = h + ctx @ p[pre + "attention.output.dense.weight"].t() + p[pre + "attention.output.dense.bias"]
-    x = layer_norm(h, p[pre + "layernorm_after.weight"], p[pre + "layernorm_after.bias"])
-    u = x @ p[pre + "intermediate.dense.weight"].t() + p[pre + "intermediate.dense.bias"]
-    h = h + gelu_erf(u) @ p[pre + "output.dense.weight"].t() + p[pre + "output.dense.bias"]
+    q = _rnd(x @ _rnd(p[a + "query.weight"], "w").t() + p[a + "query.bias"], "qkv")
+    k = _rnd(x @ _rnd(p[a + "key.weight"], "w").t() + p[a + "key.bias"], "qkv")
+    v = _rnd(x @ _rnd(p[a + "value.weight"], "w").t() + p[a + "value.bias"], "qkv")
+    ctx = _rnd(attention(q, k, v), "ctx")
+    h = h + ctx @ _rnd(p[pre + "attention.output.dense.weight"], "w").t() + p[pre + "attention.output.dense.bias"]
+    x = _rnd(layer_norm(h, p[pre + "layernorm_after.weight"], p[pre + "layernorm_after.bias"]), "xn")
+    u = x @ _rnd(p[pre + "intermediate.dense.weight"], "w").t() + p[pre + "intermediate.dense.bias"]
+    h = h + _rnd(gelu_erf(u), "h") @ _rnd(p[pre + "output.dense.weight"], "w").t() + p[pre + "output.dense.bias"]
     return h
 
 
@@ -345,3 +395,28 @@ def ssp_step(state, opt, x1, x2, lr=1e-4, momentum=MOMENTUM, mask_online=None, m
     state, opt = adam_step(state, grads, opt, lr=lr)
     state = ema_update(state, momentum)
     return loss, grads, state, opt
+
+
+def train_loop(state, batches, epochs, accumulation_steps=8, lr=1e-4, momentum=MOMENTUM):
+    """``train_self_supervised`` (ref:ssp_vit2spn_tiny.py:197-232) without the AMP scaler (disabled on CPU, ref:175) and
+    the checkpoint I/O: per epoch ``zero_grad``; per micro-batch ``loss = -mean(cos)/accumulation_steps`` accumulated
+    into the gradients (ref:211-213); on every ``accumulation_steps``-th micro-batch AND on the last one of the epoch
+    (ref:215) Adam step, ``zero_grad``, EMA update; ``epoch_loss += loss.item() * accumulation_steps`` (ref:220) and the
+    logged value is ``epoch_loss / len(dataloader)`` (ref:226).  ``batches`` = list of (view1, view2).
+    Returns (loss_history, final_state, optimizer_state)."""
+    opt, history = {}, []
+    names = trainable_names()
+    for _ in range(epochs):
+        acc = {k: torch.zeros_like(state[k]) for k in names}
+        epoch_loss = 0.0
+        for i, (v1, v2) in enumerate(batches):
+            loss, _, _, grads = loss_and_grads(state, v1, v2, accumulation_steps)
+            for k in names:
+                acc[k] += grads[k]
+            if (i + 1) % accumulation_steps == 0 or (i + 1) == len(batches):
+                state, opt = adam_step(state, acc, opt, lr=lr)
+                acc = {k: torch.zeros_like(state[k]) for k in names}
+                state = ema_update(state, momentum)
+            epoch_loss += float(loss) * accumulation_steps
+        history.append(epoch_loss / len(batches))
+    return history, state, opt

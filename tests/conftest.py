@@ -4,6 +4,8 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# no ImageNet checkpoint offline: parity runs load explicit oracle weights over the random init (north_star)
+os.environ.setdefault("V2S_ALLOW_RANDOM_INIT", "1")
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 

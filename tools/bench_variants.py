@@ -19,6 +19,8 @@ All device-timed with CUDA events on the current stream after warm-up, inputs re
 import argparse
 import json
 import os
+
+os.environ.setdefault("V2S_ALLOW_RANDOM_INIT", "1")   # random-init weights by specification (no checkpoint offline)
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

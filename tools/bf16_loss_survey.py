@@ -8,6 +8,8 @@ B=128, the loss error and the gradient rel-L2 error against the fp32 oracle (run
 PyTorch path does in bf16.   python tools/bf16_loss_survey.py > profiles/bf16_loss_survey_rNN.json"""
 import json
 import os
+
+os.environ.setdefault("V2S_ALLOW_RANDOM_INIT", "1")   # random-init weights by specification (no checkpoint offline)
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

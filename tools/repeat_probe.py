@@ -1,4 +1,6 @@
 """Run-to-run differences of the bf16 SSP step on fixed inputs (diagnostic)."""
+import os
+os.environ.setdefault("V2S_ALLOW_RANDOM_INIT", "1")   # random-init weights by specification (no checkpoint offline)
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

@@ -20,6 +20,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
+import sys
 import warnings
 import weakref
 
@@ -361,6 +362,48 @@ class _BackboneFn(torch.autograd.Function):
         return None, None, None, None, None
 
 
+_warned_random_init = False
+
+
+def _resolve_checkpoint(name):
+    """Weight file for `name`: a file, a directory holding model.safetensors / pytorch_model.bin, or a hub repo id
+    looked up in the HuggingFace cache (downloaded only if the hub is reachable and not disabled)."""
+    files = ("model.safetensors", "pytorch_model.bin")
+    if os.path.isfile(name):
+        return name
+    if os.path.isdir(name):
+        for f in files:
+            if os.path.isfile(os.path.join(name, f)):
+                return os.path.join(name, f)
+        return None
+    try:
+        import huggingface_hub as hub
+    except ImportError:
+        return None
+    offline = any(os.environ.get(k, "0") not in ("0", "") for k in ("HF_HUB_OFFLINE", "TRANSFORMERS_OFFLINE"))
+    for f in files:
+        try:
+            hit = hub.try_to_load_from_cache(name, f)
+            if isinstance(hit, str) and os.path.isfile(hit):
+                return hit
+        except Exception:  # noqa: BLE001  (malformed repo id etc.: treated as "not cached")
+            pass
+    if not offline:
+        for f in files:
+            try:
+                return hub.hf_hub_download(name, f)
+            except Exception:  # noqa: BLE001  (no network / no such file)
+                continue
+    return None
+
+
+def _load_weight_file(path):
+    if path.endswith(".safetensors"):
+        from safetensors.torch import load_file
+        return load_file(path, device="cpu")
+    return torch.load(path, map_location="cpu", weights_only=True)
+
+
 class ViTModel(nn.Module):
     """Drop-in for ``transformers.ViTModel`` as used by the reference (ViT-Tiny/16@224 only)."""
 
@@ -417,20 +460,39 @@ class ViTModel(nn.Module):
 
     @classmethod
     def from_pretrained(cls, name, **kw):
-        """The reference loads ``WinKawaks/vit-tiny-patch16-224`` (ref:ssp_vit2spn_tiny.py:112).  A local
-        HF checkpoint directory / state-dict file is loaded if `name` is a path; otherwise (offline)
-        the same architecture is built with HF random init."""
+        """The reference loads ``WinKawaks/vit-tiny-patch16-224`` (ref:ssp_vit2spn_tiny.py:112), i.e. it starts from
+        the ImageNet-1K ViT-Tiny.  `name` is resolved like transformers does: a local directory / weight file, else
+        the HuggingFace cache (and the hub, unless offline).  ``model.safetensors`` and ``pytorch_model.bin`` are both
+        read; missing / unexpected keys are reported.  If no checkpoint can be found this RAISES — training from random
+        weights while the script asked for pretrained ones must not happen silently — unless
+        ``V2S_ALLOW_RANDOM_INIT=1`` is set (offline boxes, benchmarks, tests: north_star specifies random init
+        there), in which case the HF random initialisation is kept and said so on stderr."""
         cfg_kw = {k: v for k, v in kw.items() if k in ("output_hidden_states",)}
         model = cls(ViTConfig(**cfg_kw))
-        path = name if os.path.exists(str(name)) else None
-        if path is not None:
-            f = os.path.join(path, "pytorch_model.bin") if os.path.isdir(path) else path
-            sd = torch.load(f, map_location="cpu")
-            sd = {k[4:] if k.startswith("vit.") else k: v for k, v in sd.items()}
-            model.load_state_dict(sd, strict=False)
-        else:
-            warnings.warn(f"vit2spn.ViTModel.from_pretrained({name!r}): no local checkpoint (offline); "
-                          "using HF random initialisation of ViT-Tiny/16")
+        path = _resolve_checkpoint(str(name))
+        if path is None:
+            if os.environ.get("V2S_ALLOW_RANDOM_INIT", "0") != "1":
+                raise OSError(
+                    f"vit2spn.ViTModel.from_pretrained({name!r}): no local checkpoint, nothing in the HuggingFace cache and "
+                    "the hub is not reachable.  The reference starts from these pretrained weights; set "
+                    "V2S_ALLOW_RANDOM_INIT=1 to start from HF random initialisation instead.")
+            global _warned_random_init
+            if not _warned_random_init:
+                print(f"vit2spn: from_pretrained({name!r}) found no checkpoint; V2S_ALLOW_RANDOM_INIT=1 -> RANDOM INIT "
+                      "(ViT-Tiny/16, HF _init_weights), not the pretrained weights", file=sys.stderr, flush=True)
+                _warned_random_init = True
+            return model
+        sd = _load_weight_file(path)
+        sd = {k[4:] if k.startswith("vit.") else k: v for k, v in sd.items()}
+        res = model.load_state_dict(sd, strict=False)
+        # a ViTForImageClassification checkpoint has a classifier and no pooler: exactly what transformers tolerates
+        missing = [k for k in res.missing_keys if not k.startswith("pooler.")]
+        unexpected = [k for k in res.unexpected_keys if not k.startswith("classifier.")]
+        print(f"vit2spn: loaded {path} ({len(sd) - len(res.unexpected_keys)} tensors; missing {res.missing_keys or 'none'}; "
+              f"unexpected {res.unexpected_keys or 'none'})", file=sys.stderr, flush=True)
+        if missing or unexpected:
+            raise RuntimeError(f"vit2spn.ViTModel.from_pretrained({name!r}): checkpoint does not match ViT-Tiny/16: "
+                               f"missing {missing}, unexpected {unexpected}")
         return model
 
     def _apply(self, fn, *a, **k):
@@ -460,9 +522,7 @@ class ViTBackbone(nn.Module):
 
     def __init__(self):
         super().__init__()
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            self.vit = ViTModel.from_pretrained("WinKawaks/vit-tiny-patch16-224", output_hidden_states=True)
+        self.vit = ViTModel.from_pretrained("WinKawaks/vit-tiny-patch16-224", output_hidden_states=True)
 
     def forward(self, x):
         return self.vit.features(x)
