@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="pairs per GPU")
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=8, help="bounded CPU sample (pairs per CPU step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -26,11 +26,17 @@
 extern "C" {
 #endif
 
-#define V2S_ABI_VERSION 1
+#define V2S_ABI_VERSION 2
 
 /* compute modes */
 #define V2S_MODE_FP32 0 /* fp32 activations + fp32 SIMT GEMMs: the "fp32 check mode" of north_star */
 #define V2S_MODE_BF16 1 /* bf16 GEMM operands (tcgen05), fp32 accumulate / residual / LN / softmax */
+#define V2S_MODE_FP16 2 /* fp16 GEMM operands: the reference's own CUDA precision (torch.autocast default dtype +
+                           GradScaler, ref:ssp_vit2spn_tiny.py:175,209-217); needs loss scaling (v2s_*_amp) */
+
+/* format of the 16-bit shadow copy of a flat parameter buffer (params_lp) */
+#define V2S_LP_BF16 0
+#define V2S_LP_FP16 1
 
 /* model constants: ViT-Tiny/16 @224 (ref:ssp_ssl/ssl_vit2spn_scratch.py:100-108) */
 #define V2S_HIDDEN 192
@@ -112,6 +118,13 @@ int v2s_heads_loss_fwd_bwd(const float* head_params, float* head_grads, const fl
                            float* target_proj, float* loss, int batch, int accumulation_steps,
                            float grad_scale, int with_backward, void* workspace,
                            int64_t workspace_bytes, void* stream);
+/* same with the loss scale read from device memory (*grad_scale_dev, e.g. torch.amp.GradScaler's scale tensor):
+ * scaler.scale(loss).backward() of ref:ssp_vit2spn_tiny.py:213 without a host synchronisation */
+int v2s_heads_loss_fwd_bwd_amp(const float* head_params, float* head_grads, const float* feat_online,
+                               const float* feat_target, const float* mask_online, const float* mask_target,
+                               float* dfeat_online, float* pred, float* target_proj, float* loss, int batch,
+                               int accumulation_steps, const float* grad_scale_dev, int with_backward,
+                               void* workspace, int64_t workspace_bytes, void* stream);
 
 /* The same three stages as separate calls, for the autograd-compatible path where the script's
  * own criterion computes the loss between forward and backward (ref:210-213).  The heads'
@@ -145,14 +158,36 @@ typedef struct v2s_range {
 } v2s_range_t;
 int v2s_adam_step(const v2s_range_t* host_ranges, int n_ranges, int64_t step, double lr, double beta1,
                   double beta2, double eps, double weight_decay, double grad_scale, void* stream);
+/* same, with the format of params_lp given (V2S_LP_BF16 / V2S_LP_FP16) */
+int v2s_adam_step_lp(const v2s_range_t* host_ranges, int n_ranges, int64_t step, double lr, double beta1,
+                     double beta2, double eps, double weight_decay, double grad_scale, int lp_format, void* stream);
+/* The optimizer step under torch.amp.GradScaler (ref:ssp_vit2spn_tiny.py:175,216-217: scaler.step(optimizer) /
+ * scaler.update()), without a host synchronisation: the step count lives on the device and the call is a no-op when
+ * the scaler found an inf / nan.  state8 = 8 caller-owned device floats, state8[0] = optimizer steps taken so far
+ * (initialise to 0; [1..7] are scratch); gradients are multiplied by grad_multiplier / (*grad_scale_dev)
+ * (grad_scale_dev = the scaler's scale tensor, may be NULL = 1); found_inf_dev (may be NULL) != 0 skips the update and
+ * leaves the step count unchanged, as torch's fused Adam does.  No host-side value changes from call to call, so the
+ * call can be captured in a CUDA graph.  advance_step = 1 starts a new optimizer step (advances state8[0] and derives
+ * the step's hyper-parameters into state8[1..4]); 0 applies the step already prepared in state8 to further ranges
+ * (more than 4 ranges sharing one step count). */
+int v2s_adam_step_amp(const v2s_range_t* host_ranges, int n_ranges, float* state8, double lr, double beta1,
+                      double beta2, double eps, double weight_decay, double grad_multiplier,
+                      const float* grad_scale_dev, const float* found_inf_dev, int lp_format, int advance_step,
+                      void* stream);
 
 /* update_target_network (ref:162-166): target = m*target + (1-m)*online over flat buffers */
 int v2s_ema_update(float* const* host_targets, const float* const* host_onlines,
                    void* const* host_targets_lp, int n_pairs, int64_t numel, double momentum,
                    void* stream);
 
+int v2s_ema_update_lp(float* const* host_targets, const float* const* host_onlines,
+                      void* const* host_targets_lp, int n_pairs, int64_t numel, double momentum, int lp_format,
+                      void* stream);
+
 /* fp32 → bf16 shadow copy of a flat buffer */
 int v2s_cast_bf16(const float* src, void* dst, int64_t numel, void* stream);
+/* fp32 → 16-bit shadow copy in the given format (V2S_LP_BF16 / V2S_LP_FP16) */
+int v2s_cast_lp(const float* src, void* dst, int64_t numel, int lp_format, void* stream);
 
 /* synthetic OCTMNIST-shaped input pipeline (ref:ssp_vit2spn_tiny.py:84-96, deterministic part):
  * uint8 [batch,1,28,28] → bilinear 224x224 → 3 channels → ImageNet normalise → fp32 NCHW */

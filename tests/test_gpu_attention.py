@@ -18,17 +18,18 @@ def _ref(qkv, dctx):
 
 
 @pytest.mark.parametrize("batch,scale", [(1, 1.0), (3, 1.0), (5, 4.0), (64, 0.5)])
-@pytest.mark.parametrize("variant", [0, 1])          # 0 = tensor-core kernels, 1 = SIMT reference kernels
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])    # bit 0: SIMT reference kernels instead of tensor-core; bit 1: fp16 tensors
 def test_attention_forward_backward(batch, scale, variant):
     import vit2spn  # noqa: F401
     from vit2spn import _lib
     dev = torch.device("cuda", 0)
     _lib.init_device(0)
     g = torch.Generator(device=dev).manual_seed(batch)
-    qkv = (torch.randn(batch, 197, 576, device=dev, generator=g) * scale).bfloat16()
-    dctx = torch.randn(batch, 197, 192, device=dev, generator=g).bfloat16()
+    lp = torch.float16 if variant & 2 else torch.bfloat16
+    qkv = (torch.randn(batch, 197, 576, device=dev, generator=g) * scale).to(lp)
+    dctx = torch.randn(batch, 197, 192, device=dev, generator=g).to(lp)
     o_ref, lse_ref, dqkv_ref = _ref(qkv, dctx)
-    ctx = torch.full((batch, 197, 192), float("nan"), device=dev, dtype=torch.bfloat16)
+    ctx = torch.full((batch, 197, 192), float("nan"), device=dev, dtype=lp)
     lse = torch.full((batch, 3, 197), float("nan"), device=dev)
     _lib.check(_lib.lib.v2s_test_attention(0, _lib.ptr(qkv), _lib.ptr(ctx), _lib.ptr(lse), None, None, batch, variant,
                                            _lib.stream_ptr()), "attention fwd")
@@ -38,7 +39,7 @@ def test_attention_forward_backward(batch, scale, variant):
     assert torch.isfinite(ctx.float()).all()
     assert (ctx.float() - o_ref).abs().max().item() <= 0.02 * max(1.0, o_ref.abs().max().item())
     assert (lse - lse_ref).abs().max().item() <= 2e-3 * max(1.0, lse_ref.abs().max().item())
-    dqkv = torch.full((batch, 197, 576), float("nan"), device=dev, dtype=torch.bfloat16)
+    dqkv = torch.full((batch, 197, 576), float("nan"), device=dev, dtype=lp)
     _lib.check(_lib.lib.v2s_test_attention(1, _lib.ptr(qkv), _lib.ptr(ctx), _lib.ptr(lse), _lib.ptr(dctx), _lib.ptr(dqkv),
                                            batch, variant, _lib.stream_ptr()), "attention bwd")
     torch.cuda.synchronize()

@@ -16,48 +16,55 @@ SHAPES = [
 ]
 
 
+LP = {0: torch.bfloat16, 2: torch.float16}      # v2s_test_gemm variant bit 1: fp16 instead of bf16 tensors
+
+
 @pytest.mark.parametrize("which,m,n,k", SHAPES)
-def test_tcgen05_gemm_matches_fp32_matmul(which, m, n, k):
+@pytest.mark.parametrize("fmt", [0, 2])
+def test_tcgen05_gemm_matches_fp32_matmul(which, m, n, k, fmt):
     from vit2spn import _lib
     _lib.init_device(0)
     dev = torch.device("cuda:0")
+    lp = LP[fmt]
     g = torch.Generator(device=dev).manual_seed(which * 1000 + m + n + k)
     if which == 0:
-        a = torch.randn(m, k, device=dev, generator=g).bfloat16(); b = torch.randn(n, k, device=dev, generator=g).bfloat16()
+        a = torch.randn(m, k, device=dev, generator=g).to(lp); b = torch.randn(n, k, device=dev, generator=g).to(lp)
         ref = a.float() @ b.float().t()
     elif which == 1:
-        a = torch.randn(m, k, device=dev, generator=g).bfloat16(); b = torch.randn(k, n, device=dev, generator=g).bfloat16()
+        a = torch.randn(m, k, device=dev, generator=g).to(lp); b = torch.randn(k, n, device=dev, generator=g).to(lp)
         ref = a.float() @ b.float()
     else:
-        a = torch.randn(k, m, device=dev, generator=g).bfloat16(); b = torch.randn(k, n, device=dev, generator=g).bfloat16()
+        a = torch.randn(k, m, device=dev, generator=g).to(lp); b = torch.randn(k, n, device=dev, generator=g).to(lp)
         ref = a.float().t() @ b.float()
     if which == 2:
         base = torch.randn(m, n, device=dev, generator=g)
         c = base.clone()                         # accumulate-into semantics (+=)
         ref = ref + base
     else:
-        c = torch.full((m, n), float("nan"), device=dev, dtype=torch.bfloat16)
-    _lib.check(_lib.lib.v2s_test_gemm(which, _lib.ptr(a), _lib.ptr(b), _lib.ptr(c), m, n, k, 0, _lib.stream_ptr()))
+        c = torch.full((m, n), float("nan"), device=dev, dtype=lp)
+    _lib.check(_lib.lib.v2s_test_gemm(which, _lib.ptr(a), _lib.ptr(b), _lib.ptr(c), m, n, k, fmt, _lib.stream_ptr()))
     torch.cuda.synchronize()
     assert _lib.lib.v2s_debug_flag() == 0, "tcgen05 pipeline protocol timeout"
     err = (c.float() - ref).abs().max().item()
     scale = ref.abs().max().item()
-    assert err <= (2e-5 if which == 2 else 6e-3) * scale + 1e-3, (err, scale)
+    assert err <= (2e-5 if which == 2 else 6e-3 if fmt == 0 else 1e-3) * scale + 1e-3, (err, scale)
 
 
 @pytest.mark.parametrize("m,n,k", [(256, 768, 192), (1576, 768, 192)])
-def test_gelu_epilogues_match_erf_gelu(m, n, k):
+@pytest.mark.parametrize("fmt", [0, 2])
+def test_gelu_epilogues_match_erf_gelu(m, n, k, fmt):
     """fc1 epilogue (u = x W^T, h = gelu(u)) and the dgrad epilogue (dy W * gelu'(u)) of the bf16 path against the
     exact erf form (HF hidden_act="gelu"): the fast erf approximation (|error| < 1.5e-7) must disappear inside the
     bf16 rounding of the stored value."""
     from vit2spn import _lib
     _lib.init_device(0)
     dev = torch.device("cuda:0")
+    lp = LP[fmt]
     g = torch.Generator(device=dev).manual_seed(m + n)
-    a = torch.randn(m, k, device=dev, generator=g).bfloat16()
-    b = (torch.randn(n, k, device=dev, generator=g) * 0.15).bfloat16()          # u ~ N(0, 2): covers both tails
-    out = torch.full((2, m, n), float("nan"), device=dev, dtype=torch.bfloat16)
-    _lib.check(_lib.lib.v2s_test_gemm(5, _lib.ptr(a), _lib.ptr(b), _lib.ptr(out), m, n, k, 0, _lib.stream_ptr()))
+    a = torch.randn(m, k, device=dev, generator=g).to(lp)
+    b = (torch.randn(n, k, device=dev, generator=g) * 0.15).to(lp)          # u ~ N(0, 2): covers both tails
+    out = torch.full((2, m, n), float("nan"), device=dev, dtype=lp)
+    _lib.check(_lib.lib.v2s_test_gemm(5, _lib.ptr(a), _lib.ptr(b), _lib.ptr(out), m, n, k, fmt, _lib.stream_ptr()))
     torch.cuda.synchronize()
     assert _lib.lib.v2s_debug_flag() == 0
     u_ref = a.float() @ b.float().t()
@@ -67,11 +74,11 @@ def test_gelu_epilogues_match_erf_gelu(m, n, k):
     assert ((h - h_ref).abs() <= 4e-3 * h_ref.abs() + 2e-4).all(), (h - h_ref).abs().max().item()
     # derivative epilogue: dy [m, n2] @ W [n2, n] * gelu'(u)
     n2 = 192
-    dy = torch.randn(m, n2, device=dev, generator=g).bfloat16()
-    w = (torch.randn(n2, n, device=dev, generator=g) * 0.1).bfloat16()
-    buf = torch.empty(2, m, n, device=dev, dtype=torch.bfloat16)
+    dy = torch.randn(m, n2, device=dev, generator=g).to(lp)
+    w = (torch.randn(n2, n, device=dev, generator=g) * 0.1).to(lp)
+    buf = torch.empty(2, m, n, device=dev, dtype=lp)
     buf[1] = out[1]
-    _lib.check(_lib.lib.v2s_test_gemm(6, _lib.ptr(dy), _lib.ptr(w), _lib.ptr(buf), m, n, n2, 0, _lib.stream_ptr()))
+    _lib.check(_lib.lib.v2s_test_gemm(6, _lib.ptr(dy), _lib.ptr(w), _lib.ptr(buf), m, n, n2, fmt, _lib.stream_ptr()))
     torch.cuda.synchronize()
     assert _lib.lib.v2s_debug_flag() == 0
     uu = out[1].float().requires_grad_(True)

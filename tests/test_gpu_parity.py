@@ -692,3 +692,68 @@ def test_bf16_eval1024_and_finetune_parity(dev):
     assert g_rnd <= 2e-2
     assert g_rel <= max(2e-2, 1.25 * g_torch)
     opt.step()
+
+
+def test_fp16_mode_meets_the_loss_gate_and_grad_scaler_recipe(dev):
+    """The reference's own CUDA precision (ref:ssp_vit2spn_tiny.py:175,209-217: fp16 autocast + GradScaler), B = 128,
+    seed 42.  (a) forward: loss <= 1e-3 relative against the fp32 oracle — the north_star gate that bf16 cannot meet
+    (11-bit mantissa: weight rounding is 8x smaller) — and against the fp16 rounding model of the oracle;
+    (b) one step of the recipe through torch.amp.GradScaler (scale 65536): scaled backward, scaler.step unscales inside
+    the Adam kernel, gradients <= 2e-2 rel-L2 against the fp32 oracle, the optimizer moved the weights;
+    (c) an overflowing scale makes found_inf skip the update on the device and halves the scale (ref:216-217)."""
+    import vit2spn
+    from oracle import vit2spn_oracle as orc
+    state = orc.init_state(42, 0.0)
+    x1, x2 = orc.synthetic_views(128, seed=42)
+    a, b = x1.to(dev), x2.to(dev)
+    model = _build(state, dev, "fp16")
+    o_loss, o_grads = _gpu_oracle(orc, state, x1, x2, dev, "fp32")
+    r_loss, _ = _gpu_oracle(orc, state, x1, x2, dev, "rounded", dtype=torch.float16, grads=False)
+    t_loss, _ = _gpu_oracle(orc, state, x1, x2, dev, "autocast", dtype=torch.float16, grads=False)
+    opt = vit2spn.FusedAdam(model.parameters(), lr=1e-4)
+    scaler = torch.amp.GradScaler("cuda")
+    opt.zero_grad()
+    loss = model.ssp_step(a, b, accumulation_steps=1, grad_scale=scaler)
+    rel = abs(loss.item() - o_loss) / abs(o_loss)
+    scale = scaler.get_scale()
+    grads = {n: (p.grad / scale) for n, p in model.named_parameters() if p.grad is not None}
+    assert all(torch.isfinite(g).all() for g in grads.values())
+    g_rel, worst = _rel_l2(grads, o_grads)
+    print(f"[fp16 B=128] loss {loss.item():.8f} fp32 oracle {o_loss:.8f} rel {rel:.2e} | fp16 rounding model rel "
+          f"{abs(loss.item() - r_loss) / abs(r_loss):.2e} | torch fp16 autocast vs fp32 {abs(t_loss - o_loss) / abs(o_loss):.2e} "
+          f"| scale {scale:g} grads rel-L2 {g_rel:.2e} worst {worst}")
+    _report["fp16_b128"] = dict(loss=loss.item(), fp32_oracle_loss=o_loss, loss_rel_vs_fp32_oracle=rel,
+                                loss_rel_vs_rounding_model=abs(loss.item() - r_loss) / abs(r_loss),
+                                torch_fp16_autocast_rel_vs_fp32=abs(t_loss - o_loss) / abs(o_loss), loss_scale=scale,
+                                grad_rel_l2_vs_fp32_oracle=g_rel)
+    _dump()
+    assert scale == 65536.0
+    assert rel <= 1e-3
+    assert abs(loss.item() - r_loss) / abs(r_loss) <= 1e-3
+    assert g_rel <= 2e-2
+    before = model.online_network_1.vit.encoder.layer[0].intermediate.dense.weight.detach().clone()
+    t_before = model.target_network_1.vit.encoder.layer[0].intermediate.dense.weight.detach().clone()
+    scaler.step(opt)
+    scaler.update()
+    model.update_target_network()
+    after = model.online_network_1.vit.encoder.layer[0].intermediate.dense.weight.detach()
+    # first Adam step: every element with a non-negligible gradient moves by ~lr, whatever the loss scale was
+    moved = (after - before).abs()
+    assert 0.5e-4 < float(moved.median()) < 1.5e-4, float(moved.median())
+    assert scaler.get_scale() == 65536.0
+    assert float(opt.state_dict()["state"][0]["step"]) == 1.0
+    # the fp16 shadow the tensor cores read follows the fp32 masters (refreshed inside the Adam / EMA kernels)
+    st = model.online_network_1.vit._store
+    assert st.flat_lp.dtype == torch.float16 and torch.equal(st.flat_lp[:st.active_numel], st.flat[:st.active_numel].half())
+    assert torch.equal(model.target_network_1.vit._store.flat_lp, model.target_network_1.vit._store.flat.half())
+    assert not torch.equal(t_before, model.target_network_1.vit.encoder.layer[0].intermediate.dense.weight.detach())
+    # (c) overflow: a huge scale drives the fp16 gradients to inf -> the step is skipped and the scale backs off
+    big = torch.amp.GradScaler("cuda", init_scale=2.0 ** 40)
+    opt.zero_grad()
+    model.ssp_step(a, b, accumulation_steps=1, grad_scale=big)
+    snap = model.online_network_1.vit._store.flat.clone()
+    big.step(opt)
+    big.update()
+    assert torch.equal(snap, model.online_network_1.vit._store.flat), "the update must be skipped on overflow"
+    assert big.get_scale() == 2.0 ** 39
+    assert float(opt.state_dict()["state"][0]["step"]) == 1.0          # a skipped step does not count (as torch's fused Adam)

@@ -13,6 +13,9 @@ LIB_PATH = os.path.join(_HERE, "libvit2spn.so")
 
 MODE_FP32 = 0
 MODE_BF16 = 1
+MODE_FP16 = 2
+LP_BF16 = 0
+LP_FP16 = 1
 MAX_GROUPS = 4
 
 if not os.path.exists(LIB_PATH):
@@ -54,11 +57,17 @@ _SIGS = {
     "v2s_backbone_backward": (C.c_int, [C.POINTER(Group), _i, _i, _i, _vp, _i64, _vp]),
     "v2s_heads_loss_fwd_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i,
                                          _vp, _i64, _vp]),
+    "v2s_heads_loss_fwd_bwd_amp": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i,
+                                             _vp, _i64, _vp]),
     "v2s_heads_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i64, _vp]),
     "v2s_heads_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i64, _vp]),
     "v2s_cosine_loss": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "v2s_dropout_mask": (C.c_int, [_vp, _i64, _f, C.c_uint64, C.c_uint64, _vp]),
     "v2s_adam_step": (C.c_int, [C.POINTER(Range), _i, _i64, _d, _d, _d, _d, _d, _d, _vp]),
+    "v2s_adam_step_lp": (C.c_int, [C.POINTER(Range), _i, _i64, _d, _d, _d, _d, _d, _d, _i, _vp]),
+    "v2s_adam_step_amp": (C.c_int, [C.POINTER(Range), _i, _vp, _d, _d, _d, _d, _d, _d, _vp, _vp, _i, _i, _vp]),
+    "v2s_ema_update_lp": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i, _i64, _d, _i, _vp]),
+    "v2s_cast_lp": (C.c_int, [_vp, _vp, _i64, _i, _vp]),
     "v2s_ema_update": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i, _i64, _d, _vp]),
     "v2s_cast_bf16": (C.c_int, [_vp, _vp, _i64, _vp]),
     "v2s_preprocess_u8": (C.c_int, [_vp, _vp, _i, _vp]),

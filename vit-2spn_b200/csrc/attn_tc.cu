@@ -13,6 +13,7 @@
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
+#include "tc_math.cuh"
 
 namespace v2s {
 
@@ -240,7 +241,7 @@ struct alignas(64) AttnFwdPParams {
   long long* dbg;   // optional cycle counters of CTA 0 (V2S_GEMM_DEBUG): [0..3] UMMA warp waits, [8..15] softmax thread phases
 };
 
-template <bool DBG>   // DBG: instrumented build (phase cycle counters), launched only when V2S_GEMM_DEBUG is set
+template <bool DBG, typename LP>   // DBG: instrumented build (phase cycle counters), launched only when V2S_GEMM_DEBUG is set
 __global__ void __launch_bounds__(PF_THREADS, 1) attn_fwd_persist_kernel(const __grid_constant__ AttnFwdPParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -302,8 +303,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) attn_fwd_persist_kernel(const _
     }
   } else if (warp == 1) {
     // ---- UMMA issuer: S(n) as soon as its stage and slot are ready, then P V of job n-1 ----
-    const uint32_t idesc_s = ptx::make_idesc_bf16(QT, KPAD, 0, 0);
-    const uint32_t idesc_o = ptx::make_idesc_bf16(QT, DH, 0, 1);
+    const uint32_t idesc_s = make_idesc_lp(LP::kIdescFmt, QT, KPAD, 0, 0);
+    const uint32_t idesc_o = make_idesc_lp(LP::kIdescFmt, QT, DH, 0, 1);
     const uint32_t sbase = ptx::smem_u32(smem);
     long long w_load = 0, w_tfree = 0, w_p = 0; const long long t_mma0 = clock64();
     for (int n = 0; n <= njobs; ++n) {
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) attn_fwd_persist_kernel(const _
           const float e0 = ptx::ex2_approx(fmaf(__uint_as_float(v[2 * i]), SCALE_LOG2E, -moff));
           const float e1 = ptx::ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), SCALE_LOG2E, -moff));
           sum += e0 + e1;
-          pw[i] = pack2(e0, e1);
+          pw[i] = LP::pack(e0, e1);
         }
         ptx::tmem_st_32x16(taddr + pcol, pw);
       };
@@ -442,7 +443,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) attn_fwd_persist_kernel(const _
           const float e0 = (176 + 2 * i < NT) ? ptx::ex2_approx(fmaf(__uint_as_float(v[2 * i]), SCALE_LOG2E, -moff)) : 0.f;
           const float e1 = (177 + 2 * i < NT) ? ptx::ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), SCALE_LOG2E, -moff)) : 0.f;
           sum += e0 + e1;
-          pw[i] = pack2(e0, e1);
+          pw[i] = LP::pack(e0, e1);
         }
         ptx::tmem_st_32x16(taddr + pcol, pw);
       };
@@ -463,7 +464,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) attn_fwd_persist_kernel(const _
           const float e0 = ptx::ex2_approx(fmaf(__uint_as_float(r2[2 * i]), SCALE_LOG2E, -moff));
           const float e1 = ptx::ex2_approx(fmaf(__uint_as_float(r2[2 * i + 1]), SCALE_LOG2E, -moff));
           sum += e0 + e1;
-          pw[i] = pack2(e0, e1);
+          pw[i] = LP::pack(e0, e1);
         }
         ptx::tmem_st_32x8(taddr + 48, pw);
       }
@@ -491,10 +492,10 @@ __global__ void __launch_bounds__(PF_THREADS, 1) attn_fwd_persist_kernel(const _
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         uint4 v;
-        v.x = pack2(__uint_as_float(r[8 * jj]) * inv, __uint_as_float(r[8 * jj + 1]) * inv);
-        v.y = pack2(__uint_as_float(r[8 * jj + 2]) * inv, __uint_as_float(r[8 * jj + 3]) * inv);
-        v.z = pack2(__uint_as_float(r[8 * jj + 4]) * inv, __uint_as_float(r[8 * jj + 5]) * inv);
-        v.w = pack2(__uint_as_float(r[8 * jj + 6]) * inv, __uint_as_float(r[8 * jj + 7]) * inv);
+        v.x = LP::pack(__uint_as_float(r[8 * jj]) * inv, __uint_as_float(r[8 * jj + 1]) * inv);
+        v.y = LP::pack(__uint_as_float(r[8 * jj + 2]) * inv, __uint_as_float(r[8 * jj + 3]) * inv);
+        v.z = LP::pack(__uint_as_float(r[8 * jj + 4]) * inv, __uint_as_float(r[8 * jj + 5]) * inv);
+        v.w = LP::pack(__uint_as_float(r[8 * jj + 6]) * inv, __uint_as_float(r[8 * jj + 7]) * inv);
         *reinterpret_cast<uint4*>(stg + row * 128 + (((hf * 4 + jj) ^ (row & 7)) << 4)) = v;
       }
       ptx::fence_proxy_async();
@@ -554,7 +555,7 @@ __device__ __forceinline__ uint4 load_p_chunk(const uint8_t* tile, int r, int c8
   return *reinterpret_cast<const uint4*>(tile + block * (QT * 128) + r * 128 + ((chunk ^ (r & 7)) << 4));
 }
 
-template <bool DBG>
+template <bool DBG, typename LP>
 __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -606,9 +607,9 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
     const uint32_t sbase = ptx::smem_u32(smem);
     const uint32_t sq = sbase + B_OFF_Q, sdo = sbase + B_OFF_DO, sk = sbase + B_OFF_K, sv = sbase + B_OFF_V;
     const uint32_t sp = sbase + B_OFF_P, sds = sbase + B_OFF_DS;
-    const uint32_t idesc_s = ptx::make_idesc_bf16(QT, KPAD, 0, 0);
-    const uint32_t idesc_dq = ptx::make_idesc_bf16(QT, DH, 0, 1);
-    const uint32_t idesc_kv = ptx::make_idesc_bf16(QT, DH, 1, 1);
+    const uint32_t idesc_s = make_idesc_lp(LP::kIdescFmt, QT, KPAD, 0, 0);
+    const uint32_t idesc_dq = make_idesc_lp(LP::kIdescFmt, QT, DH, 0, 1);
+    const uint32_t idesc_kv = make_idesc_lp(LP::kIdescFmt, QT, DH, 1, 1);
 #pragma unroll 1
     for (int t = 0; t < 2; ++t) {
       if (t == 1) {
@@ -705,10 +706,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
           const uint32_t ow[4] = {ov[c].x, ov[c].y, ov[c].z, ov[c].w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const __nv_bfloat162 o2 = *reinterpret_cast<const __nv_bfloat162*>(&ow[e]);
-            const __nv_bfloat162 d2 = *reinterpret_cast<const __nv_bfloat162*>(&dw[e]);
-            Dr = fmaf(__low2float(o2), __low2float(d2), Dr);
-            Dr = fmaf(__high2float(o2), __high2float(d2), Dr);
+            Dr = fmaf(LP::lo(ow[e]), LP::lo(dw[e]), Dr);
+            Dr = fmaf(LP::hi(ow[e]), LP::hi(dw[e]), Dr);
           }
         }
       }
@@ -735,7 +734,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
               e[i] = (176 + j * 8 + i < NT) ? ptx::ex2_approx(fmaf(__uint_as_float(r[8 * j + i]), SCALE_LOG2E, -lse2)) : 0.f;
           }
           uint4 v;
-          v.x = pack2(e[0], e[1]); v.y = pack2(e[2], e[3]); v.z = pack2(e[4], e[5]); v.w = pack2(e[6], e[7]);
+          v.x = LP::pack(e[0], e[1]); v.y = LP::pack(e[2], e[3]); v.z = LP::pack(e[4], e[5]); v.w = LP::pack(e[6], e[7]);
           store_p_chunk_s(prow_s, rx, (col0 + c * 32) / 8 + j, v);
         }
       }
@@ -749,7 +748,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
           for (int i = 0; i < 8; ++i)
             e[i] = ptx::ex2_approx(fmaf(__uint_as_float(r[8 * j + i]), SCALE_LOG2E, -lse2));
           uint4 v;
-          v.x = pack2(e[0], e[1]); v.y = pack2(e[2], e[3]); v.z = pack2(e[4], e[5]); v.w = pack2(e[6], e[7]);
+          v.x = LP::pack(e[0], e[1]); v.y = LP::pack(e[2], e[3]); v.z = LP::pack(e[4], e[5]); v.w = LP::pack(e[6], e[7]);
           store_p_chunk_s(prow_s, rx, 12 + j, v);
         }
       }
@@ -774,12 +773,11 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
           float d[8];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const __nv_bfloat162 p2 = *reinterpret_cast<const __nv_bfloat162*>(&pw[e]);
-            d[2 * e] = __low2float(p2) * fmaf(__uint_as_float(r[8 * j + 2 * e]), SCALE, mDs);
-            d[2 * e + 1] = __high2float(p2) * fmaf(__uint_as_float(r[8 * j + 2 * e + 1]), SCALE, mDs);
+            d[2 * e] = LP::lo(pw[e]) * fmaf(__uint_as_float(r[8 * j + 2 * e]), SCALE, mDs);
+            d[2 * e + 1] = LP::hi(pw[e]) * fmaf(__uint_as_float(r[8 * j + 2 * e + 1]), SCALE, mDs);
           }
           uint4 v;
-          v.x = pack2(d[0], d[1]); v.y = pack2(d[2], d[3]); v.z = pack2(d[4], d[5]); v.w = pack2(d[6], d[7]);
+          v.x = LP::pack(d[0], d[1]); v.y = LP::pack(d[2], d[3]); v.z = LP::pack(d[4], d[5]); v.w = LP::pack(d[6], d[7]);
           store_p_chunk_s(dsrow_s, rx, c8, v);
         }
       }
@@ -793,12 +791,11 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
           float d[8];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const __nv_bfloat162 p2 = *reinterpret_cast<const __nv_bfloat162*>(&pw[e]);
-            d[2 * e] = __low2float(p2) * fmaf(__uint_as_float(r[8 * j + 2 * e]), SCALE, mDs);
-            d[2 * e + 1] = __high2float(p2) * fmaf(__uint_as_float(r[8 * j + 2 * e + 1]), SCALE, mDs);
+            d[2 * e] = LP::lo(pw[e]) * fmaf(__uint_as_float(r[8 * j + 2 * e]), SCALE, mDs);
+            d[2 * e + 1] = LP::hi(pw[e]) * fmaf(__uint_as_float(r[8 * j + 2 * e + 1]), SCALE, mDs);
           }
           uint4 v;
-          v.x = pack2(d[0], d[1]); v.y = pack2(d[2], d[3]); v.z = pack2(d[4], d[5]); v.w = pack2(d[6], d[7]);
+          v.x = LP::pack(d[0], d[1]); v.y = LP::pack(d[2], d[3]); v.z = LP::pack(d[4], d[5]); v.w = LP::pack(d[6], d[7]);
           store_p_chunk_s(dsrow_s, rx, 12 + j, v);
         }
       }
@@ -819,10 +816,10 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 v;
-        v.x = pack2(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]));
-        v.y = pack2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
-        v.z = pack2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
-        v.w = pack2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+        v.x = LP::pack(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]));
+        v.y = LP::pack(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+        v.z = LP::pack(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+        v.w = LP::pack(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
         *reinterpret_cast<uint4*>(stg + row * 128 + (((half * 4 + j) ^ (row & 7)) << 4)) = v;
       }
       ptx::fence_proxy_async();
@@ -849,10 +846,10 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint4 v;
-          v.x = pack2(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]));
-          v.y = pack2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
-          v.z = pack2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
-          v.w = pack2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+          v.x = LP::pack(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]));
+          v.y = LP::pack(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+          v.z = LP::pack(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+          v.w = LP::pack(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
           *reinterpret_cast<uint4*>(stg + row * 128 + (((half * 4 + j) ^ (row & 7)) << 4)) = v;
         }
       }
@@ -886,7 +883,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
 }  // namespace
 
 int launch_attn_fwd_tc(const void* const* qkv, void* const* ctx, float* const* lse, int groups, int B,
-                       cudaStream_t s) {
+                       cudaStream_t s, int lp_f16) {
   AttnFwdParams p;
   memset(&p, 0, sizeof(p));
   p.err_flag = tc_err_flag();
@@ -897,7 +894,7 @@ int launch_attn_fwd_tc(const void* const* qkv, void* const* ctx, float* const* l
     p.lse[g] = lse ? lse[g] : nullptr;
   }
   static const bool legacy = getenv("V2S_ATTN_FWD") && strcmp(getenv("V2S_ATTN_FWD"), "v1") == 0;
-  if (legacy) {      // one CTA per job, two CTAs per SM (kept for A/B measurements)
+  if (legacy && !lp_f16) {      // one CTA per job, two CTAs per SM (kept for A/B measurements; bf16 only)
     static bool attr = false;
     if (!attr) {
       V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
@@ -917,12 +914,19 @@ int launch_attn_fwd_tc(const void* const* qkv, void* const* ctx, float* const* l
     int dev = 0;
     V2S_CUDA_OK(cudaGetDevice(&dev));
     V2S_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
-    V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_persist_kernel<false, LpBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_persist_kernel<true, LpBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_persist_kernel<false, LpF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_persist_kernel<true, LpF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
   }
   const int grid = pp.total_jobs < num_sms ? pp.total_jobs : num_sms;
-  if (pp.dbg) V2S_CUDA_OK(launch_pdl(attn_fwd_persist_kernel<true>, dim3(grid), dim3(PF_THREADS), (size_t)PF_SMEM, s, pp));
-  else V2S_CUDA_OK(launch_pdl(attn_fwd_persist_kernel<false>, dim3(grid), dim3(PF_THREADS), (size_t)PF_SMEM, s, pp));
+  if (lp_f16) {
+    if (pp.dbg) V2S_CUDA_OK(launch_pdl(attn_fwd_persist_kernel<true, LpF16>, dim3(grid), dim3(PF_THREADS), (size_t)PF_SMEM, s, pp));
+    else V2S_CUDA_OK(launch_pdl(attn_fwd_persist_kernel<false, LpF16>, dim3(grid), dim3(PF_THREADS), (size_t)PF_SMEM, s, pp));
+  } else {
+    if (pp.dbg) V2S_CUDA_OK(launch_pdl(attn_fwd_persist_kernel<true, LpBf16>, dim3(grid), dim3(PF_THREADS), (size_t)PF_SMEM, s, pp));
+    else V2S_CUDA_OK(launch_pdl(attn_fwd_persist_kernel<false, LpBf16>, dim3(grid), dim3(PF_THREADS), (size_t)PF_SMEM, s, pp));
+  }
   V2S_LAUNCH_CHECK();
   return 0;
 }
@@ -932,7 +936,7 @@ int launch_attn_fwd_tc(const void* const* qkv, void* const* ctx, float* const* l
 namespace v2s {
 
 int launch_attn_bwd_tc(const void* const* qkv, const void* const* ctx, const float* const* lse,
-                       const void* const* dctx, void* const* dqkv, int groups, int B, cudaStream_t s) {
+                       const void* const* dctx, void* const* dqkv, int groups, int B, cudaStream_t s, int lp_f16) {
   AttnBwdParams p;
   memset(&p, 0, sizeof(p));
   p.err_flag = tc_err_flag();
@@ -947,12 +951,20 @@ int launch_attn_bwd_tc(const void* const* qkv, const void* const* ctx, const flo
   p.dbg = tc_dbg_counters();
   static bool attr = false;
   if (!attr) {
-    V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
-    V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, LpBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<true, LpBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, LpF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<true, LpF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
     attr = true;
   }
-  if (p.dbg) V2S_CUDA_OK(launch_pdl(attn_bwd_tc_kernel<true>, dim3(NH, B, groups), dim3(B_THREADS), (size_t)B_SMEM, s, p));
-  else V2S_CUDA_OK(launch_pdl(attn_bwd_tc_kernel<false>, dim3(NH, B, groups), dim3(B_THREADS), (size_t)B_SMEM, s, p));
+  const dim3 grid(NH, B, groups);
+  if (lp_f16) {
+    if (p.dbg) V2S_CUDA_OK(launch_pdl(attn_bwd_tc_kernel<true, LpF16>, grid, dim3(B_THREADS), (size_t)B_SMEM, s, p));
+    else V2S_CUDA_OK(launch_pdl(attn_bwd_tc_kernel<false, LpF16>, grid, dim3(B_THREADS), (size_t)B_SMEM, s, p));
+  } else {
+    if (p.dbg) V2S_CUDA_OK(launch_pdl(attn_bwd_tc_kernel<true, LpBf16>, grid, dim3(B_THREADS), (size_t)B_SMEM, s, p));
+    else V2S_CUDA_OK(launch_pdl(attn_bwd_tc_kernel<false, LpBf16>, grid, dim3(B_THREADS), (size_t)B_SMEM, s, p));
+  }
   V2S_LAUNCH_CHECK();
   return 0;
 }

@@ -1,6 +1,7 @@
 // Shared definitions for the vit2spn sm_100a kernels.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
@@ -12,6 +13,9 @@
 namespace v2s {
 
 typedef __nv_bfloat16 bf16;
+typedef __half f16;
+// activation type tags used across the launchers: 0 = fp32, 1 = bf16, 2 = fp16
+constexpr int AT_F32 = 0, AT_BF16 = 1, AT_F16 = 2;
 
 constexpr int D = V2S_HIDDEN;        // 192
 constexpr int NT = V2S_TOKENS;       // 197
@@ -114,9 +118,11 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f<f16>(f16 v) { return __half2float(v); }
 template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ f16 from_f<f16>(float v) { return __float2half_rn(v); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

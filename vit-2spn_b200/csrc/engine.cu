@@ -78,7 +78,7 @@ Plan make_plan(int B, int mode) {
   Plan p;
   memset(&p, 0, sizeof(p));
   p.B = B;
-  p.at = mode == V2S_MODE_BF16 ? 1 : 0;
+  p.at = mode == V2S_MODE_BF16 ? AT_BF16 : mode == V2S_MODE_FP16 ? AT_F16 : AT_F32;   // activation type tag
   p.es = p.at ? 2 : 4;
   p.M = (int64_t)B * NT;
   p.MP = (int64_t)B * NP;
@@ -187,13 +187,13 @@ inline const void* weight_ptr(const v2s_group_t& g, int at, int64_t off) {
 int launch_attention_fwd(const void* const* qkv, void* const* ctx, float* const* lse, int groups, int B, int at,
                          cudaStream_t s) {
   prof::Scope scope(prof::C_ATTN_F, 4.0 * B * NH * (double)NT * NT * DH * groups, s, (double)B * NT * 4 * D * 2.0 * groups);
-  if (at == 1 && tc_enabled()) return launch_attn_fwd_tc(qkv, ctx, lse, groups, B, s);
+  if (at != AT_F32 && tc_enabled()) return launch_attn_fwd_tc(qkv, ctx, lse, groups, B, s, at == AT_F16);
   return launch_attn_fwd_simt(qkv, ctx, lse, groups, B, at, s);
 }
 int launch_attention_bwd(const void* const* qkv, const void* const* ctx, const float* const* lse,
                          const void* const* dctx, void* const* dqkv, int groups, int B, int at, cudaStream_t s) {
   prof::Scope scope(prof::C_ATTN_B, 10.0 * B * NH * (double)NT * NT * DH * groups, s, (double)B * NT * 8 * D * 2.0 * groups);
-  if (at == 1 && tc_enabled()) return launch_attn_bwd_tc(qkv, ctx, lse, dctx, dqkv, groups, B, s);
+  if (at != AT_F32 && tc_enabled()) return launch_attn_bwd_tc(qkv, ctx, lse, dctx, dqkv, groups, B, s, at == AT_F16);
   return launch_attn_bwd_simt(qkv, ctx, lse, dctx, dqkv, groups, B, at, s);
 }
 
@@ -211,6 +211,7 @@ int wgrad_split(int64_t rows) {
 // =============================================================================================
 static int backbone_forward_impl(const v2s_group_t* gs, int G, int B, int mode, void* ws, int64_t ws_bytes,
                                  cudaStream_t st) {
+  if (mode < V2S_MODE_FP32 || mode > V2S_MODE_FP16) { set_error("bad compute mode %d", mode); return 1; }
   if (G < 1 || G > MAXG) { set_error("backbone_forward: 1..4 groups"); return 1; }
   if (B < 1) { set_error("backbone_forward: batch must be >= 1"); return 1; }
   const Plan p = make_plan(B, mode);
@@ -220,7 +221,7 @@ static int backbone_forward_impl(const v2s_group_t* gs, int G, int B, int mode, 
   V2S_TRY(resolve_regions(p, ws, ws_bytes, G, n_saved, &R));
   for (int g = 0; g < G; ++g) {
     if (!gs[g].params || !gs[g].x) { set_error("backbone_forward: group %d has null params/x", g); return 1; }
-    if (at && !gs[g].params_lp) { set_error("backbone_forward: bf16 mode needs params_lp (group %d)", g); return 1; }
+    if (at && !gs[g].params_lp) { set_error("backbone_forward: the 16-bit modes need params_lp (group %d)", g); return 1; }
     if (gs[g].slot >= MAXG) { set_error("backbone_forward: bad slot"); return 1; }
   }
   const int64_t M = p.M, MP = p.MP;
@@ -252,7 +253,7 @@ static int backbone_forward_impl(const v2s_group_t* gs, int G, int B, int mode, 
     d.a_rs = KPE; d.a_cs = 1; d.b_rs = 1; d.b_cs = KPE;
     d.ldc = D;
     const float* pp[MAXG]; const float* tok[MAXG];
-    const bool two_pass = at == 1 && tc_enabled();   // tensor-core GEMM into patch rows, then assemble tokens
+    const bool two_pass = at != AT_F32 && tc_enabled();   // tensor-core GEMM into patch rows, then assemble tokens
     d.epi = two_pass ? EPI_STORE : EPI_PATCH;
     for (int g = 0; g < G; ++g) {
       x_cur[g] = reinterpret_cast<float*>(saved(g) ? sb(g, p.s_x[0]) : fb(g, p.f_xa));
@@ -273,10 +274,10 @@ static int backbone_forward_impl(const v2s_group_t* gs, int G, int B, int mode, 
   // ---- 12 pre-LN blocks ----
   // On the tensor-core path every LayerNorm except the first is fused into the epilogue of the GEMM that
   // produces its input row (attention projection → LN2, fc2 → LN1 of the next block): V2S_NO_LNFUSE=1 disables.
-  const bool ln_fuse = at == 1 && tc_enabled() && !getenv("V2S_NO_LNFUSE");
+  const bool ln_fuse = at != AT_F32 && tc_enabled() && !getenv("V2S_NO_LNFUSE");
   // fc1 -> GELU -> fc2 chained on chip (mlp_tc.cu): V2S_NO_MLPFUSE=1 falls back to the two separate GEMMs
   const bool mlp_fuse = ln_fuse && !getenv("V2S_NO_MLPFUSE");
-  const int lp_f16 = 0;
+  const int lp_f16 = at == AT_F16 ? 1 : 0;
   bool ln1_done = false;
   for (int l = 0; l < NL; ++l) {
     const int64_t lo = layer_off(l);
@@ -456,7 +457,7 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
   // dW[N_out, K_in] += dY[M, N_out]^T * X[M, K_in]   (token dimension is the reduction)
   // bias_goff >= 0: also accumulate the bias gradient (column sums of dY) — inside the tensor-core wgrad
   // kernel (extra N=16 MMA against a ones tile), or with the column-sum kernel on the SIMT path
-  const bool tc = at == 1 && tc_enabled();
+  const bool tc = at != AT_F32 && tc_enabled();
   const bool mlp_fuse = tc && !getenv("V2S_NO_MLPFUSE") && !getenv("V2S_NO_LNFUSE");
   auto wgrad = [&](void* const* dy, int n_out, void* const* x, int k_in, int64_t goff, bool remap,
                    int64_t bias_goff = -1) -> int {
@@ -517,7 +518,7 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
     if (mlp_fuse) {
       // du = (dx W2) * gelu'(u) and d xn2 = du W1 chained on chip (du is still written once: dW1 needs it)
       MlpDesc d = make_mlp_desc();
-      d.mode = MLP_BWD; d.M = (int)M; d.groups = G; d.lp_f16 = 0; d.late_wait = (l != NL - 1 && !getenv("V2S_NO_LATE_WAIT")) ? 1 : 0;
+      d.mode = MLP_BWD; d.M = (int)M; d.groups = G; d.lp_f16 = at == AT_F16 ? 1 : 0; d.late_wait = (l != NL - 1 && !getenv("V2S_NO_LATE_WAIT")) ? 1 : 0;
       for (int g = 0; g < G; ++g) {
         d.a[g] = dxlp[g]; d.w1[g] = weight_ptr(gs[g], at, lo + L_W1); d.w2[g] = weight_ptr(gs[g], at, lo + L_W2);
         d.u[g] = u[g]; d.h[g] = big[g]; d.out[g] = tmp[g];
@@ -574,7 +575,7 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
     const float* cdx[MAXG]; float* gr[MAXG]; void* pt[MAXG];
     for (int g = 0; g < G; ++g) { cdx[g] = dx[g]; gr[g] = gs[g].grads; pt[g] = sb(g, p.s_patches); }
     V2S_TRY(launch_embed_bwd(cdx, gr, G, B, st));
-    if (at == 1 && tc_enabled()) {          // compact the patch rows, then the ordinary tensor-core wgrad
+    if (tc) {          // compact the patch rows, then the ordinary tensor-core wgrad
       const void* src[MAXG];
       for (int g = 0; g < G; ++g) src[g] = dxlp[g];
       V2S_TRY(launch_gather_patch_rows(src, tmp, G, B, at, st));
@@ -707,12 +708,12 @@ static int heads_backward_impl(const float* hp, float* hg, const float* fo, cons
 
 static int heads_impl(const float* hp, float* hg, const float* fo, const float* ft, const float* mo, const float* mt,
                       float* dfo, float* pred_out, float* tgt_out, float* loss, int B, int accum, float grad_scale,
-                      int with_backward, void* ws, int64_t ws_bytes, cudaStream_t st) {
+                      int with_backward, void* ws, int64_t ws_bytes, cudaStream_t st, const float* grad_scale_dev = nullptr) {
   if (!loss) { set_error("heads: null loss"); return 1; }
   V2S_TRY(heads_forward_impl(hp, fo, ft, mo, mt, pred_out, tgt_out, B, ws, ws_bytes, st));
   HeadsBufs hb;
   V2S_TRY(heads_bufs(ws, ws_bytes, B, &hb));
-  V2S_TRY(launch_cosine_loss(hb.pr, hb.zt, loss, with_backward ? hb.dp : nullptr, B, accum, grad_scale, st));
+  V2S_TRY(launch_cosine_loss(hb.pr, hb.zt, loss, with_backward ? hb.dp : nullptr, B, accum, grad_scale, st, grad_scale_dev));
   if (!with_backward) return 0;
   return heads_backward_impl(hp, hg, fo, mo, nullptr, dfo, B, ws, ws_bytes, st);
 }
@@ -800,6 +801,17 @@ int v2s_heads_loss_fwd_bwd(const float* head_params, float* head_grads, const fl
                     workspace_bytes, (cudaStream_t)stream);
 }
 
+int v2s_heads_loss_fwd_bwd_amp(const float* head_params, float* head_grads, const float* feat_online,
+                               const float* feat_target, const float* mask_online, const float* mask_target,
+                               float* dfeat_online, float* pred, float* target_proj, float* loss, int batch,
+                               int accumulation_steps, const float* grad_scale_dev, int with_backward, void* workspace,
+                               int64_t workspace_bytes, void* stream) {
+  if (batch < 1 || accumulation_steps < 1) { set_error("heads: bad batch/accumulation_steps"); return 1; }
+  return heads_impl(head_params, head_grads, feat_online, feat_target, mask_online, mask_target, dfeat_online, pred,
+                    target_proj, loss, batch, accumulation_steps, 1.0f, with_backward, workspace, workspace_bytes,
+                    (cudaStream_t)stream, grad_scale_dev);
+}
+
 int v2s_heads_forward(const float* head_params, const float* feat_online, const float* feat_target,
                       const float* mask_online, const float* mask_target, float* pred, float* target_proj, int batch,
                       void* workspace, int64_t workspace_bytes, void* stream) {
@@ -840,10 +852,49 @@ int v2s_adam_step(const v2s_range_t* ranges, int n_ranges, int64_t step, double 
   return launch_adam(ranges, n_ranges, step, lr, beta1, beta2, eps, weight_decay, grad_scale, (cudaStream_t)stream);
 }
 
+static int check_ranges(const v2s_range_t* ranges, int n_ranges) {
+  for (int i = 0; i < n_ranges; ++i)
+    if ((reinterpret_cast<uintptr_t>(ranges[i].params) | reinterpret_cast<uintptr_t>(ranges[i].grads) |
+         reinterpret_cast<uintptr_t>(ranges[i].exp_avg) | reinterpret_cast<uintptr_t>(ranges[i].exp_avg_sq)) & 15) {
+      set_error("adam: range %d is not 16-byte aligned", i);
+      return 1;
+    }
+  return 0;
+}
+
+int v2s_adam_step_lp(const v2s_range_t* ranges, int n_ranges, int64_t step, double lr, double beta1, double beta2,
+                     double eps, double weight_decay, double grad_scale, int lp_format, void* stream) {
+  if (!ranges || step < 1) { set_error("adam: bad argument"); return 1; }
+  V2S_TRY(check_ranges(ranges, n_ranges));
+  return launch_adam(ranges, n_ranges, step, lr, beta1, beta2, eps, weight_decay, grad_scale, (cudaStream_t)stream,
+                     lp_format == V2S_LP_FP16);
+}
+
+int v2s_adam_step_amp(const v2s_range_t* ranges, int n_ranges, float* state8, double lr, double beta1, double beta2,
+                      double eps, double weight_decay, double grad_multiplier, const float* grad_scale_dev,
+                      const float* found_inf_dev, int lp_format, int advance_step, void* stream) {
+  if (!ranges || !state8) { set_error("adam_amp: bad argument"); return 1; }
+  V2S_TRY(check_ranges(ranges, n_ranges));
+  return launch_adam_amp(ranges, n_ranges, state8, lr, beta1, beta2, eps, weight_decay, grad_multiplier, grad_scale_dev,
+                         found_inf_dev, lp_format == V2S_LP_FP16, advance_step, (cudaStream_t)stream);
+}
+
 int v2s_ema_update(float* const* targets, const float* const* onlines, void* const* targets_lp, int n_pairs,
                    int64_t numel, double momentum, void* stream) {
   if (!targets || !onlines) { set_error("ema: null"); return 1; }
   return launch_ema(targets, onlines, targets_lp, n_pairs, numel, momentum, (cudaStream_t)stream);
+}
+
+int v2s_ema_update_lp(float* const* targets, const float* const* onlines, void* const* targets_lp, int n_pairs,
+                      int64_t numel, double momentum, int lp_format, void* stream) {
+  if (!targets || !onlines) { set_error("ema: null"); return 1; }
+  return launch_ema(targets, onlines, targets_lp, n_pairs, numel, momentum, (cudaStream_t)stream, lp_format == V2S_LP_FP16);
+}
+
+int v2s_cast_lp(const float* src, void* dst, int64_t numel, int lp_format, void* stream) {
+  if (!src || !dst || numel < 0) { set_error("cast: bad argument"); return 1; }
+  if (numel == 0) return 0;
+  return launch_cast_bf16(src, dst, numel, (cudaStream_t)stream, lp_format == V2S_LP_FP16);
 }
 
 int v2s_cast_bf16(const float* src, void* dst, int64_t numel, void* stream) {
@@ -905,13 +956,15 @@ int v2s_test_attention(int which, const void* qkv, void* ctx, float* lse, const 
   cudaStream_t st = (cudaStream_t)stream;
   const void* cq[1] = {qkv}; void* cc[1] = {ctx}; float* ls[1] = {lse};
   const void* cctx[1] = {ctx}; const float* cls[1] = {lse}; const void* cd[1] = {dctx}; void* dq[1] = {dqkv};
+  // variant: bit 0 = SIMT reference kernels, bit 1 = fp16 instead of bf16 tensors
+  const int f16 = (variant & 2) ? 1 : 0, at = f16 ? AT_F16 : AT_BF16;
   if (which == 0) {
-    if (variant == 1) return launch_attn_fwd_simt(cq, cc, ls, 1, batch, 1, st);
-    return launch_attn_fwd_tc(cq, cc, ls, 1, batch, st);
+    if (variant & 1) return launch_attn_fwd_simt(cq, cc, ls, 1, batch, at, st);
+    return launch_attn_fwd_tc(cq, cc, ls, 1, batch, st, f16);
   }
   if (which == 1) {
-    if (variant == 1) return launch_attn_bwd_simt(cq, cctx, cls, cd, dq, 1, batch, 1, st);
-    return launch_attn_bwd_tc(cq, cctx, cls, cd, dq, 1, batch, st);
+    if (variant & 1) return launch_attn_bwd_simt(cq, cctx, cls, cd, dq, 1, batch, at, st);
+    return launch_attn_bwd_tc(cq, cctx, cls, cd, dq, 1, batch, st, f16);
   }
   set_error("v2s_test_attention: which must be 0 or 1");
   return 1;

@@ -184,6 +184,8 @@ int launch_gemm_simt(const GemmDesc& d, int ta, int tb, int to, cudaStream_t str
   if (ta == 0 && tb == 0 && to == 0) return launch_t<float, float, float>(d, stream);
   if (ta == 1 && tb == 1 && to == 1) return launch_t<bf16, bf16, bf16>(d, stream);
   if (ta == 1 && tb == 1 && to == 0) return launch_t<bf16, bf16, float>(d, stream);
+  if (ta == 2 && tb == 2 && to == 2) return launch_t<f16, f16, f16>(d, stream);
+  if (ta == 2 && tb == 2 && to == 0) return launch_t<f16, f16, float>(d, stream);
   set_error("gemm_simt: unsupported type combination %d %d %d", ta, tb, to);
   return 1;
 }

@@ -47,6 +47,7 @@ struct GemmDesc {
   // back in the stream and its output is not touched by the kernel launched just before it -> start without
   // draining that kernel, wait for it just before exiting (see gemm_tc.cu)
   int late_wait;
+  int lp_f16;       // tensor-core path: the 16-bit operands / outputs are fp16 (1) instead of bf16 (0)
 };
 
 inline GemmDesc make_gemm_desc() {
@@ -58,7 +59,7 @@ inline GemmDesc make_gemm_desc() {
   return d;
 }
 
-// type tags: 0 = fp32, 1 = bf16
+// type tags: 0 = fp32, 1 = bf16, 2 = fp16
 int launch_gemm_simt(const GemmDesc& d, int ta, int tb, int to, cudaStream_t stream);
 
 }  // namespace v2s

@@ -84,14 +84,10 @@ struct alignas(64) TcParams {
   int dbg_flags;      // experiments (V2S_GEMM_DEBUG=<n>): 2 skip TMEM loads, 4 skip epilogue math + stores, 8 skip the u store, 16 skip TMA stores only
 };
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
 
 // DBG: the instrumented build of the kernel (per-role cycle counters, ablation switches), launched only when
 // V2S_GEMM_DEBUG is set: even predicated-off clock reads cost issue slots in the issue-bound epilogues.
-template <int EPI, bool OUT_BF16, bool DBG>
+template <int EPI, bool OUT_BF16, bool DBG, typename LP>
 __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -132,9 +128,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     ptx::tmem_relinquish();
   }
   if (EPI == T_ACCUM && warp == 3) {
-    // bf16 1.0 = 0x3F80; the swizzle only permutes 16-byte chunks inside a row, so a constant row is layout-proof
+    // a row of 16-bit 1.0 values; the swizzle only permutes 16-byte chunks inside a row, so a constant row is layout-proof
     for (int i = lane; i < 2048 / 4; i += 32)
-      reinterpret_cast<uint32_t*>(ones_tile)[i] = (i < 32) ? 0x3F803F80u : 0u;
+      reinterpret_cast<uint32_t*>(ones_tile)[i] = (i < 32) ? LP::kOnePair : 0u;
     ptx::fence_proxy_async();
   }
   // Programmatic dependent launch.  Every kernel of this library waits for its predecessor and only THEN
@@ -231,7 +227,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     if (DBG && blockIdx.x == 0 && lane == 0) { p.dbg[0] = prod_wait; p.dbg[1] = clock64() - prod_t0; }
   } else if (warp == 1) {
     // ================= MMA issuer (whole warp walks the loop; one elected lane issues) =================
-    const uint32_t idesc = ptx::make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+    const uint32_t idesc = make_idesc_lp(LP::kIdescFmt, BM, BN, p.a_mn, p.b_mn);
     // descriptor low words per smem slot; a K-step of 16 adds 32 B (K-major) or 2048 B (MN-major), >> 4
     const uint32_t smem_base = ptx::smem_u32(smem);
     const uint32_t a_step = p.a_mn ? (2048u >> 4) : (32u >> 4), b_step = p.b_mn ? (2048u >> 4) : (32u >> 4);
@@ -239,7 +235,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     const uint32_t a_slot0 = p.b_stationary ? p.kb_total * B_STAGE_BYTES : 0, a_slot_stride = p.b_stationary ? A_STAGE_BYTES : STAGE_BYTES;
     const uint32_t b_slot0 = p.b_stationary ? 0 : A_STAGE_BYTES, b_slot_stride = p.b_stationary ? B_STAGE_BYTES : STAGE_BYTES;
     const uint32_t a_lo0 = ptx::desc_lo(smem_base + a_slot0, a_lbo), b_lo0 = ptx::desc_lo(smem_base + b_slot0, b_lbo);
-    const uint32_t idesc_rs = ptx::make_idesc_bf16(BM, 16, p.a_mn, 0);
+    const uint32_t idesc_rs = make_idesc_lp(LP::kIdescFmt, BM, 16, p.a_mn, 0);
     const uint32_t ones_lo = ptx::desc_lo(ptx::smem_u32(ones_tile), 16);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
@@ -482,9 +478,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
               uint32_t o[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const __nv_bfloat162 u2 = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
-                o[e] = pack_bf16(v[8 * j + 2 * e] * gelu_grad_fast(__low2float(u2)),
-                                 v[8 * j + 2 * e + 1] * gelu_grad_fast(__high2float(u2)));
+                o[e] = LP::pack(v[8 * j + 2 * e] * gelu_grad_fast(LP::lo(w[e])),
+                                v[8 * j + 2 * e + 1] * gelu_grad_fast(LP::hi(w[e])));
               }
               ptx::sts128(slot, o[0], o[1], o[2], o[3]);
             }
@@ -495,8 +490,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
                 uint4 o;
-                o.x = pack_bf16(v[8 * j], v[8 * j + 1]); o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-                o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                o.x = LP::pack(v[8 * j], v[8 * j + 1]); o.y = LP::pack(v[8 * j + 2], v[8 * j + 3]);
+                o.z = LP::pack(v[8 * j + 4], v[8 * j + 5]); o.w = LP::pack(v[8 * j + 6], v[8 * j + 7]);
                 ptx::sts128(stg_s + 8192 + row * 64 + (((hf * 2 + j) ^ ((row >> 1) & 3)) << 4), o.x, o.y, o.z, o.w);
               }
             }
@@ -506,8 +501,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             uint4 o;
-            o.x = pack_bf16(v[8 * j], v[8 * j + 1]); o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-            o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+            o.x = LP::pack(v[8 * j], v[8 * j + 1]); o.y = LP::pack(v[8 * j + 2], v[8 * j + 3]);
+            o.z = LP::pack(v[8 * j + 4], v[8 * j + 5]); o.w = LP::pack(v[8 * j + 6], v[8 * j + 7]);
             ptx::sts128(stg_s + row * 64 + (((hf * 2 + j) ^ ((row >> 1) & 3)) << 4), o.x, o.y, o.z, o.w);
           }
         } else {
@@ -559,8 +554,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
 #pragma unroll
           for (int j = 0; j < 2; ++j) {             // bf16 chunk: 64-byte rows, SWIZZLE_64B, first 8 KB of the buffer
             uint4 o;
-            o.x = pack_bf16(v[8 * j], v[8 * j + 1]); o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-            o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+            o.x = LP::pack(v[8 * j], v[8 * j + 1]); o.y = LP::pack(v[8 * j + 2], v[8 * j + 3]);
+            o.z = LP::pack(v[8 * j + 4], v[8 * j + 5]); o.w = LP::pack(v[8 * j + 6], v[8 * j + 7]);
             ptx::sts128(stg_s + row * 64 + (((hf * 2 + j) ^ ((row >> 1) & 3)) << 4), o.x, o.y, o.z, o.w);
           }
           publish_slot(cnt);
@@ -689,11 +684,11 @@ bool tc_enabled() { return g_encode != nullptr && !g_disabled; }
 
 namespace {
 
-template <int EPI, bool OUT_BF16, bool DBG>
+template <int EPI, bool OUT_BF16, bool DBG, typename LP>
 int launch_kernel_impl(TcParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    V2S_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI, OUT_BF16, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    V2S_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI, OUT_BF16, DBG, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set = true;
   }
   // split the 227 KB between the operand ring and the epilogue staging ring of this variant
@@ -728,14 +723,16 @@ int launch_kernel_impl(TcParams& p, cudaStream_t stream) {
   const int SMEM_TOTAL = p.bar_off + SMEM_BAR_BYTES + 1024;
   int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   if (p.b_stationary) grid = p.groups * p.tiles_n * p.ctas_per_combo;
-  V2S_CUDA_OK(launch_pdl(gemm_tc_kernel<EPI, OUT_BF16, DBG>, dim3(grid), dim3(N_THREADS), (size_t)SMEM_TOTAL, stream, p));
+  V2S_CUDA_OK(launch_pdl(gemm_tc_kernel<EPI, OUT_BF16, DBG, LP>, dim3(grid), dim3(N_THREADS), (size_t)SMEM_TOTAL, stream, p));
   V2S_LAUNCH_CHECK();
   return 0;
 }
 
 template <int EPI, bool OUT_BF16>
-int launch_kernel(TcParams& p, cudaStream_t stream) {
-  return p.dbg ? launch_kernel_impl<EPI, OUT_BF16, true>(p, stream) : launch_kernel_impl<EPI, OUT_BF16, false>(p, stream);
+int launch_kernel(TcParams& p, int lp_f16, cudaStream_t stream) {
+  if (lp_f16)
+    return p.dbg ? launch_kernel_impl<EPI, OUT_BF16, true, LpF16>(p, stream) : launch_kernel_impl<EPI, OUT_BF16, false, LpF16>(p, stream);
+  return p.dbg ? launch_kernel_impl<EPI, OUT_BF16, true, LpBf16>(p, stream) : launch_kernel_impl<EPI, OUT_BF16, false, LpBf16>(p, stream);
 }
 
 }  // namespace
@@ -783,7 +780,9 @@ int gemm_tc_error_flag() {
 int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t stream, int* handled) {
   *handled = 0;
   if (g_disabled || !g_encode) return 0;
-  if (ta != 1 || tb != 1) return 0;                       // fp32 check mode stays on the SIMT kernel
+  if (ta == 0 || ta != tb) return 0;                      // fp32 check mode stays on the SIMT kernel
+  if (to != 0 && to != ta) return 0;
+  const int lp_f16 = (ta == AT_F16) ? 1 : 0;
   if (d.a_remap || d.b_remap) return 0;
   int epi;
   switch (d.epi) {
@@ -795,7 +794,7 @@ int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t strea
     default: return 0;
   }
   if (d.alpha != 1.0f) return 0;
-  const bool out_bf16 = (to == 1);
+  const bool out_bf16 = (to != 0);                        // 16-bit output (bf16 or fp16, as the operands)
   if ((epi == T_RESID || epi == T_ACCUM) && out_bf16) return 0;
   if ((epi == T_GELU || epi == T_DGELU) && !out_bf16) return 0;
   int a_mn, b_mn;
@@ -861,11 +860,11 @@ int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t strea
   }
   int rc;
   switch (epi) {
-    case T_STORE: rc = out_bf16 ? launch_kernel<T_STORE, true>(p, stream) : launch_kernel<T_STORE, false>(p, stream); break;
-    case T_RESID: rc = launch_kernel<T_RESID, false>(p, stream); break;
-    case T_GELU: rc = launch_kernel<T_GELU, true>(p, stream); break;
-    case T_DGELU: rc = launch_kernel<T_DGELU, true>(p, stream); break;
-    default: rc = launch_kernel<T_ACCUM, false>(p, stream); break;
+    case T_STORE: rc = out_bf16 ? launch_kernel<T_STORE, true>(p, lp_f16, stream) : launch_kernel<T_STORE, false>(p, lp_f16, stream); break;
+    case T_RESID: rc = launch_kernel<T_RESID, false>(p, lp_f16, stream); break;
+    case T_GELU: rc = launch_kernel<T_GELU, true>(p, lp_f16, stream); break;
+    case T_DGELU: rc = launch_kernel<T_DGELU, true>(p, lp_f16, stream); break;
+    default: rc = launch_kernel<T_ACCUM, false>(p, lp_f16, stream); break;
   }
   if (rc) return rc;
   *handled = 1;
@@ -893,9 +892,12 @@ int gemm_tc_test(int which, const void* a, const void* b, void* c, int m, int n,
     d.aux[0] = static_cast<const bf16*>(c) + (size_t)m * n;
   }
   else { set_error("gemm_tc_test: which must be 0..6"); return 1; }
-  if (variant == 1) return launch_gemm_simt(d, 1, 1, to, stream);
+  // variant: bit 0 = SIMT reference instead of the tensor-core path, bit 1 = fp16 instead of bf16 tensors
+  const int t16 = (variant & 2) ? AT_F16 : AT_BF16;
+  if (to) to = t16;
+  if (variant & 1) return launch_gemm_simt(d, t16, t16, to, stream);
   int handled = 0;
-  V2S_TRY(launch_gemm_tc(d, 1, 1, to, stream, &handled));
+  V2S_TRY(launch_gemm_tc(d, t16, t16, to, stream, &handled));
   if (!handled) { set_error("gemm_tc_test: shape not handled by the tensor-core path"); return 1; }
   return 0;
 }

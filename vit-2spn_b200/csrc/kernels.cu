@@ -104,12 +104,39 @@ template <> __device__ __forceinline__ void store4<bf16>(bf16* dst, float a, flo
   u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
   *reinterpret_cast<uint2*>(dst) = u;
 }
+template <> __device__ __forceinline__ void store4<f16>(f16* dst, float a, float b, float c, float d) {
+  __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(dst) = u;
+}
 template <typename T> __device__ __forceinline__ float4 load4(const T* src);
 template <> __device__ __forceinline__ float4 load4<float>(const float* src) { return *reinterpret_cast<const float4*>(src); }
 template <> __device__ __forceinline__ float4 load4<bf16>(const bf16* src) {
   const uint2 u = *reinterpret_cast<const uint2*>(src);
   const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
   return make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+}
+
+template <> __device__ __forceinline__ float4 load4<f16>(const f16* src) {
+  const uint2 u = *reinterpret_cast<const uint2*>(src);
+  const __half2 lo = *reinterpret_cast<const __half2*>(&u.x), hi = *reinterpret_cast<const __half2*>(&u.y);
+  return make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+}
+
+// runs `...` with T = float / bf16 / f16 for the activation type tag 0 / 1 / 2
+#define V2S_DISPATCH_AT(at, ...)                            \
+  switch (at) {                                             \
+    case AT_F32: { using T = float; __VA_ARGS__; } break;   \
+    case AT_BF16: { using T = bf16; __VA_ARGS__; } break;   \
+    default: { using T = f16; __VA_ARGS__; } break;         \
+  }
+
+// packs two floats into the 16-bit shadow format of a flat parameter buffer (bf16, or fp16 when f16 != 0)
+__device__ __forceinline__ uint32_t pack_lp(float a, float b, int f16) {
+  if (f16) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
 }
 
 template <typename T>
@@ -467,7 +494,7 @@ __global__ void __launch_bounds__(256) attn_bwd_simt_kernel(G4<const T*> qkv, G4
 __global__ void __launch_bounds__(256) cosine_loss_kernel(const float* __restrict__ p,
                                                           const float* __restrict__ z, float* loss,
                                                           float* dp, int B, float inv_count,
-                                                          float grad_scale) {
+                                                          float grad_scale, const float* __restrict__ grad_scale_dev) {
   __shared__ float part[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float eps = 1e-8f;
@@ -487,7 +514,7 @@ __global__ void __launch_bounds__(256) cosine_loss_kernel(const float* __restric
       // d cos / d p = z/(pc*zc) - [pn > eps] * cos * p / pn^2
       const float a = 1.0f / (pc * zc);
       const float c = (pn > eps) ? cosv / pp : 0.f;
-      const float s = -inv_count * grad_scale;
+      const float s = -inv_count * grad_scale * (grad_scale_dev ? __ldg(grad_scale_dev) : 1.0f);
       float4 o;
       o.x = s * (zv.x * a - c * pv.x); o.y = s * (zv.y * a - c * pv.y);
       o.z = s * (zv.z * a - c * pv.z); o.w = s * (zv.w * a - c * pv.w);
@@ -511,16 +538,37 @@ struct AdamRanges {
   int n;
 };
 
-__global__ void __launch_bounds__(256) adam_kernel(AdamRanges rs, float step_size, float bc2_sqrt,
-                                                   float om_b1, float b2, float om_b2, float eps, float wd,
-                                                   float grad_scale) {
+struct AdamHyper { float step_size, bc2_sqrt, skip, gmul; };
+
+// device-resident optimizer-step state (v2s_adam_step_amp): state8[0] = optimizer steps taken, [1..4] = AdamHyper of the
+// step being applied.  One thread; double-precision bias corrections like the host path.
+__global__ void adam_prologue_kernel(float* state8, double lr, double b1, double b2, double grad_multiplier,
+                                     const float* grad_scale_dev, const float* found_inf_dev) {
+  const bool skip = found_inf_dev != nullptr && *found_inf_dev != 0.f;
+  float step = state8[0];
+  if (!skip) step += 1.0f;
+  state8[0] = step;
+  const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
+  state8[1] = skip ? 0.f : (float)(lr / bc1);
+  state8[2] = skip ? 1.f : (float)sqrt(bc2);
+  state8[3] = skip ? 1.f : 0.f;
+  state8[4] = (float)(grad_multiplier / (grad_scale_dev ? (double)*grad_scale_dev : 1.0));
+}
+
+template <bool DEV>
+__global__ void __launch_bounds__(256) adam_kernel(AdamRanges rs, AdamHyper hv, const float* __restrict__ state8, float om_b1,
+                                                   float b2, float om_b2, float eps, float wd, int lp_f16) {
+  AdamHyper hy = hv;
+  if (DEV) { hy.step_size = state8[1]; hy.bc2_sqrt = state8[2]; hy.skip = state8[3]; hy.gmul = state8[4]; }
+  if (hy.skip != 0.f) return;                 // GradScaler found an inf / nan: the step changes nothing (ref:216-217)
+  const float step_size = hy.step_size, bc2_sqrt = hy.bc2_sqrt, grad_scale = hy.gmul;
   const v2s_range_t r = rs.r[blockIdx.y];
   const int64_t n4 = r.numel / 4;
   float4* p4 = reinterpret_cast<float4*>(r.params);
   const float4* g4 = reinterpret_cast<const float4*>(r.grads);
   float4* m4 = reinterpret_cast<float4*>(r.exp_avg);
   float4* v4 = reinterpret_cast<float4*>(r.exp_avg_sq);
-  bf16* lp = static_cast<bf16*>(r.params_lp);
+  uint16_t* lp = static_cast<uint16_t*>(r.params_lp);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 p = p4[i], g = g4[i], m = m4[i], v = v4[i];
     float* pp = &p.x; float* gg = &g.x; float* mm = &m.x; float* vv = &v.x;
@@ -535,9 +583,8 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamRanges rs, float step_siz
     }
     p4[i] = p; m4[i] = m; v4[i] = v;
     if (lp) {
-      __nv_bfloat162 a = __floats2bfloat162_rn(p.x, p.y), b = __floats2bfloat162_rn(p.z, p.w);
       uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+      u.x = pack_lp(p.x, p.y, lp_f16); u.y = pack_lp(p.z, p.w, lp_f16);
       reinterpret_cast<uint2*>(lp)[i] = u;
     }
   }
@@ -552,21 +599,21 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamRanges rs, float step_siz
     const float denom = sqrtf(v) / bc2_sqrt + eps;
     const float pn = r.params[i] - step_size * (m / denom);
     r.params[i] = pn; r.exp_avg[i] = m; r.exp_avg_sq[i] = v;
-    if (lp) lp[i] = __float2bfloat16_rn(pn);
+    if (lp) lp[i] = (uint16_t)(pack_lp(pn, 0.f, lp_f16) & 0xffffu);
   }
 }
 
 struct EmaPairs {
   float* t[4];
   const float* o[4];
-  bf16* lp[4];
+  uint16_t* lp[4];
 };
 
 // target = m*target + (1-m)*online, rounded exactly as torch's two multiplies + add (ref:164)
-__global__ void __launch_bounds__(256) ema_kernel(EmaPairs pr, int64_t numel, float m, float om) {
+__global__ void __launch_bounds__(256) ema_kernel(EmaPairs pr, int64_t numel, float m, float om, int lp_f16) {
   float4* t4 = reinterpret_cast<float4*>(pr.t[blockIdx.y]);
   const float4* o4 = reinterpret_cast<const float4*>(pr.o[blockIdx.y]);
-  bf16* lp = pr.lp[blockIdx.y];
+  uint16_t* lp = pr.lp[blockIdx.y];
   const int64_t n4 = numel / 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 t = t4[i];
@@ -577,24 +624,23 @@ __global__ void __launch_bounds__(256) ema_kernel(EmaPairs pr, int64_t numel, fl
     t.w = __fadd_rn(__fmul_rn(m, t.w), __fmul_rn(om, o.w));
     t4[i] = t;
     if (lp) {
-      __nv_bfloat162 a = __floats2bfloat162_rn(t.x, t.y), b = __floats2bfloat162_rn(t.z, t.w);
       uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+      u.x = pack_lp(t.x, t.y, lp_f16); u.y = pack_lp(t.z, t.w, lp_f16);
       reinterpret_cast<uint2*>(lp)[i] = u;
     }
   }
 }
 
-__global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n) {
+__global__ void cast_lp_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int64_t n, int lp_f16) {
   const int64_t n4 = n / 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(src)[i];
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
     uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    u.x = pack_lp(v.x, v.y, lp_f16); u.y = pack_lp(v.z, v.w, lp_f16);
     reinterpret_cast<uint2*>(dst)[i] = u;
   }
-  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[n4 * 4 + threadIdx.x] = __float2bfloat16_rn(src[n4 * 4 + threadIdx.x]);
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3))
+    dst[n4 * 4 + threadIdx.x] = (uint16_t)(pack_lp(src[n4 * 4 + threadIdx.x], 0.f, lp_f16) & 0xffffu);
 }
 
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
@@ -648,8 +694,7 @@ inline int grid_for(int64_t n, int threads, int max_blocks = 148 * 8) {
 // ------------------------------------------------------------------------------------------
 int launch_im2col(const float* const* x, void* const* out, int groups, int B, int at, cudaStream_t s) {
   dim3 grid(grid_for((int64_t)B * NP * (KPE / 4), 256, 148 * 16), groups);
-  if (at == 0) im2col_kernel<float><<<grid, 256, 0, s>>>(pack4<const float*>(x, groups), pack4<float*>(out, groups), B);
-  else im2col_kernel<bf16><<<grid, 256, 0, s>>>(pack4<const float*>(x, groups), pack4<bf16*>(out, groups), B);
+  V2S_DISPATCH_AT(at, im2col_kernel<T><<<grid, 256, 0, s>>>(pack4<const float*>(x, groups), pack4<T*>(out, groups), B));
   V2S_LAUNCH_CHECK();
   return 0;
 }
@@ -670,8 +715,7 @@ int launch_assemble_tokens(const float* const* params, const float* const* tok, 
 
 int launch_gather_patch_rows(const void* const* src, void* const* dst, int groups, int B, int at, cudaStream_t s) {
   dim3 grid(8, B, groups);
-  if (at == 0) gather_patch_rows_kernel<float><<<grid, 256, 0, s>>>(pack4<const float*>(src, groups), pack4<float*>(dst, groups));
-  else gather_patch_rows_kernel<bf16><<<grid, 256, 0, s>>>(pack4<const bf16*>(src, groups), pack4<bf16*>(dst, groups));
+  V2S_DISPATCH_AT(at, gather_patch_rows_kernel<T><<<grid, 256, 0, s>>>(pack4<const T*>(src, groups), pack4<T*>(dst, groups)));
   V2S_LAUNCH_CHECK();
   return 0;
 }
@@ -688,8 +732,7 @@ int launch_ln_fwd(const float* const* x, const float* const* gamma, const float*
   int bx = (M + 15) / 16;
   if (bx > 148 * 6) bx = 148 * 6;
   dim3 grid(bx, groups);
-  if (at == 0) V2S_CUDA_OK(launch_pdl(ln_fwd_kernel<float>, grid, dim3(256), 0, s, p));
-  else V2S_CUDA_OK(launch_pdl(ln_fwd_kernel<bf16>, grid, dim3(256), 0, s, p));
+  V2S_DISPATCH_AT(at, V2S_CUDA_OK(launch_pdl(ln_fwd_kernel<T>, grid, dim3(256), 0, s, p)));
   V2S_LAUNCH_CHECK();
   return 0;
 }
@@ -708,8 +751,7 @@ int launch_ln_bwd(const void* const* dy, const float* const* x, const float* con
   int bx = (M + 15) / 16;
   if (bx > 148 * 4) bx = 148 * 4;
   dim3 grid(bx, groups);
-  if (at == 0) V2S_CUDA_OK(launch_pdl(ln_bwd_kernel<float>, grid, dim3(256), 0, s, p));
-  else V2S_CUDA_OK(launch_pdl(ln_bwd_kernel<bf16>, grid, dim3(256), 0, s, p));
+  V2S_DISPATCH_AT(at, V2S_CUDA_OK(launch_pdl(ln_bwd_kernel<T>, grid, dim3(256), 0, s, p)));
   V2S_LAUNCH_CHECK();
   return 0;
 }
@@ -727,8 +769,7 @@ int launch_colsum(const void* const* dy, float* const* db, int groups, int M, in
   if (bx < 1) bx = 1;
   p.rows_per_block = (M + bx - 1) / bx;
   dim3 grid(bx, groups);
-  if (t == 0) colsum_kernel<float><<<grid, 256, 0, s>>>(p);
-  else colsum_kernel<bf16><<<grid, 256, 0, s>>>(p);
+  V2S_DISPATCH_AT(t, colsum_kernel<T><<<grid, 256, 0, s>>>(p));
   V2S_LAUNCH_CHECK();
   return 0;
 }
@@ -753,12 +794,9 @@ int launch_pool_bwd(const float* const* dfeat, const int64_t* dfeat_stride, cons
       return 1;
     }
   dim3 grid(8, B, groups);
-  if (at == 0)
-    pool_bwd_kernel<float><<<grid, 256, 0, s>>>(pack4<const float*>(dfeat, groups), st, pack4<const float*>(dhidden, groups),
-                                              pack4<float*>(dx, groups), pack4<float*>(dx_lp, groups));
-  else
-    pool_bwd_kernel<bf16><<<grid, 256, 0, s>>>(pack4<const float*>(dfeat, groups), st, pack4<const float*>(dhidden, groups),
-                                             pack4<float*>(dx, groups), pack4<bf16*>(dx_lp, groups));
+  V2S_DISPATCH_AT(at, pool_bwd_kernel<T><<<grid, 256, 0, s>>>(pack4<const float*>(dfeat, groups), st,
+                                                             pack4<const float*>(dhidden, groups), pack4<float*>(dx, groups),
+                                                             pack4<T*>(dx_lp, groups)));
   V2S_LAUNCH_CHECK();
   return 0;
 }
@@ -773,15 +811,10 @@ int launch_attn_fwd_simt(const void* const* qkv, void* const* ctx, float* const*
                          cudaStream_t s) {
   const size_t smem = (size_t)(2 * NT * ASTR + 8 * 200 + 8 * DH) * sizeof(float);
   dim3 grid(NH, B, groups);
-  if (at == 0) {
-    V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_fwd_simt_kernel<float><<<grid, 256, smem, s>>>(pack4<const float*>(qkv, groups), pack4<float*>(ctx, groups),
-                                                        pack4<float*>(lse, groups));
-  } else {
-    V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_fwd_simt_kernel<bf16><<<grid, 256, smem, s>>>(pack4<const bf16*>(qkv, groups), pack4<bf16*>(ctx, groups),
-                                                       pack4<float*>(lse, groups));
-  }
+  V2S_DISPATCH_AT(at, {
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_fwd_simt_kernel<T><<<grid, 256, smem, s>>>(pack4<const T*>(qkv, groups), pack4<T*>(ctx, groups), pack4<float*>(lse, groups));
+  });
   V2S_LAUNCH_CHECK();
   return 0;
 }
@@ -790,69 +823,91 @@ int launch_attn_bwd_simt(const void* const* qkv, const void* const* ctx, const f
                          const void* const* dctx, void* const* dqkv, int groups, int B, int at, cudaStream_t s) {
   const size_t smem = (size_t)(4 * NT * ASTR + 2 * NT + 16 * 200) * sizeof(float);
   dim3 grid(NH, B, groups);
-  if (at == 0) {
-    V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_bwd_simt_kernel<float><<<grid, 256, smem, s>>>(pack4<const float*>(qkv, groups), pack4<const float*>(ctx, groups),
-                                                        pack4<const float*>(lse, groups), pack4<const float*>(dctx, groups),
-                                                        pack4<float*>(dqkv, groups));
-  } else {
-    V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_bwd_simt_kernel<bf16><<<grid, 256, smem, s>>>(pack4<const bf16*>(qkv, groups), pack4<const bf16*>(ctx, groups),
-                                                       pack4<const float*>(lse, groups), pack4<const bf16*>(dctx, groups),
-                                                       pack4<bf16*>(dqkv, groups));
-  }
+  V2S_DISPATCH_AT(at, {
+    V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_bwd_simt_kernel<T><<<grid, 256, smem, s>>>(pack4<const T*>(qkv, groups), pack4<const T*>(ctx, groups),
+                                                   pack4<const float*>(lse, groups), pack4<const T*>(dctx, groups),
+                                                   pack4<T*>(dqkv, groups));
+  });
   V2S_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_cosine_loss(const float* p, const float* z, float* loss, float* dp, int B, int accum, float grad_scale,
-                       cudaStream_t s) {
+                       cudaStream_t s, const float* grad_scale_dev) {
   const float inv_count = 1.0f / ((float)B * (float)accum);
-  cosine_loss_kernel<<<1, 256, 0, s>>>(p, z, loss, dp, B, inv_count, grad_scale);
+  cosine_loss_kernel<<<1, 256, 0, s>>>(p, z, loss, dp, B, inv_count, grad_scale, grad_scale_dev);
   V2S_LAUNCH_CHECK();
   return 0;
 }
 
-int launch_adam(const v2s_range_t* ranges, int n, int64_t step, double lr, double b1, double b2, double eps, double wd,
-                double grad_scale, cudaStream_t s) {
+namespace {
+int pack_ranges(const v2s_range_t* ranges, int n, AdamRanges* rs, int64_t* mx) {
   if (n < 1 || n > 4) { set_error("adam: 1..4 ranges"); return 1; }
-  AdamRanges rs;
-  int64_t mx = 0;
+  *mx = 0;
   for (int i = 0; i < 4; ++i) {
-    if (i < n) { rs.r[i] = ranges[i]; if (ranges[i].numel > mx) mx = ranges[i].numel; }
-    else memset(&rs.r[i], 0, sizeof(v2s_range_t));
+    if (i < n) { rs->r[i] = ranges[i]; if (ranges[i].numel > *mx) *mx = ranges[i].numel; }
+    else memset(&rs->r[i], 0, sizeof(v2s_range_t));
   }
-  rs.n = n;
+  rs->n = n;
+  return 0;
+}
+}  // namespace
+
+int launch_adam(const v2s_range_t* ranges, int n, int64_t step, double lr, double b1, double b2, double eps, double wd,
+                double grad_scale, cudaStream_t s, int lp_f16) {
+  AdamRanges rs;
+  int64_t mx;
+  V2S_TRY(pack_ranges(ranges, n, &rs, &mx));
   const double bc1 = 1.0 - pow(b1, (double)step);
   const double bc2 = 1.0 - pow(b2, (double)step);
-  const float step_size = (float)(lr / bc1);
-  const float bc2_sqrt = (float)sqrt(bc2);
+  AdamHyper hy;
+  hy.step_size = (float)(lr / bc1); hy.bc2_sqrt = (float)sqrt(bc2); hy.skip = 0.f; hy.gmul = (float)grad_scale;
   dim3 grid(grid_for(mx / 4 + 1, 256, 148 * 8), n);
-  adam_kernel<<<grid, 256, 0, s>>>(rs, step_size, bc2_sqrt, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2),
-                                   (float)eps, (float)wd, (float)grad_scale);
+  adam_kernel<false><<<grid, 256, 0, s>>>(rs, hy, nullptr, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), (float)eps,
+                                          (float)wd, lp_f16);
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_adam_amp(const v2s_range_t* ranges, int n, float* state8, double lr, double b1, double b2, double eps, double wd,
+                    double grad_multiplier, const float* grad_scale_dev, const float* found_inf_dev, int lp_f16, int advance,
+                    cudaStream_t s) {
+  AdamRanges rs;
+  int64_t mx;
+  V2S_TRY(pack_ranges(ranges, n, &rs, &mx));
+  if (advance) {
+    adam_prologue_kernel<<<1, 1, 0, s>>>(state8, lr, b1, b2, grad_multiplier, grad_scale_dev, found_inf_dev);
+    V2S_LAUNCH_CHECK();
+  }
+  AdamHyper hy;
+  memset(&hy, 0, sizeof(hy));
+  dim3 grid(grid_for(mx / 4 + 1, 256, 148 * 8), n);
+  adam_kernel<true><<<grid, 256, 0, s>>>(rs, hy, state8, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), (float)eps, (float)wd,
+                                         lp_f16);
   V2S_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_ema(float* const* tgt, const float* const* onl, void* const* tgt_lp, int n_pairs, int64_t numel,
-               double momentum, cudaStream_t s) {
+               double momentum, cudaStream_t s, int lp_f16) {
   if (n_pairs < 1 || n_pairs > 4) { set_error("ema: 1..4 pairs"); return 1; }
   if (numel % 4) { set_error("ema: numel must be a multiple of 4"); return 1; }
   EmaPairs pr;
   for (int i = 0; i < 4; ++i) {
     pr.t[i] = i < n_pairs ? tgt[i] : nullptr;
     pr.o[i] = i < n_pairs ? onl[i] : nullptr;
-    pr.lp[i] = (i < n_pairs && tgt_lp) ? static_cast<bf16*>(tgt_lp[i]) : nullptr;
+    pr.lp[i] = (i < n_pairs && tgt_lp) ? static_cast<uint16_t*>(tgt_lp[i]) : nullptr;
   }
   const float om = (float)(1.0 - momentum);   // python: (1 - momentum) in double, then fp32
   dim3 grid(grid_for(numel / 4, 256, 148 * 8), n_pairs);
-  ema_kernel<<<grid, 256, 0, s>>>(pr, numel, (float)momentum, om);
+  ema_kernel<<<grid, 256, 0, s>>>(pr, numel, (float)momentum, om, lp_f16);
   V2S_LAUNCH_CHECK();
   return 0;
 }
 
-int launch_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t s) {
-  cast_bf16_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, s>>>(src, static_cast<bf16*>(dst), n);
+int launch_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t s, int lp_f16) {
+  cast_lp_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, s>>>(src, static_cast<uint16_t*>(dst), n, lp_f16);
   V2S_LAUNCH_CHECK();
   return 0;
 }

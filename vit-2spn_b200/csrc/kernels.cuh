@@ -5,7 +5,7 @@
 
 namespace v2s {
 
-// type tag: 0 = fp32 activations, 1 = bf16 activations
+// type tag `at`: 0 = fp32 activations, 1 = bf16, 2 = fp16
 int launch_im2col(const float* const* x, void* const* out, int groups, int B, int at, cudaStream_t s);
 int launch_cls_rows(const float* const* params, float* const* hidden, int groups, int B, cudaStream_t s);
 int launch_assemble_tokens(const float* const* params, const float* const* tok, float* const* hidden, int groups,
@@ -35,20 +35,24 @@ int launch_attn_bwd_simt(const void* const* qkv, const void* const* ctx, const f
                          const void* const* dctx, void* const* dqkv, int groups, int B, int at,
                          cudaStream_t s);
 
-// tcgen05 versions (bf16 only)
+// tcgen05 versions (bf16, or fp16 with lp_f16 = 1)
 int launch_attn_fwd_tc(const void* const* qkv, void* const* ctx, float* const* lse, int groups, int B,
-                       cudaStream_t s);
+                       cudaStream_t s, int lp_f16 = 0);
 
 int launch_attn_bwd_tc(const void* const* qkv, const void* const* ctx, const float* const* lse,
-                       const void* const* dctx, void* const* dqkv, int groups, int B, cudaStream_t s);
+                       const void* const* dctx, void* const* dqkv, int groups, int B, cudaStream_t s, int lp_f16 = 0);
 
 int launch_cosine_loss(const float* p, const float* z, float* loss, float* dp, int B, int accum,
-                       float grad_scale, cudaStream_t s);
+                       float grad_scale, cudaStream_t s, const float* grad_scale_dev = nullptr);
 int launch_adam(const v2s_range_t* ranges, int n, int64_t step, double lr, double b1, double b2, double eps,
-                double wd, double grad_scale, cudaStream_t s);
+                double wd, double grad_scale, cudaStream_t s, int lp_f16 = 0);
+// device-resident step state (GradScaler-style skipping, CUDA-graph capturable): see v2s_adam_step_amp
+int launch_adam_amp(const v2s_range_t* ranges, int n, float* state8, double lr, double b1, double b2, double eps, double wd,
+                    double grad_multiplier, const float* grad_scale_dev, const float* found_inf_dev, int lp_f16, int advance,
+                    cudaStream_t s);
 int launch_ema(float* const* tgt, const float* const* onl, void* const* tgt_lp, int n_pairs,
-               int64_t numel, double momentum, cudaStream_t s);
-int launch_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t s);
+               int64_t numel, double momentum, cudaStream_t s, int lp_f16 = 0);
+int launch_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t s, int lp_f16 = 0);
 int launch_dropout_mask(float* mask, int64_t n, float p, uint64_t seed, uint64_t offset, cudaStream_t s);
 int launch_preprocess_u8(const uint8_t* src, float* dst, int B, cudaStream_t s);
 int launch_augment_finish(const uint8_t* src, int n, int in_size, const int32_t* bounds, const int32_t* coefs, int ksize,

@@ -17,6 +17,7 @@ namespace v2s {
 struct LpBf16 {
   static constexpr uint32_t kIdescFmt = 1;      // a_format / b_format = BF16
   static constexpr bool kIsF16 = false;
+  static constexpr uint32_t kOnePair = 0x3F803F80u;   // (1.0, 1.0)
   static __device__ __forceinline__ uint32_t pack(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -27,6 +28,7 @@ struct LpBf16 {
 struct LpF16 {
   static constexpr uint32_t kIdescFmt = 0;      // a_format / b_format = F16
   static constexpr bool kIsF16 = true;
+  static constexpr uint32_t kOnePair = 0x3C003C00u;   // (1.0, 1.0)
   static __device__ __forceinline__ uint32_t pack(float a, float b) {
     __half2 v = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);

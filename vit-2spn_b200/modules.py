@@ -32,12 +32,19 @@ from ._lib import Group, lib, check, ptr, stream_ptr
 
 momentum = 0.999            # ref:ssp_vit2spn_tiny.py:38 (module-level constant in the reference)
 
-_MODE_NAMES = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16}
+_MODE_NAMES = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16, "fp16": _lib.MODE_FP16}
+_LP_DTYPES = {_lib.LP_BF16: torch.bfloat16, _lib.LP_FP16: torch.float16}
+
+
+def _lp_format(mode):
+    """16-bit shadow format of a compute mode (None for the fp32 check mode)."""
+    return {_lib.MODE_BF16: _lib.LP_BF16, _lib.MODE_FP16: _lib.LP_FP16}.get(mode)
 _default_mode = os.environ.get("V2S_MODE", "bf16")
 
 
 def set_compute_mode(mode: str) -> None:
-    """'bf16' (tcgen05 GEMMs, fp32 accumulate/residual/LN/softmax) or 'fp32' (check mode)."""
+    """'bf16' (tcgen05 GEMMs, fp32 accumulate/residual/LN/softmax), 'fp16' (the same kernels on fp16 operands: the
+    reference's own CUDA precision, ref:ssp_vit2spn_tiny.py:175,209 — needs a GradScaler) or 'fp32' (check mode)."""
     global _default_mode
     if mode not in _MODE_NAMES:
         raise ValueError(f"mode must be one of {list(_MODE_NAMES)}")
@@ -70,6 +77,7 @@ class FlatStore:
         self.flat = None
         self.flat_grad = None
         self.flat_lp = None
+        self.lp_fmt = _lib.LP_BF16   # format of the 16-bit shadow (follows the compute mode that last asked for it)
         self._grad_views = None
         self._active = None
         self.lp_fresh = False        # set by the fused Adam / EMA kernels that refresh the shadow
@@ -105,13 +113,16 @@ class FlatStore:
                 break
         return self.flat
 
-    def lp(self, refresh=True):
-        """bf16 shadow copy of the flat buffer (same element offsets)."""
-        if self.flat_lp is None or self.flat_lp.device != self.flat.device:
-            self.flat_lp = torch.empty(self.numel, dtype=torch.bfloat16, device=self.flat.device)
+    def lp(self, refresh=True, fmt=None):
+        """16-bit shadow copy of the flat buffer (same element offsets), bf16 or fp16 (`fmt`: _lib.LP_*; None keeps
+        the current format)."""
+        fmt = self.lp_fmt if fmt is None else fmt
+        if self.flat_lp is None or self.flat_lp.device != self.flat.device or fmt != self.lp_fmt:
+            self.flat_lp = torch.empty(self.numel, dtype=_LP_DTYPES[fmt], device=self.flat.device)
+            self.lp_fmt = fmt
             self.lp_fresh = False
         if refresh and not (self.lp_fresh and self._ver == self._version_sum()):
-            check(lib.v2s_cast_bf16(ptr(self.flat), ptr(self.flat_lp), self.numel, stream_ptr()), "cast_bf16")
+            check(lib.v2s_cast_lp(ptr(self.flat), ptr(self.flat_lp), self.numel, self.lp_fmt, stream_ptr()), "cast_lp")
             self.lp_fresh = False
         return self.flat_lp
 
@@ -231,7 +242,7 @@ def _group(store, mode, x, slot, grads=None, hidden=None, feat=None, feat_stride
            dfeat_stride=0, dhidden=None):
     g = Group()
     g.params = store.flat.data_ptr()
-    g.params_lp = store.lp().data_ptr() if mode == _lib.MODE_BF16 else None
+    g.params_lp = store.lp(fmt=_lp_format(mode)).data_ptr() if mode != _lib.MODE_FP32 else None
     g.grads = grads.data_ptr() if grads is not None else None
     g.x = x.data_ptr()
     g.hidden = hidden.data_ptr() if hidden is not None else None
@@ -680,16 +691,32 @@ class DualStreamNetwork(nn.Module):
         n = st[0].numel
         tg = (C.c_void_p * 2)(st[2].flat.data_ptr(), st[3].flat.data_ptr())
         on = (C.c_void_p * 2)(st[0].flat.data_ptr(), st[1].flat.data_ptr())
-        lp = (C.c_void_p * 2)(st[2].lp(refresh=False).data_ptr(), st[3].lp(refresh=False).data_ptr())
+        fmt = _lp_format(self._mode())
+        fmt = st[2].lp_fmt if fmt is None else fmt
+        lp = (C.c_void_p * 2)(st[2].lp(refresh=False, fmt=fmt).data_ptr(), st[3].lp(refresh=False, fmt=fmt).data_ptr())
         m = globals().get("momentum", 0.999) if self.momentum is None else self.momentum
-        check(lib.v2s_ema_update(tg, on, lp, 2, n, float(m), stream_ptr()), "ema_update")
+        check(lib.v2s_ema_update_lp(tg, on, lp, 2, n, float(m), fmt, stream_ptr()), "ema_update")
         st[2].mark_lp_fresh()
         st[3].mark_lp_fresh()
 
     # -- fused native step (no autograd graph): fwd + loss + bwd in the library --------------
     def ssp_step(self, x1, x2, accumulation_steps=1, grad_scale=1.0, with_backward=True):
         """One micro-step of ref:ssp_vit2spn_tiny.py:209-213 — returns the loss tensor (already divided
-        by ``accumulation_steps``); gradients are accumulated into ``.grad`` of the parameters."""
+        by ``accumulation_steps``, NOT multiplied by the loss scale); gradients are accumulated into ``.grad`` of
+        the parameters.  ``grad_scale``: a float, a one-element CUDA tensor, or a ``torch.amp.GradScaler`` (fp16
+        mode, ref:213 ``scaler.scale(loss).backward()``): tensor / scaler values are read on the device, no
+        host synchronisation."""
+        scale_t = None
+        if isinstance(grad_scale, torch.amp.GradScaler):
+            if grad_scale.is_enabled():
+                if grad_scale._scale is None:                      # lazily created on first use, as scaler.scale() does
+                    grad_scale.scale(torch.zeros(1, device=x1.device))
+                scale_t = grad_scale._scale
+            grad_scale = 1.0
+        elif isinstance(grad_scale, torch.Tensor):
+            scale_t, grad_scale = grad_scale.to(torch.float32), 1.0
+            if not scale_t.is_cuda or scale_t.numel() != 1:
+                raise ValueError("grad_scale tensor must be a one-element CUDA tensor")
         x1, x2 = _check_images(x1), _check_images(x2)
         st, hs = self._stores(), self._head_store
         for s in st:
@@ -713,10 +740,16 @@ class DualStreamNetwork(nn.Module):
             loss, dfeat = out[:1], out[4:].view(B, 384)
             base, nbytes = _aligned(ws)
             hg = hs.grads() if with_backward else None
-            check(lib.v2s_heads_loss_fwd_bwd(ptr(hs.flat), ptr(hg), ptr(feat_o), ptr(feat_t), ptr(mask_o), ptr(mask_t),
-                                             ptr(dfeat), None, None, ptr(loss), B, int(accumulation_steps),
-                                             float(grad_scale), 1 if with_backward else 0, C.c_void_p(base), nbytes,
-                                             stream_ptr()), "heads_loss_fwd_bwd")
+            if scale_t is not None:
+                check(lib.v2s_heads_loss_fwd_bwd_amp(ptr(hs.flat), ptr(hg), ptr(feat_o), ptr(feat_t), ptr(mask_o),
+                                                     ptr(mask_t), ptr(dfeat), None, None, ptr(loss), B,
+                                                     int(accumulation_steps), ptr(scale_t), 1 if with_backward else 0,
+                                                     C.c_void_p(base), nbytes, stream_ptr()), "heads_loss_fwd_bwd_amp")
+            else:
+                check(lib.v2s_heads_loss_fwd_bwd(ptr(hs.flat), ptr(hg), ptr(feat_o), ptr(feat_t), ptr(mask_o), ptr(mask_t),
+                                                 ptr(dfeat), None, None, ptr(loss), B, int(accumulation_steps),
+                                                 float(grad_scale), 1 if with_backward else 0, C.c_void_p(base), nbytes,
+                                                 stream_ptr()), "heads_loss_fwd_bwd")
             if with_backward:
                 bw = [
                     _group(st[0], mode, x1, 0, grads=st[0].grads(), dfeat=dfeat, dfeat_stride=384),
@@ -758,7 +791,7 @@ class SingleStreamNetwork(nn.Module):
         tg = (C.c_void_p * 1)(st.flat.data_ptr())
         on = (C.c_void_p * 1)(so.flat.data_ptr())
         lp = (C.c_void_p * 1)(st.lp(refresh=False).data_ptr())
-        check(lib.v2s_ema_update(tg, on, lp, 1, so.numel, float(momentum), stream_ptr()), "ema_update")
+        check(lib.v2s_ema_update_lp(tg, on, lp, 1, so.numel, float(momentum), st.lp_fmt, stream_ptr()), "ema_update")
         st.mark_lp_fresh()
 
 

@@ -47,12 +47,12 @@ def allreduce_buckets(buckets, group=None, average=True, async_op=True):
 
 def allreduce_gradients(model, group=None, optimizer=None):
     """Gradient all-reduce for one optimizer step.  With a ``FusedAdam`` the 1/world factor is folded
-    into the Adam kernel (``optimizer.grad_scale``) instead of a separate pass over the gradients."""
+    into the Adam kernel (``optimizer.grad_multiplier``) instead of a separate pass over the gradients."""
     buckets = gradient_buckets(model)
-    fold = optimizer is not None and hasattr(optimizer, "grad_scale")
+    fold = optimizer is not None and hasattr(optimizer, "grad_multiplier")
     world = allreduce_buckets(buckets, group=group, average=not fold)
     if fold:
-        optimizer.grad_scale = 1.0 / world
+        optimizer.grad_multiplier = 1.0 / world
     return world
 
 

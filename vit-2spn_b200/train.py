@@ -6,6 +6,11 @@ import os
 import torch
 import torch.nn as nn
 
+
+def _default_mode():
+    from .modules import get_compute_mode
+    return get_compute_mode()
+
 # reference constants (ref:ssp_vit2spn_tiny.py:35-39)
 batch_size = 128
 epochs = 100
@@ -40,16 +45,22 @@ def load_checkpoint(model, optimizer, path="checkpoint.pth", device=None):
 
 
 def train_self_supervised(model, dataloader, epochs, optimizer, criterion, checkpoint_path="checkpoint.pth",
-                          accumulation_steps=accumulation_steps, device=None, log=print):
+                          accumulation_steps=accumulation_steps, device=None, log=print, scaler=None):
     """ref:ssp_vit2spn_tiny.py:197-232.  With the reference's criterion (``nn.CosineSimilarity(dim=1)``)
     the whole micro-step (4 backbones, heads, loss, backward) runs in the CUDA library via
     ``model.ssp_step``; any other criterion goes through the autograd-compatible ``model(x1, x2)``.
-    bf16 needs no loss scaling, so the reference's GradScaler (fp16) has no counterpart here.
-    The per-micro-step ``loss.item()`` host sync of the reference (ref:220) is replaced by a
-    device-side accumulation read once per epoch."""
+    In the fp16 compute mode (the reference's CUDA precision) a ``torch.amp.GradScaler`` is used exactly as ref:175,
+    213,216-217 do (``scaler`` argument, created here if omitted): the loss is scaled on the device inside the fused
+    step, ``scaler.step(optimizer)`` skips the update on overflow and ``scaler.update()`` adapts the scale; bf16 and the
+    fp32 check mode need no scaling.  The per-micro-step ``loss.item()`` host sync of the reference (ref:220) is
+    replaced by a device-side accumulation read once per epoch."""
     model, optimizer, start_epoch, _ = load_checkpoint(model, optimizer, checkpoint_path, device)
     device = device or next(model.parameters()).device
     fused = isinstance(criterion, nn.CosineSimilarity) and criterion.dim == 1 and hasattr(model, "ssp_step")
+    if scaler is None and getattr(model, "compute_mode", None) == "fp16" or \
+            (scaler is None and getattr(model, "compute_mode", None) is None and _default_mode() == "fp16"):
+        scaler = torch.amp.GradScaler("cuda")                      # ref:175
+    use_scaler = scaler is not None and scaler.is_enabled()
     model.train()
     loss_history = []
     for epoch in range(start_epoch, epochs):
@@ -60,13 +71,17 @@ def train_self_supervised(model, dataloader, epochs, optimizer, criterion, check
             view1, view2 = views
             view1, view2 = view1.to(device, non_blocking=True), view2.to(device, non_blocking=True)
             if fused:
-                loss = model.ssp_step(view1, view2, accumulation_steps)
+                loss = model.ssp_step(view1, view2, accumulation_steps, grad_scale=scaler if use_scaler else 1.0)
             else:
                 pred, tgt = model(view1, view2)
                 loss = -torch.mean(criterion(pred, tgt)) / accumulation_steps
-                loss.backward()
+                (scaler.scale(loss) if use_scaler else loss).backward()
             if (i + 1) % accumulation_steps == 0 or (i + 1) == n:
-                optimizer.step()
+                if use_scaler:
+                    scaler.step(optimizer)
+                    scaler.update()
+                else:
+                    optimizer.step()
                 optimizer.zero_grad()
                 model.update_target_network()
             epoch_loss += loss.detach() * accumulation_steps
