@@ -57,7 +57,9 @@ int v2s_abi_version(void);
 const char* v2s_last_error(void);
 
 /* Verifies that `device` is an sm_100 part and selects it.  Replaces nothing in the reference
- * (torch picks the device, ref:ssp_vit2spn_tiny.py:32); exists so that the product fails loudly. */
+ * (torch picks the device, ref:ssp_vit2spn_tiny.py:32); exists so that the product fails loudly.  The caller's current
+ * device is not changed; every other entry point works on the CURRENT device of the calling thread, which must be
+ * the device its pointers live on (the host mirror makes it so around each call). */
 int v2s_init(int device);
 
 /* ---- flat parameter layout --------------------------------------------------------------
@@ -202,6 +204,10 @@ int v2s_preprocess_u8(const uint8_t* src, float* dst, int batch, void* stream);
 int v2s_augment_finish_u8(const uint8_t* src, int n, int in_size, const int32_t* bounds, const int32_t* coefs, int ksize,
                           const float* k1d, const int32_t* erase, const float* host_mean3, const float* host_std3,
                           float* dst, void* stream);
+
+/* Persistent kernels (GEMM, MLP, attention forward) size their grids to at most n_sms SMs until reset with 0: leaves
+ * SMs to a collective that runs concurrently with the backward pass (gradient all-reduce overlap). */
+int v2s_set_sm_limit(int n_sms);
 
 /* test hooks: individual operators, used by tests/ to localise a parity failure */
 int v2s_test_gemm(int which, const void* a, const void* b, void* c, int m, int n, int k,

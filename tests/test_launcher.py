@@ -37,6 +37,7 @@ def test_shims_only_fill_gaps(monkeypatch):
 def test_medmnist_shim_contract(monkeypatch):
     """Item / labels contract the reference relies on (ref:octmnist_ft_vit2spn.py:47-50,177)."""
     monkeypatch.setenv("V2S_SHIM_DATASET_SIZE", "12")
+    monkeypatch.setenv("V2S_SYNTHETIC_DATA", "1")
     import importlib.util
     d = os.path.join(ROOT, "vit-2spn_b200", "compat", "medmnist")
     spec = importlib.util.spec_from_file_location("_v2s_medmnist", os.path.join(d, "__init__.py"),
@@ -55,6 +56,9 @@ def test_medmnist_shim_contract(monkeypatch):
         seen = []
         ds2 = mod.OCTMNIST(split="val", transform=lambda im: seen.append(im.size) or 1.5)
         assert ds2[0][0] == 1.5 and seen == [(28, 28)]
+        monkeypatch.setenv("V2S_SYNTHETIC_DATA", "0")          # fabricated data is opt-in
+        with pytest.raises(ImportError, match="V2S_SYNTHETIC_DATA"):
+            mod.OCTMNIST(split="train")
     finally:
         for k in [k for k in sys.modules if k.startswith("_v2s_medmnist")]:
             del sys.modules[k]
@@ -86,12 +90,12 @@ def test_launcher_runs_reference_style_script(tmp_path):
     """A script written against transformers / medmnist / fvcore / matplotlib, with its own dual-stream model,
     autocast + GradScaler loop and ``.data`` EMA, runs unchanged; the saved backbone has HF key names and loads
     into the stock ``transformers.ViTModel``."""
-    env = dict(os.environ, PYTHONPATH=ROOT, V2S_SHIM_DATASET_SIZE="12")
+    env = dict(os.environ, PYTHONPATH=ROOT, V2S_SHIM_DATASET_SIZE="12", V2S_SYNTHETIC_DATA="1")
     out = tmp_path / "bb.pth"
     r = subprocess.run([sys.executable, "-m", "vit2spn.run", os.path.join(ROOT, "tests", "data", "mini_user_script.py"),
                         str(out)], capture_output=True, text=True, env=env, cwd=tmp_path, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert "MINI_OK 6" in r.stdout
+    assert "MINI_OK 6" in r.stdout and "SYNTHETIC DATA" in r.stdout
     sd = torch.load(out, map_location="cpu")
     assert len(sd) == 200 and "vit.embeddings.cls_token" in sd
     from transformers import ViTConfig, ViTModel

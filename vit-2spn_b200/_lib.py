@@ -76,6 +76,7 @@ _SIGS = {
     "v2s_test_mlp": (C.c_int, [_i] + [_vp] * 14 + [_i, _i, _vp]),
     "v2s_test_attention": (C.c_int, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "v2s_launch_count": (_i64, []),
+    "v2s_set_sm_limit": (C.c_int, [_i]),
     "v2s_debug_flag": (C.c_int, []),
     "v2s_debug_counters": (C.c_int, [C.POINTER(_i64)]),
     "v2s_prof_enable": (C.c_int, [_i]),
@@ -139,6 +140,14 @@ def ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """The current torch stream of `device` (default: the current device)."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def on_device(t):
+    """Context manager: make the device of tensor `t` current around library calls (the library's per-device state —
+    kernel attributes, error flag, SM count — and stream_ptr() follow the current device)."""
+    import torch
+    return torch.cuda.device(t.device)

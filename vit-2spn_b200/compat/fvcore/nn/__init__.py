@@ -5,6 +5,7 @@ cannot be traced, so the count is analytic: 1 253 491 200 MAC per image per ViT-
 import torch.nn as nn
 
 VIT_TINY_MAC_PER_IMAGE = 28901376 + 12 * 102049152
+_announced = False
 
 
 def _is_backbone(m):
@@ -26,6 +27,11 @@ class FlopCountAnalysis:
         self.batch = int(first.shape[0]) if hasattr(first, "shape") and len(first.shape) > 0 else 1
 
     def total(self):
+        global _announced
+        if not _announced:
+            print("vit2spn: fvcore is not installed; FlopCountAnalysis returns an ANALYTIC count (1 FLOP per MAC of the "
+                  "ViT-Tiny backbones and nn.Linear layers), not a traced measurement", flush=True)
+            _announced = True
         return int(_count(self.model, self.batch))
 
     def by_module(self):

@@ -13,7 +13,12 @@ class OCTMNIST:
 
     def __init__(self, split, transform=None, target_transform=None, download=False, as_rgb=False, root=None,
                  size=None, mmap_mode=None):
+        if os.environ.get("V2S_SYNTHETIC_DATA", "0") != "1":
+            raise ImportError("vit2spn's medmnist stand-in fabricates data; set V2S_SYNTHETIC_DATA=1 to opt in")
+        print(f"*** SYNTHETIC DATA *** OCTMNIST('{split}') is a seeded stand-in (stripes + noise, random labels), not medmnist",
+              flush=True)
         self.info = INFO[self.flag]
+        self.synthetic = True
         self.split, self.transform, self.target_transform, self.as_rgb = split, transform, target_transform, as_rgb
         n = self.info["n_samples"][split]
         cap = os.environ.get("V2S_SHIM_DATASET_SIZE")

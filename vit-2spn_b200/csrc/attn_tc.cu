@@ -895,10 +895,10 @@ int launch_attn_fwd_tc(const void* const* qkv, void* const* ctx, float* const* l
   }
   static const bool legacy = getenv("V2S_ATTN_FWD") && strcmp(getenv("V2S_ATTN_FWD"), "v1") == 0;
   if (legacy && !lp_f16) {      // one CTA per job, two CTAs per SM (kept for A/B measurements; bf16 only)
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[MAX_DEVICES] = {false};
+    if (!attr[cur_device()]) {
       V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
-      attr = true;
+      attr[cur_device()] = true;
     }
     V2S_CUDA_OK(launch_pdl(attn_fwd_tc_kernel, dim3(NH * 2, B, groups), dim3(F_THREADS), (size_t)F_SMEM, s, p));
     V2S_LAUNCH_CHECK();
@@ -909,16 +909,15 @@ int launch_attn_fwd_tc(const void* const* qkv, void* const* ctx, float* const* l
   memcpy(pp.tmQ, p.tmQ, sizeof(p.tmQ)); memcpy(pp.tmKV, p.tmKV, sizeof(p.tmKV)); memcpy(pp.tmCtx, p.tmCtx, sizeof(p.tmCtx));
   for (int g = 0; g < groups; ++g) pp.lse[g] = p.lse[g];
   pp.B = B; pp.total_jobs = 2 * NH * B * groups; pp.err_flag = p.err_flag; pp.dbg = tc_dbg_counters();
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    V2S_CUDA_OK(cudaGetDevice(&dev));
-    V2S_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  static bool pattr[MAX_DEVICES] = {false};
+  if (!pattr[cur_device()]) {
     V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_persist_kernel<false, LpBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
     V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_persist_kernel<true, LpBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
     V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_persist_kernel<false, LpF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
     V2S_CUDA_OK(cudaFuncSetAttribute(attn_fwd_persist_kernel<true, LpF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+    pattr[cur_device()] = true;
   }
+  const int num_sms = tc_num_sms();
   const int grid = pp.total_jobs < num_sms ? pp.total_jobs : num_sms;
   if (lp_f16) {
     if (pp.dbg) V2S_CUDA_OK(launch_pdl(attn_fwd_persist_kernel<true, LpF16>, dim3(grid), dim3(PF_THREADS), (size_t)PF_SMEM, s, pp));
@@ -949,13 +948,13 @@ int launch_attn_bwd_tc(const void* const* qkv, const void* const* ctx, const flo
     p.lse[g] = lse[g];
   }
   p.dbg = tc_dbg_counters();
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[MAX_DEVICES] = {false};
+  if (!attr[cur_device()]) {
     V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, LpBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
     V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<true, LpBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
     V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, LpF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
     V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<true, LpF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
-    attr = true;
+    attr[cur_device()] = true;
   }
   const dim3 grid(NH, B, groups);
   if (lp_f16) {

@@ -140,10 +140,10 @@ int launch_augment_finish(const uint8_t* src, int n, int in_size, const int32_t*
   for (int c = 0; c < 3; ++c) { p.mean[c] = mean3[c]; p.std[c] = std3[c]; }
   p.in_size = in_size; p.ksize = ksize;
   const size_t smem = AUG_MAX_IN * AUG_MAX_IN + AUG_MAX_IN * AUG_OUT + AUG_ROWS * AUG_OUT;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[MAX_DEVICES] = {false};
+  if (!attr[cur_device()]) {
     V2S_CUDA_OK(cudaFuncSetAttribute(augment_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
+    attr[cur_device()] = true;
   }
   augment_finish_kernel<<<dim3(n, 2), 256, smem, s>>>(p);
   V2S_LAUNCH_CHECK();

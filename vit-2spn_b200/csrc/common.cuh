@@ -71,6 +71,15 @@ static_assert(HEADS_NUMEL == 558464, "heads numel");
 
 inline int64_t layer_off(int l) { return OFF_LAYER0 + (int64_t)l * LAYER_NUMEL; }
 
+// per-device library state (function attributes, error flag, SM count) is indexed by the CURRENT device of the calling
+// thread: the host mirror makes the tensors' device current around every call
+constexpr int MAX_DEVICES = 16;
+inline int cur_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
+  return d < MAX_DEVICES ? d : MAX_DEVICES - 1;
+}
+
 // ---- error handling ---------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 extern int64_t g_launch_count;

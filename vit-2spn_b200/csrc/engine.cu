@@ -741,8 +741,13 @@ int v2s_init(int device) {
     set_error("device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
     return 1;
   }
+  // per-device state is created with `device` current; the caller's current device is left as it was
+  int prev = 0;
+  V2S_CUDA_OK(cudaGetDevice(&prev));
   V2S_CUDA_OK(cudaSetDevice(device));
-  return gemm_tc_init();
+  const int rc = gemm_tc_init();
+  cudaSetDevice(prev);
+  return rc;
 }
 
 int64_t v2s_backbone_numel(void) { return BACKBONE_NUMEL; }
@@ -917,6 +922,11 @@ int v2s_augment_finish_u8(const uint8_t* src, int n, int in_size, const int32_t*
 }
 
 int64_t v2s_launch_count(void) { return g_launch_count; }
+
+int v2s_set_sm_limit(int n_sms) {
+  tc_set_sm_limit(n_sms);
+  return 0;
+}
 
 int v2s_prof_enable(int on) {
   prof::enabled = on != 0;

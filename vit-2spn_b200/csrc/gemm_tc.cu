@@ -584,9 +584,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
-int* g_err_flag = nullptr;      // device int, allocated once at init (4 bytes; the only allocation)
-long long* g_dbg = nullptr;     // 32 counters, only with V2S_GEMM_DEBUG=1
-int g_num_sms = 148;
+int* g_err_flag[MAX_DEVICES] = {nullptr};      // device int per GPU, allocated once at init (4 bytes; the only allocation)
+long long* g_dbg[MAX_DEVICES] = {nullptr};     // 32 counters, only with V2S_GEMM_DEBUG=1
+int g_num_sms_dev[MAX_DEVICES] = {0};
+int g_sm_limit = 0;             // v2s_set_sm_limit: persistent grids leave SMs to a concurrent collective
 int g_dbg_flags = 0;
 bool g_disabled = false;
 
@@ -677,20 +678,25 @@ int tmap_get_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uin
                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
 }
-int tc_num_sms() { return g_num_sms; }
-int* tc_err_flag() { return g_err_flag; }
-long long* tc_dbg_counters() { return g_dbg; }
+int tc_num_sms() {
+  const int n = g_num_sms_dev[cur_device()] > 0 ? g_num_sms_dev[cur_device()] : 148;
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
+}
+void tc_set_sm_limit(int n) { g_sm_limit = n > 0 ? n : 0; }
+int* tc_err_flag() { return g_err_flag[cur_device()]; }
+long long* tc_dbg_counters() { return g_dbg[cur_device()]; }
 bool tc_enabled() { return g_encode != nullptr && !g_disabled; }
 
 namespace {
 
 template <int EPI, bool OUT_BF16, bool DBG, typename LP>
 int launch_kernel_impl(TcParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[MAX_DEVICES] = {false};
+  if (!attr_set[cur_device()]) {
     V2S_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI, OUT_BF16, DBG, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_set = true;
+    attr_set[cur_device()] = true;
   }
+  const int g_num_sms = tc_num_sms();
   // split the 227 KB between the operand ring and the epilogue staging ring of this variant
   const int budget = SMEM_LIMIT - 1024 - SMEM_BAR_BYTES - Cfg<EPI, OUT_BF16>::STAGING_BYTES;
   if (p.b_stationary) {
@@ -738,42 +744,46 @@ int launch_kernel(TcParams& p, int lp_f16, cudaStream_t stream) {
 }  // namespace
 
 int gemm_tc_init() {
-  if (g_encode) return 0;
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
-    set_error("cuTensorMapEncodeTiled entry point not available: %s", cudaGetErrorString(e));
-    return 1;
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      set_error("cuTensorMapEncodeTiled entry point not available: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    const char* env = getenv("V2S_GEMM");
+    g_disabled = env && strcmp(env, "simt") == 0;   // debugging: route every GEMM through the SIMT kernel
+    if (getenv("V2S_GEMM_DEBUG")) g_dbg_flags = atoi(getenv("V2S_GEMM_DEBUG"));
   }
-  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-  int dev = 0;
-  V2S_CUDA_OK(cudaGetDevice(&dev));
-  V2S_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  V2S_CUDA_OK(cudaMalloc(&g_err_flag, sizeof(int)));
-  V2S_CUDA_OK(cudaMemset(g_err_flag, 0, sizeof(int)));
+  // per-device state of the CURRENT device
+  const int dev = cur_device();
+  if (g_err_flag[dev]) return 0;
+  V2S_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms_dev[dev], cudaDevAttrMultiProcessorCount, dev));
+  V2S_CUDA_OK(cudaMalloc(&g_err_flag[dev], sizeof(int)));
+  V2S_CUDA_OK(cudaMemset(g_err_flag[dev], 0, sizeof(int)));
   if (getenv("V2S_GEMM_DEBUG")) {
-    g_dbg_flags = atoi(getenv("V2S_GEMM_DEBUG"));
-    V2S_CUDA_OK(cudaMalloc(&g_dbg, 32 * sizeof(long long)));
-    V2S_CUDA_OK(cudaMemset(g_dbg, 0, 32 * sizeof(long long)));
+    V2S_CUDA_OK(cudaMalloc(&g_dbg[dev], 32 * sizeof(long long)));
+    V2S_CUDA_OK(cudaMemset(g_dbg[dev], 0, 32 * sizeof(long long)));
   }
-  const char* env = getenv("V2S_GEMM");
-  g_disabled = env && strcmp(env, "simt") == 0;   // debugging: route every GEMM through the SIMT kernel
   return 0;
 }
 
 int gemm_tc_debug_counters(long long* host32) {
-  if (!g_dbg) { set_error("V2S_GEMM_DEBUG not set"); return 1; }
-  V2S_CUDA_OK(cudaMemcpy(host32, g_dbg, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
-  V2S_CUDA_OK(cudaMemset(g_dbg, 0, 32 * sizeof(long long)));
+  long long* dbg = tc_dbg_counters();
+  if (!dbg) { set_error("V2S_GEMM_DEBUG not set"); return 1; }
+  V2S_CUDA_OK(cudaMemcpy(host32, dbg, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+  V2S_CUDA_OK(cudaMemset(dbg, 0, 32 * sizeof(long long)));
   return 0;
 }
 
 int gemm_tc_error_flag() {
-  if (!g_err_flag) return 0;
+  int* flag = tc_err_flag();
+  if (!flag) return 0;
   int v = 0;
-  cudaMemcpy(&v, g_err_flag, sizeof(int), cudaMemcpyDeviceToHost);
-  if (v) cudaMemset(g_err_flag, 0, sizeof(int));
+  cudaMemcpy(&v, flag, sizeof(int), cudaMemcpyDeviceToHost);
+  if (v) cudaMemset(flag, 0, sizeof(int));
   return v;
 }
 
@@ -803,6 +813,7 @@ int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t strea
   if (d.b_rs == 1) { b_mn = 0; b_ld = d.b_cs; } else if (d.b_cs == 1) { b_mn = 1; b_ld = d.b_rs; } else return 0;
   if ((a_ld % 8) || (b_ld % 8) || (d.ldc % 8) || (d.N % 8)) return 0;
 
+  const int g_num_sms = tc_num_sms();
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.M = d.M; p.N = d.N; p.K = d.K; p.groups = d.groups;
@@ -832,8 +843,8 @@ int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t strea
     p.ctas_per_combo = cpc;
   }
   p.late_wait = (d.late_wait && !getenv("V2S_NO_LATE_WAIT")) ? 1 : 0;
-  p.err_flag = g_err_flag;
-  p.dbg = g_dbg;
+  p.err_flag = tc_err_flag();
+  p.dbg = tc_dbg_counters();
   p.dbg_flags = g_dbg_flags;
   const CUtensorMapSwizzle out_swz = out_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   for (int g = 0; g < d.groups; ++g) {

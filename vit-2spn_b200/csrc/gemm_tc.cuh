@@ -18,7 +18,8 @@ int tmap_get_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uin
 // cached rank-2 tensor map of a row-major [d1 rows, d0 cols] 16-bit (is_lp) or fp32 tensor, box b0 x b1
 int tmap_get_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t stride1_elems, uint32_t b0,
                 uint32_t b1, bool is_lp, int swizzle_bytes);
-int tc_num_sms();
+int tc_num_sms();              // SMs persistent grids may use on the current device (see v2s_set_sm_limit)
+void tc_set_sm_limit(int n);
 int* tc_err_flag();
 long long* tc_dbg_counters();   // 32 device counters when V2S_GEMM_DEBUG is set, else NULL
 bool tc_enabled();

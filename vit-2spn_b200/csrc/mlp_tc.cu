@@ -604,11 +604,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
 
 template <int MODE, typename LP>
 int launch_impl(const MlpParams& p, int grid, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[MAX_DEVICES] = {false};
+  if (!attr_set[cur_device()]) {
     V2S_CUDA_OK(cudaFuncSetAttribute(mlp_tc_kernel<MODE, LP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     V2S_CUDA_OK(cudaFuncSetAttribute(mlp_tc_kernel<MODE, LP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
+    attr_set[cur_device()] = true;
   }
   if (p.dbg) V2S_CUDA_OK(launch_pdl(mlp_tc_kernel<MODE, LP, true>, dim3(grid), dim3(N_THREADS), (size_t)SMEM_BYTES, stream, p));
   else V2S_CUDA_OK(launch_pdl(mlp_tc_kernel<MODE, LP, false>, dim3(grid), dim3(N_THREADS), (size_t)SMEM_BYTES, stream, p));

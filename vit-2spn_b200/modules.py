@@ -55,6 +55,23 @@ def get_compute_mode() -> str:
     return _default_mode
 
 
+def _with_device_of(get):
+    """Decorator: run the method with the device of `get(*args)` current (the library's launches, its
+    per-device state and `stream_ptr()` follow the current device, so a model on cuda:1 must not launch on cuda:0)."""
+    import functools
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapped(*a, **k):
+            t = get(*a, **k)
+            if t is None or not t.is_cuda:
+                return fn(*a, **k)
+            with torch.cuda.device(t.device):
+                return fn(*a, **k)
+        return wrapped
+    return deco
+
+
 def _require_cuda(t: torch.Tensor, what: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(
@@ -113,6 +130,7 @@ class FlatStore:
                 break
         return self.flat
 
+    @_with_device_of(lambda self, *a, **k: self.flat)
     def lp(self, refresh=True, fmt=None):
         """16-bit shadow copy of the flat buffer (same element offsets), bf16 or fp16 (`fmt`: _lib.LP_*; None keeps
         the current format)."""
@@ -336,6 +354,7 @@ class _BackboneFn(torch.autograd.Function):
     """x -> (hidden_states[-1] | mean-pooled features) for one backbone, autograd-compatible."""
 
     @staticmethod
+    @_with_device_of(lambda ctx, x, *a, **k: x)
     def forward(ctx, x, anchor, model, pooled, need_grad):
         store = model._store
         store.ensure()
@@ -359,6 +378,7 @@ class _BackboneFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_with_device_of(lambda ctx, dout: dout)
     def backward(ctx, dout):
         model, store = ctx.model, ctx.model._store
         if ctx.ws is None:
@@ -546,6 +566,7 @@ class _DualStreamFn(torch.autograd.Function):
     """(x1, x2) -> (online_pred, target_proj): 4 grouped backbones + heads in the CUDA library."""
 
     @staticmethod
+    @_with_device_of(lambda ctx, x1, *a, **k: x1)
     def forward(ctx, x1, x2, anchor, model, need_grad):
         st = model._stores()
         for s in st:
@@ -579,6 +600,7 @@ class _DualStreamFn(torch.autograd.Function):
         return pred, tgt
 
     @staticmethod
+    @_with_device_of(lambda ctx, dpred, _dtgt: dpred)
     def backward(ctx, dpred, _dtgt):
         model = ctx.model
         if ctx.ws is None:
@@ -682,6 +704,7 @@ class DualStreamNetwork(nn.Module):
         anchor = self.online_network_1.vit.embeddings.cls_token
         return _DualStreamFn.apply(x1, x2, anchor, self, anchor.requires_grad and torch.is_grad_enabled())
 
+    @_with_device_of(lambda self: self.online_network_1.vit._store.flat)
     def update_target_network(self):
         """ref:ssp_vit2spn_tiny.py:162-166 as one flat-buffer kernel over both (online, target) pairs."""
         st = self._stores()
@@ -700,6 +723,7 @@ class DualStreamNetwork(nn.Module):
         st[3].mark_lp_fresh()
 
     # -- fused native step (no autograd graph): fwd + loss + bwd in the library --------------
+    @_with_device_of(lambda self, x1, *a, **k: x1)
     def ssp_step(self, x1, x2, accumulation_steps=1, grad_scale=1.0, with_backward=True):
         """One micro-step of ref:ssp_vit2spn_tiny.py:209-213 — returns the loss tensor (already divided
         by ``accumulation_steps``, NOT multiplied by the loss scale); gradients are accumulated into ``.grad`` of
@@ -784,6 +808,7 @@ class SingleStreamNetwork(nn.Module):
         target_proj_feat = self.projection_head(feat_target).detach()
         return online_pred_feat, target_proj_feat
 
+    @_with_device_of(lambda self, *a, **k: self.online_network.vit._store.flat)
     def update_target_network(self, momentum=0.99):
         so, st = self.online_network.vit._store, self.target_network.vit._store
         so.ensure(); st.ensure()

@@ -180,6 +180,7 @@ class FusedAdam(torch.optim.Optimizer):
             dev_launches = {}      # (id(state8), lp_fmt) -> (state8, [Range]); one shared state8 per step count
             fresh8 = {}            # (device, step) -> state8 created in this call
             covered, keep = set(), []
+            dev_of = {}            # Range.params address -> device (host-path launches run with that device current)
 
             def new_state8(dev, step):
                 s8 = fresh8.get((dev, step))
@@ -217,7 +218,8 @@ class FusedAdam(torch.optim.Optimizer):
                         ent[3], ent[4] = None, state8
                     dev_launches.setdefault((id(state8), store.lp_fmt), (state8, []))[1].append(rng)
                 else:
-                    host_launches.setdefault((step + 1, store.lp_fmt), []).append(rng)
+                    host_launches.setdefault((step + 1, store.lp_fmt, store.flat.device), []).append(rng)
+                    dev_of[rng.params] = store.flat.device
                     ent[3] = step + 1
                 if lp is not None:
                     store.mark_lp_fresh()
@@ -244,13 +246,15 @@ class FusedAdam(torch.optim.Optimizer):
                     else:
                         step = int(float(st["step"]))
                         st["step"] += 1
-                        host_launches.setdefault((step + 1, _lib.LP_BF16), []).append(rng)
-            for (step, fmt), rs in host_launches.items():
+                        host_launches.setdefault((step + 1, _lib.LP_BF16, p.device), []).append(rng)
+                        dev_of[rng.params] = p.device
+            for (step, fmt, _dev), rs in host_launches.items():
                 for i in range(0, len(rs), 4):
                     chunk = rs[i:i + 4]
                     arr = (Range * len(chunk))(*chunk)
-                    check(lib.v2s_adam_step_lp(arr, len(chunk), int(step), float(lr), float(b1), float(b2), float(eps),
-                                               float(wd), float(self.grad_multiplier), int(fmt), stream_ptr()), "adam_step")
+                    with torch.cuda.device(dev_of[chunk[0].params]):
+                        check(lib.v2s_adam_step_lp(arr, len(chunk), int(step), float(lr), float(b1), float(b2), float(eps),
+                                                   float(wd), float(self.grad_multiplier), int(fmt), stream_ptr()), "adam_step")
             advanced = set()
             for (sid, fmt), (state8, rs) in dev_launches.items():
                 dev = state8.device
@@ -260,8 +264,9 @@ class FusedAdam(torch.optim.Optimizer):
                 for i in range(0, len(rs), 4):
                     chunk = rs[i:i + 4]
                     arr = (Range * len(chunk))(*chunk)
-                    check(lib.v2s_adam_step_amp(arr, len(chunk), state8.data_ptr(), float(lr), float(b1), float(b2),
-                                                float(eps), float(wd), float(self.grad_multiplier), sp, fp, int(fmt),
-                                                0 if sid in advanced else 1, stream_ptr()), "adam_step_amp")
+                    with torch.cuda.device(dev):
+                        check(lib.v2s_adam_step_amp(arr, len(chunk), state8.data_ptr(), float(lr), float(b1), float(b2),
+                                                    float(eps), float(wd), float(self.grad_multiplier), sp, fp, int(fmt),
+                                                    0 if sid in advanced else 1, stream_ptr()), "adam_step_amp")
                     advanced.add(sid)
         return loss

@@ -9,8 +9,11 @@ What it does before handing control to the script ("what scripts ca
   (ref:ssp_vit2spn_tiny.py:112) and ``ViTModel(ViTConfig(...))`` (ref:ssp_ssl/ssl_vit2spn_scratch.py:100-109)
   build the CUDA backbone; the script's own ``ViTBackbone`` / ``DualStreamNetwork`` / training loop,
   ``torch.optim.Adam``, ``GradScaler`` and ``.data`` EMA rebinding run as written.
-* modules the image lacks (``medmnist``, ``fvcore``, ``matplotlib``) are served from ``vit2spn/compat``
-  when — and only when — the real ones cannot be imported.
+* modules the image lacks (``fvcore``, ``matplotlib``) are served from ``vit2spn/compat`` when — and only when —
+  the real ones cannot be imported.  The ``medmnist`` stand-in FABRICATES data (seeded synthetic OCTMNIST-shaped
+  images with random labels), so it is opt-in: ``V2S_SYNTHETIC_DATA=1``; without it a missing ``medmnist`` stays an
+  ImportError.  Every run on fabricated data says so on stdout (``SYNTHETIC DATA`` banner), and the analytic FLOP
+  count of the ``fvcore`` stand-in is labelled as such.
 * the script's output directories are created relative to the current directory, as it assumes.
 
 The script's own classes call the backbone once per network (4 launches of the grouped kernels instead of 1);
@@ -31,6 +34,8 @@ def install_shims(names=SHIMS):
     for name in names:
         if name in sys.modules:
             continue
+        if name == "medmnist" and os.environ.get("V2S_SYNTHETIC_DATA", "0") != "1":
+            continue              # fabricated data is opt-in: the script's own `import medmnist` fails loudly instead
         try:
             found = importlib.util.find_spec(name) is not None
         except (ImportError, ValueError):
@@ -69,6 +74,13 @@ def main(argv=None):
     patch_transformers()
     if shimmed:
         print(f"vit2spn.run: stand-ins active for {', '.join(shimmed)} (not installed in this image)", file=sys.stderr)
+    if "medmnist" in shimmed:
+        print("vit2spn.run: *** SYNTHETIC DATA *** medmnist is not installed and V2S_SYNTHETIC_DATA=1: every dataset the "
+              "script loads is FABRICATED (seeded stripes + noise, random labels); losses, accuracies and AUCs of this run "
+              "say nothing about OCT images", flush=True)
+    elif "medmnist" not in sys.modules and importlib.util.find_spec("medmnist") is None:
+        print("vit2spn.run: medmnist is not installed; set V2S_SYNTHETIC_DATA=1 to run on fabricated OCTMNIST-shaped data",
+              file=sys.stderr)
     # the fine-tune scripts savefig into this directory without creating it (ref:octmnist_ft_vit2spn.py:166)
     os.makedirs("./ssp_retinaloct_tbme/vit2spn_tiny/result", exist_ok=True)
     sys.argv = [script] + argv[1:]
