@@ -4,11 +4,13 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
 
-A "step" is one full SSP step of the reference recipe with accumulation_steps=1:
-zero_grad → 4 backbones forward (2 online with grad, 2 EMA targets) → heads → -mean(cos)/1 →
-backward → [gradient all-reduce if N>1] → Adam(lr 1e-4) → EMA(0.999), on one batch of 128 synthetic
-OCTMNIST-shaped pairs per GPU (uint8 28x28 → bilinear 224 → 3ch → ImageNet-normalised fp32).
-Prints ONE JSON line on rank 0.
+A "step" (default workload `ssp`) is one full SSP step of the reference recipe with accumulation_steps=1
+(BASELINE.md §3): zero_grad → 4 backbones forward (2 online with grad, 2 EMA targets) → heads → -mean(cos)/1 →
+backward → [gradient all-reduce, overlapped with backward, if N>1] → Adam(lr 1e-4) → EMA(0.999), on one batch of 128
+synthetic OCTMNIST-shaped pairs per GPU (uint8 28x28 → bilinear 224 → 3ch → ImageNet-normalised fp32).
+Other workloads (`--workload`): `accum8` = the reference recipe proper (8 micro-steps per optimizer step, ref:39,
+215), `finetune` = FineTunedModel step (BASELINE config 4), `eval1024` = forward-only feature extraction at batch
+1024 (config 5).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -21,11 +23,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 # random-init ViT-Tiny weights by specification (north_star: no ImageNet checkpoint offline)
 os.environ.setdefault("V2S_ALLOW_RANDOM_INIT", "1")
+# the gradient all-reduce overlaps the backward pass on the SMs the compute grids leave free (parallel.py)
+os.environ.setdefault("NCCL_MAX_CTAS", "8")
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 FLOP_PER_PAIR = 19.945e9          # algorithmic FLOPs of one pair per micro-step
+FLOP_PER_IMAGE_FT = 7.463e9       # fine-tune step per image, FLOP_PER_IMAGE_FWD forward only
+FLOP_PER_IMAGE_FWD = 2.507e9
 METRIC = "dual-view SSP pairs/sec, ViT-Tiny b128/GPU"
+COMM_SMS = 8
 
 
 def parse():
@@ -34,11 +41,17 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=128, help="pairs per GPU")
+    ap.add_argument("--workload", default="ssp", choices=["ssp", "accum8", "finetune", "eval1024"])
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default 128; eval1024: 1024)")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp16", "fp32"])
-    ap.add_argument("--cpu-batch", type=int, default=8, help="bounded CPU sample (pairs per CPU step)")
+    ap.add_argument("--cpu-batch", type=int, default=32, help="bounded CPU sample (pairs per CPU step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-input", default="u8", choices=["u8", "fp32"],
+                    help="host format of the e2e leg: raw uint8 28x28 source images (0.2 MB/step, resized on the GPU) or "
+                         "the reference DataLoader's fp32 views (154 MB/step)")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: plain all-reduce after backward instead of the overlapped one")
     return ap.parse_args()
 
 
@@ -46,7 +59,7 @@ def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
     except Exception:
-        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -141,7 +154,8 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = args.cpu_batch * args.steps / dt
     sample = (f"{args.steps} full SSP steps (fwd+bwd+Adam+EMA, fp32) of {args.cpu_batch} pairs each on "
-              f"{cores} host threads; oracle port of the reference algorithm")
+              f"{cores} host threads; oracle port of the reference algorithm (bounded sample of the 128-pair batch: "
+              "a 128-pair fp32 step is ~13 GB of autograd state and tens of seconds on these cores)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -172,6 +186,49 @@ def emit(line):
     os.write(_STDOUT_FD if _STDOUT_FD is not None else 1, (json.dumps(line) + "\n").encode())
 
 
+def eager_gpu_baseline(dev, B):
+    """The practical bar of SURVEY §8(d): the reference's own PyTorch path (the oracle's restatement of its classes)
+    under bf16 autocast on THIS GPU — stock eager kernels (cuBLAS / SDPA), full step incl. Adam + EMA."""
+    import torch
+    from oracle import vit2spn_oracle as orc
+    state = {k: v.to(dev) for k, v in orc.init_state(42, 0.0).items()}
+    x1, x2 = (t.to(dev) for t in orc.synthetic_views(B, seed=0))
+    names = orc.trainable_names()
+    params = [state[k].clone().requires_grad_(True) for k in names]
+    opt = torch.optim.Adam(params, lr=1e-4)
+
+    def step():
+        st = dict(state)
+        st.update(dict(zip(names, params)))
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            p, t = orc.dual_stream_forward(st, x1, x2)
+        loss = orc.ssp_loss(p.float(), t.float())
+        loss.backward()
+        opt.step()
+        with torch.no_grad():                       # EMA as one foreach pass (kinder than the reference's Python loop)
+            for o, t_ in (("online_network_1", "target_network_1"), ("online_network_2", "target_network_2")):
+                ks = list(orc.backbone_param_shapes())
+                tg = [state[f"{t_}.vit.{k}"] for k in ks]
+                on = [st[f"{o}.vit.{k}"].detach() for k in ks]
+                torch._foreach_mul_(tg, 0.999)
+                torch._foreach_add_(tg, on, alpha=0.001)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 5
+    e0.record()
+    for _ in range(n):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return {"value": B / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "steps": n,
+            "what": "oracle restatement of the reference classes, torch.autocast(bf16), torch.optim.Adam, foreach EMA, "
+                    f"batch {B}, same GPU (stock PyTorch kernels)"}
+
+
 def main():
     args = parse()
     claim_stdout()
@@ -191,35 +248,82 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
+    B = args.batch or (1024 if args.workload == "eval1024" else 128)
     vit2spn.set_compute_mode(args.mode)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-
-    # ---- model, optimizer, synthetic device-resident data -------------------------------------
-    torch.manual_seed(42)
-    model = vit2spn.DualStreamNetwork().to(dev).train()
-    vit2spn.parallel.broadcast_parameters(model)     # identical replicas
-    opt = vit2spn.FusedAdam(model.parameters(), lr=1e-4)
-    # seeded raw OCTMNIST-shaped source images, uint8 [2B,1,28,28]; rank-dependent seed
-    u8 = torch.from_numpy(np.random.default_rng(1000 + rank).integers(0, 256, size=(2 * B, 1, 28, 28), dtype=np.uint8)).to(dev)
-    views = torch.empty(2, B, 3, 224, 224, device=dev)
     _lib.init_device(local)
-    _lib.check(_lib.lib.v2s_preprocess_u8(_lib.ptr(u8), _lib.ptr(views), 2 * B, _lib.stream_ptr()))
+
+    # ---- synthetic data: seeded raw OCTMNIST-shaped source images, uint8 [2B,1,28,28]; rank-dependent --
+    u8_host = torch.from_numpy(np.random.default_rng(1000 + rank).integers(0, 256, size=(2 * B, 1, 28, 28), dtype=np.uint8))
+    u8 = u8_host.to(dev)
+    views = torch.empty(2, B, 3, 224, 224, device=dev)
+
+    def preprocess(src_u8, dst):
+        _lib.check(_lib.lib.v2s_preprocess_u8(_lib.ptr(src_u8), _lib.ptr(dst), 2 * B, _lib.stream_ptr()))
+    preprocess(u8, views)
     x1, x2 = views[0], views[1]
 
-    def grads_allreduce():
-        if world > 1:      # one collective per optimizer step over 3 flat fp32 buckets; 1/world folded into Adam
-            vit2spn.parallel.allreduce_gradients(model, optimizer=opt)
+    # ---- model / optimizer / step of the chosen workload --------------------------------------------------------
+    torch.manual_seed(42)
+    sync = None
+    if args.workload in ("ssp", "accum8"):
+        model = vit2spn.DualStreamNetwork().to(dev).train()
+        vit2spn.parallel.broadcast_parameters(model)     # identical replicas
+        opt = vit2spn.FusedAdam(model.parameters(), lr=1e-4)
+        if world > 1 and not args.no_overlap:
+            sync = vit2spn.parallel.OverlappedGradSync(model, splits=(8, 4), comm_sms=COMM_SMS)
+        micro = 8 if args.workload == "accum8" else 1
 
-    def step(a, b):
-        loss = model.ssp_step(a, b, accumulation_steps=1)
-        grads_allreduce()
-        opt.step()
-        opt.zero_grad()
-        model.update_target_network()
-        return loss
+        def step(a, b):
+            loss = None
+            for i in range(micro):
+                last = i == micro - 1
+                loss = model.ssp_step(a, b, accumulation_steps=micro, grad_sync=sync if (last and world > 1) else None)
+            if world > 1:
+                if sync is not None:
+                    sync.finish(opt)
+                else:       # one collective per optimizer step over 3 flat fp32 buckets; 1/world folded into Adam
+                    vit2spn.parallel.allreduce_gradients(model, optimizer=opt)
+            opt.step()
+            opt.zero_grad()
+            model.update_target_network()
+            return loss
+        units_per_step, unit, flop_per_unit = B * micro, "pairs/s", FLOP_PER_PAIR
+        metric = METRIC
+        workload = ("ViT-Tiny dual-stream SSP full step (4 backbones fwd, 2 bwd, heads, cosine loss, Adam lr 1e-4, EMA 0.999), "
+                    + ("accumulation 1, batch 128/GPU (BASELINE config 2)" if micro == 1 else
+                       "reference recipe: 8 accumulated micro-steps of 128 pairs per optimizer step (ref:39,215)"))
+    elif args.workload == "finetune":
+        model = vit2spn.FineTunedModel(num_classes=4).to(dev).train()
+        opt = vit2spn.FusedAdam(model.parameters(), lr=1e-4, weight_decay=1e-4)          # ref:octmnist_ft_vit2spn.py:192
+        y = (torch.arange(B, device=dev) % 4)
+        crit = torch.nn.CrossEntropyLoss(weight=torch.tensor([1.0, 2.0, 0.5, 1.5], device=dev))
+
+        def step(a, b):
+            opt.zero_grad()
+            loss = crit(model(a), y)
+            loss.backward()
+            if world > 1:       # BatchNorm1d statistics stay per-rank (the reference is single-GPU); gradients are averaged
+                for p in model.parameters():
+                    if p.grad is not None:
+                        dist.all_reduce(p.grad)
+                opt.grad_multiplier = 1.0 / world
+            opt.step()
+            return loss.detach()
+        units_per_step, unit, flop_per_unit = B, "images/s", FLOP_PER_IMAGE_FT
+        metric = "ViT-2SPN fine-tune images/sec, ViT-Tiny b128/GPU (BASELINE config 4)"
+        workload = "FineTunedModel step: backbone fwd+bwd, BatchNorm/Dropout head (torch), weighted CE, Adam lr 1e-4 + L2 1e-4"
+    else:
+        model = vit2spn.FineTunedModel(num_classes=4).to(dev).eval()
+
+        def step(a, b):
+            with torch.no_grad():
+                return torch.softmax(model(a), dim=1)[:, 0].sum()
+        units_per_step, unit, flop_per_unit = B, "images/s", FLOP_PER_IMAGE_FWD
+        metric = "forward-only feature extraction images/sec, ViT-Tiny b1024 (BASELINE config 5)"
+        workload = "FineTunedModel eval forward (backbone + head + softmax), batch 1024, no_grad (ref:octmnist_ft_vit2spn.py:129-137)"
 
     def barrier():
         if world > 1:
@@ -241,8 +345,10 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    opt.zero_grad()
-    for _ in range(max(args.warmup, 3)):
+    if hasattr(model, "ssp_step"):
+        opt.zero_grad()
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step(x1, x2)
     l0 = _lib.lib.v2s_launch_count()
     sampler.mark_begin()
@@ -259,14 +365,26 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     flag = _lib.lib.v2s_debug_flag()
     ms_per_step = ms_total / args.steps
-    value = world * B * args.steps / (ms_total * 1e-3)
+    value = world * units_per_step * args.steps / (ms_total * 1e-3)
 
-    # ---- end to end: host fp32 views (the reference's DataLoader contract, ref:206-207) → pinned H2D
-    #      every step (double-buffered on a copy stream) + loss.item() D2H every step ---------------
+    # ---- end to end through the public API with HOST buffers: every step copies its inputs from pinned host memory
+    #      (double-buffered on a copy stream) and reads its result back on the host ------------------------------
     e2e = None
     if not args.no_e2e:
-        host = [views[i].cpu().pin_memory() for i in range(2)]
-        bufs = [torch.empty_like(views) for _ in range(2)]
+        if args.e2e_input == "u8":
+            # the dataset's native format (28x28 uint8, ref:ssp_vit2spn_tiny.py:100-104): 2*B*784 bytes per step; the
+            # resize / normalise of the reference's transform runs on the GPU inside the timed region
+            host = u8_host.pin_memory()
+            raw = [torch.empty_like(u8) for _ in range(2)]
+            bufs = [torch.empty_like(views) for _ in range(2)]
+            h2d = int(host.numel())
+            what = ("raw uint8 source images [2B,1,28,28] in pinned host memory → H2D → bilinear 224 / 3 channels / "
+                    "normalise on the GPU (v2s_preprocess_u8) → step")
+        else:
+            host = [views[i].cpu().pin_memory() for i in range(2)]
+            bufs = [torch.empty_like(views) for _ in range(2)]
+            h2d = int(2 * B * 3 * 224 * 224 * 4)
+            what = "fp32 views [2,B,3,224,224] in pinned host memory (the reference DataLoader's format), double-buffered H2D"
         copy_stream = torch.cuda.Stream()
         ready = [torch.cuda.Event() for _ in range(2)]
         done = [torch.cuda.Event() for _ in range(2)]
@@ -274,11 +392,15 @@ def main():
         def upload(i):
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(done[i])
-                bufs[i][0].copy_(host[0], non_blocking=True)
-                bufs[i][1].copy_(host[1], non_blocking=True)
+                if args.e2e_input == "u8":
+                    raw[i].copy_(host, non_blocking=True)
+                    preprocess(raw[i], bufs[i])
+                else:
+                    bufs[i][0].copy_(host[0], non_blocking=True)
+                    bufs[i][1].copy_(host[1], non_blocking=True)
                 ready[i].record(copy_stream)
 
-        # the loss of every step is read on the host (ref:220 `loss.item()`), through a pinned buffer and an event,
+        # the result of every step is read on the host (ref:220 `loss.item()`), through a pinned buffer and an event,
         # one step behind: step k's value is fetched after step k+1 has been enqueued, so the host-side enqueue
         # cost of a step never leaves the GPU idle; the last value is fetched before the timed region closes
         loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -298,11 +420,11 @@ def main():
             i = state["i"]
             torch.cuda.current_stream().wait_event(ready[i])
             loss = step(bufs[i][0], bufs[i][1])
-            loss_host[i].copy_(loss.detach().reshape(()), non_blocking=True)   # D2H of the step's result, every step
+            loss_host[i].copy_(loss.detach().reshape(()).float(), non_blocking=True)   # D2H of the step's result
             loss_ev[i].record()
             done[i].record()
             upload(i)                      # refill this buffer for step i+2 while step i+1 computes
-            fetch()                        # previous step's loss
+            fetch()                        # previous step's result
             state["pending"] = i
             state["i"] = i ^ 1
 
@@ -312,12 +434,10 @@ def main():
         fetch()
         ms_e2e = timed(e2e_step, args.steps, finish=fetch)
         if state["last"] is None or state["last"] != state["last"]:
-            raise RuntimeError("e2e: loss readback failed")
-        e2e = {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s",
-               "h2d_bytes_per_step": int(2 * B * 3 * 224 * 224 * 4), "d2h_bytes_per_step": 4,
-               "ms_per_step": ms_e2e / args.steps,
-               "input": "fp32 views [2,B,3,224,224] in pinned host memory, double-buffered H2D on a copy stream",
-               "result": "loss of every step copied to pinned host memory and read there, one step behind the enqueue"}
+            raise RuntimeError("e2e: result readback failed")
+        e2e = {"value": world * units_per_step * args.steps / (ms_e2e * 1e-3), "unit": unit,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "input": what,
+               "result": "the step's loss / output checksum copied to pinned host memory and read there, one step behind the enqueue"}
 
     # ---- per-kernel-class device timing (CUDA events on the launching stream) → roofline ---------
     pk, pk_src = peaks()
@@ -327,66 +447,94 @@ def main():
         step(x1, x2)
     rep = _lib.prof_report()
     _lib.prof_enable(False)
-    classes = {k: {"launches": n // nprof, "ms_per_step": ms / nprof, "work_per_step": w / nprof,
-                   "bytes_per_step": nb / nprof} for k, (n, ms, w, nb) in rep.items()}
+    classes = {}
+    for k, (n, ms, w, nb) in rep.items():
+        c = {"launches": n // nprof, "ms_per_step": ms / nprof, "work_per_step": w / nprof, "bytes_per_step": nb / nprof}
+        sec = c["ms_per_step"] * 1e-3
+        is_tc = k.startswith("gemm") or k.startswith("attn")
+        c["achieved_GBps"] = c["bytes_per_step"] / sec / 1e9 if sec > 0 else None
+        c["frac_of_hbm_peak"] = c["achieved_GBps"] / pk["hbm_gbs"] if sec > 0 else None
+        if is_tc and sec > 0:
+            c["achieved_TFLOPs"] = c["work_per_step"] / sec / 1e12
+            c["frac_of_bf16_burst_peak"] = c["achieved_TFLOPs"] / pk["bf16_tflops"]
+            c["bound"] = "hbm" if c["bytes_per_step"] / (pk["hbm_gbs"] * 1e9) >= c["work_per_step"] / (pk["bf16_tflops_sustained"] * 1e12) else "tensor"
+        else:
+            c["bound"] = "hbm"
+        classes[k] = c
     tensor_classes = [k for k in classes if k.startswith("gemm") or k.startswith("attn")]
+    step_tflops = value / world * flop_per_unit / 1e12
     roofline = None
+    traffic_file = "ncu_r02_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "ncu_r02_traffic.json")) else "ncu_r01_traffic.json"
     try:
-        ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_r01_traffic.json")))
+        ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", traffic_file)))
     except Exception:
         ncu_traffic = {}
     if tensor_classes:
         # dominant kernel class by device time; its bound is whichever roofline time is larger for its
-        # ALGORITHMIC flops / bytes (operands and outputs once); burst peaks do not apply inside a step
+        # ALGORITHMIC flops / bytes (operands and outputs once)
         dom = max(tensor_classes, key=lambda k: classes[k]["ms_per_step"])
         c = classes[dom]
-        t_tensor = c["work_per_step"] / (pk["bf16_tflops_sustained"] * 1e12)
-        t_hbm = c["bytes_per_step"] / (pk["hbm_gbs"] * 1e9)
-        sec = c["ms_per_step"] * 1e-3
         tr = ncu_traffic.get(dom, {}).get("dram_bytes_per_launch")
-        if t_hbm >= t_tensor:
-            ach = c["bytes_per_step"] / sec / 1e9
-            roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                        "frac": ach / pk["hbm_gbs"], "traffic": tr, "peak_source": f"hbm_gbs ({pk_src})"}
+        if c["bound"] == "hbm":
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": c["achieved_GBps"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": c["frac_of_hbm_peak"], "traffic": tr, "peak_source": f"hbm_gbs ({pk_src})"}
         else:
-            ach = c["work_per_step"] / sec / 1e12
-            roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"],
-                        "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"], "traffic": tr,
-                        "peak_source": f"bf16_tflops_sustained ({pk_src})"}
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": c["achieved_TFLOPs"], "peak": pk["bf16_tflops_sustained"],
+                        "unit": "TFLOP/s", "frac": c["achieved_TFLOPs"] / pk["bf16_tflops_sustained"], "traffic": tr,
+                        "peak_source": f"bf16_tflops_sustained ({pk_src}; the kernel runs inside a long step)"}
         roofline.update({"launches_per_step": c["launches"], "ms_per_step": c["ms_per_step"],
                          "share_of_step": c["ms_per_step"] / ms_per_step,
                          "algorithmic_bytes_per_launch": c["bytes_per_step"] / max(c["launches"], 1),
                          "algorithmic_flops_per_launch": c["work_per_step"] / max(c["launches"], 1),
                          "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, "
-                                           "profiles/ncu_r01_traffic.json (cold-cache capture)"})
-    step_tflops = value / world * FLOP_PER_PAIR / 1e12
+                                           f"profiles/{traffic_file} (cold-cache capture)",
+                         # the step as a whole against the bf16 tensor roofline, both denominators
+                         "step": {"algorithmic_tflops_per_gpu": step_tflops,
+                                  "frac_of_bf16_burst_peak": step_tflops / pk["bf16_tflops"],
+                                  "frac_of_bf16_sustained_peak": step_tflops / pk["bf16_tflops_sustained"],
+                                  "algorithmic_hbm_bytes_per_step": sum(v["bytes_per_step"] for v in classes.values()),
+                                  "hbm_floor_ms": sum(v["bytes_per_step"] for v in classes.values()) / (pk["hbm_gbs"] * 1e9) * 1e3,
+                                  "tensor_floor_ms": units_per_step * flop_per_unit / (pk["bf16_tflops"] * 1e12) * 1e3},
+                         "classes": {k: {kk: v[kk] for kk in ("launches", "ms_per_step", "bound", "achieved_GBps", "frac_of_hbm_peak",
+                                                               "achieved_TFLOPs", "frac_of_bf16_burst_peak") if kk in v}
+                                     for k, v in sorted(classes.items(), key=lambda kv: -kv[1]["ms_per_step"])}})
 
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cstep, cores = cpu_reference_step_fn(args.cpu_batch)
-        cstep()
-        n = 0
-        t0 = time.perf_counter()
-        while n < 3 or (time.perf_counter() - t0 < 12 and n < 30):
-            cstep(); n += 1
-        dt = time.perf_counter() - t0
-        cpu_baseline = {"value": args.cpu_batch * n / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
-                        "sample": f"{n} full SSP steps (fwd+bwd+Adam+EMA, fp32) of {args.cpu_batch} pairs each; "
-                                  "oracle port of the reference algorithm (the reference's CPU path is torch fp32)"}
+    cpu_baseline = gpu_eager = None
+    if rank == 0 and world == 1 and args.workload == "ssp":
+        if not args.no_eager_baseline:
+            torch.cuda.empty_cache()
+            try:
+                gpu_eager = eager_gpu_baseline(dev, B)
+            except Exception as e:  # noqa: BLE001  (a baseline must never take the line down)
+                gpu_eager = {"error": str(e)[:200]}
+        if not args.no_cpu_baseline:
+            cstep, cores = cpu_reference_step_fn(args.cpu_batch)
+            cstep()
+            n = 0
+            t0 = time.perf_counter()
+            while n < 3 or (time.perf_counter() - t0 < 15 and n < 30):
+                cstep(); n += 1
+            dt = time.perf_counter() - t0
+            cpu_baseline = {"value": args.cpu_batch * n / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+                            "sample": f"{n} full SSP steps (fwd+bwd+Adam+EMA, fp32) of {args.cpu_batch} pairs each; "
+                                      "oracle port of the reference algorithm (the reference's CPU path is torch fp32)"}
 
     if rank == 0:
+        par = f"dp{world}"
+        if world > 1:
+            par += (" (gradient all-reduce in 4 buckets overlapped with backward, 1/world folded into Adam)" if sync is not None
+                    else " (3 flat all-reduces after backward)")
         line = {
-            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.mode, "data": "synthetic",
-            "config": {"workload": "ViT-Tiny dual-stream SSP full step (4 backbones fwd, 2 bwd, heads, cosine loss, "
-                                   "Adam lr 1e-4, EMA 0.999), accumulation 1, batch 128/GPU (BASELINE config 2)",
-                       "batch_per_gpu": B, "parallelism": f"dp{world}",
+            "config": {"workload": workload, "batch_per_gpu": B, "parallelism": par,
                        "l2": "inputs (154 MB/step) and activations (>2 GB/step) exceed the 126 MB L2; no explicit flush"},
             "step_tflops_per_gpu": step_tflops,
-            "step_frac_of_bf16_peak": step_tflops / pk["bf16_tflops_sustained"],
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks, "kernel_classes": classes, "debug_flag": flag, "host_enqueue_ms_per_step": host_ms,
+            "step_frac_of_bf16_peak": step_tflops / pk["bf16_tflops"],
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "gpu_eager_baseline": gpu_eager, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clocks, "kernel_classes": classes, "debug_flag": flag,
+            "host_enqueue_ms_per_step": host_ms,
         }
         emit(line)
     if world > 1:

@@ -104,6 +104,13 @@ int v2s_backbone_forward(const v2s_group_t* host_groups, int n_groups, int batch
 /* autograd backward of the above for the groups with slot >= 0 (ref:213 loss.backward()) */
 int v2s_backbone_backward(const v2s_group_t* host_groups, int n_groups, int batch, int mode,
                           void* workspace, int64_t workspace_bytes, void* stream);
+/* The same for blocks [layer_lo, layer_hi) only, highest block first.  layer_hi == V2S_LAYERS starts from dfeat /
+ * dhidden; layer_lo == 0 ends with the embedding gradients; the residual-stream gradient is carried between calls in
+ * the workspace.  The flat gradient layout is block-contiguous, so after the call for [lo, hi) the gradients of those
+ * blocks are final: a data-parallel host can all-reduce that slice while the next range computes. */
+int v2s_backbone_backward_range(const v2s_group_t* host_groups, int n_groups, int batch, int mode,
+                                void* workspace, int64_t workspace_bytes, int layer_hi, int layer_lo,
+                                void* stream);
 
 /* projection_head + prediction_head on the concatenated online features and projection_head on
  * the target features (ref:ssp_vit2spn_tiny.py:153-158), fused with the loss

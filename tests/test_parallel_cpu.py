@@ -53,6 +53,29 @@ def _worker(rank, world, port, q):
         assert all(torch.equal(lst[0], t) for t in lst)
         with pytest.raises(ValueError):
             parallel.shard_batch(torch.zeros(5, 1), rank, world)
+        # the overlapped, range-wise all-reduce (what bench.py uses at N > 1): put the rank-local oracle gradients into
+        # the model's flat gradient buffers, drive the hooks in the order ssp_step does, and compare with the average
+        gmap = dict(model.named_parameters())
+        for s_ in model._stores()[:2] + [model._head_store]:
+            s_.grads()
+        with torch.no_grad():
+            for n in names:
+                gmap[n].grad.copy_(grads[n])
+        sync = parallel.OverlappedGradSync(model, splits=(9, 5, 2), comm_sms=0)
+        assert sync.ranges == [(12, 9), (9, 5), (5, 2), (2, 0)]
+        sync.begin()
+        sync.heads_ready()
+        for hi, lo in sync.ranges:
+            sync.range_ready(hi, lo)
+        assert sync.finish(optimizer=None) == world              # no optimizer given: the mean is applied in place
+        if rank == 0:
+            q.put({n: gmap[n].grad.numpy().copy() for n in names})     # by value (numpy), not via shared memory
+        covered = torch.zeros(model._stores()[0].active_numel, dtype=torch.int32)
+        for hi, lo in sync.ranges:
+            sl = sync._slice(model._stores()[0], hi, lo)
+            off = (sl.data_ptr() - model._stores()[0].flat_grad.data_ptr()) // 4
+            covered[off:off + sl.numel()] += 1
+        assert bool((covered == 1).all()), "every active gradient element must be reduced exactly once"
     finally:
         dist.destroy_process_group()
 
@@ -66,6 +89,7 @@ def test_two_rank_gradient_average_equals_full_batch():
     for p in procs:
         p.start()
     mean_loss, buckets, groups = q.get()
+    overlapped = q.get()
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
@@ -77,3 +101,6 @@ def test_two_rank_gradient_average_equals_full_batch():
         ref = torch.cat([grads[n].flatten() for n in grp])
         rel = float((bk - ref).norm() / ref.norm())
         assert rel < 1e-5, rel
+    num = sum(float(((torch.from_numpy(overlapped[n]) - grads[n]) ** 2).sum()) for n in grads)
+    den = sum(float((grads[n] ** 2).sum()) for n in grads)
+    assert (num / den) ** 0.5 < 1e-5

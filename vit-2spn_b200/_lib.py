@@ -55,6 +55,7 @@ _SIGS = {
     "v2s_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "v2s_backbone_forward": (C.c_int, [C.POINTER(Group), _i, _i, _i, _vp, _i64, _vp]),
     "v2s_backbone_backward": (C.c_int, [C.POINTER(Group), _i, _i, _i, _vp, _i64, _vp]),
+    "v2s_backbone_backward_range": (C.c_int, [C.POINTER(Group), _i, _i, _i, _vp, _i64, _i, _i, _vp]),
     "v2s_heads_loss_fwd_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i,
                                          _vp, _i64, _vp]),
     "v2s_heads_loss_fwd_bwd_amp": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i,

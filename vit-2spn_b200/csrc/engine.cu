@@ -169,10 +169,14 @@ int max_slot(const v2s_group_t* g, int n) {
 int run_gemm(const GemmDesc& d, int ta, int tb, int to, cudaStream_t s, int cls = prof::C_MISC) {
   // algorithmic HBM bytes: both operands and the output once (+ residual / auxiliary operand, second output)
   const double ea = ta ? 2.0 : 4.0, eb = tb ? 2.0 : 4.0, eo = to ? 2.0 : 4.0;
-  double bytes = (double)d.M * d.K * ea + (double)d.N * d.K * eb + (double)d.M * d.N * eo;
-  if (d.epi == EPI_BIAS_RESID) bytes += (double)d.M * d.N * 4.0 + (d.ln_out[0] ? (double)d.M * d.N * 2.0 : 0.0);
-  if (d.epi == EPI_DGELU || (d.epi == EPI_BIAS_GELU && d.out[0])) bytes += (double)d.M * d.N * 2.0;
-  prof::Scope scope(cls, 2.0 * d.M * d.N * (double)d.K * d.groups, s, bytes * d.groups);
+  double bytes = 0.0;
+  for (int g = 0; g < d.groups; ++g) {
+    bytes += (double)d.M * d.K * ea + (double)d.N * d.K * eb + (double)d.M * d.N * eo;
+    if (d.epi == EPI_BIAS_RESID) bytes += (double)d.M * d.N * 4.0 + (d.ln_out[g] ? (double)d.M * d.N * 2.0 : 0.0);
+    // second 16-bit tensor: gelu'(u) operand of the dgrad epilogue; the pre-GELU store only for groups that keep it
+    if (d.epi == EPI_DGELU || (d.epi == EPI_BIAS_GELU && d.out[g])) bytes += (double)d.M * d.N * 2.0;
+  }
+  prof::Scope scope(cls, 2.0 * d.M * d.N * (double)d.K * d.groups, s, bytes);
   int handled = 0;
   V2S_TRY(launch_gemm_tc(d, ta, tb, to, s, &handled));
   if (handled) return 0;
@@ -422,8 +426,12 @@ static int backbone_forward_impl(const v2s_group_t* gs, int G, int B, int mode, 
 // =============================================================================================
 // backbone backward
 // =============================================================================================
+// layers [layer_lo, layer_hi) in descending order; layer_hi == NL starts from the feature / hidden-state gradient,
+// layer_lo == 0 finishes with the embedding gradients.  Between two calls the residual-stream gradient lives in the
+// workspace, so a full backward may be issued in several ranges (gradient all-reduce overlapped per range).
 static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int mode, void* ws, int64_t ws_bytes,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, int layer_hi = NL, int layer_lo = 0) {
+  if (layer_lo < 0 || layer_hi > NL || layer_lo >= layer_hi) { set_error("backbone_backward: bad layer range [%d, %d)", layer_lo, layer_hi); return 1; }
   // keep only the groups that saved activations and want gradients
   v2s_group_t gs[MAXG];
   int G = 0;
@@ -443,14 +451,14 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
   {
     const float *df[MAXG], *dh[MAXG]; int64_t dfs[MAXG]; void* lp[MAXG];
     for (int g = 0; g < G; ++g) {
-      if (!gs[g].dfeat && !gs[g].dhidden) { set_error("backbone_backward: group needs dfeat or dhidden"); return 1; }
+      if (layer_hi == NL && !gs[g].dfeat && !gs[g].dhidden) { set_error("backbone_backward: group needs dfeat or dhidden"); return 1; }
       dx[g] = (float*)bb(g, p.b_dx);
       dxlp[g] = at ? (void*)bb(g, p.b_dxlp) : (void*)dx[g];
       big[g] = bb(g, p.b_big); tmp[g] = bb(g, p.b_tmp);
       df[g] = gs[g].dfeat; dfs[g] = gs[g].dfeat_stride > 0 ? gs[g].dfeat_stride : D; dh[g] = gs[g].dhidden;
       lp[g] = at ? dxlp[g] : nullptr;
     }
-    V2S_TRY(launch_pool_bwd(df, dfs, dh, dx, lp, G, B, at, st));
+    if (layer_hi == NL) V2S_TRY(launch_pool_bwd(df, dfs, dh, dx, lp, G, B, at, st));
   }
 
   const int split = wgrad_split(M);
@@ -500,7 +508,7 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
     return launch_colsum(src, dst, G, (int)M, n, at, st);
   };
 
-  for (int l = NL - 1; l >= 0; --l) {
+  for (int l = layer_hi - 1; l >= layer_lo; --l) {
     const int64_t lo = layer_off(l);
     const LayerStash& s = p.s_layer[l];
     void *u[MAXG], *h[MAXG], *xn2[MAXG], *ctx[MAXG], *qkv[MAXG], *xn1[MAXG];
@@ -571,7 +579,7 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
     }
   }
   // ---- embeddings: d pos, d cls, d patch bias, d patch weight ----
-  {
+  if (layer_lo == 0) {
     const float* cdx[MAXG]; float* gr[MAXG]; void* pt[MAXG];
     for (int g = 0; g < G; ++g) { cdx[g] = dx[g]; gr[g] = gs[g].grads; pt[g] = sb(g, p.s_patches); }
     V2S_TRY(launch_embed_bwd(cdx, gr, G, B, st));
@@ -793,6 +801,13 @@ int v2s_backbone_backward(const v2s_group_t* groups, int n_groups, int batch, in
                           int64_t workspace_bytes, void* stream) {
   if (!groups) { set_error("null groups"); return 1; }
   return backbone_backward_impl(groups, n_groups, batch, mode, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int v2s_backbone_backward_range(const v2s_group_t* groups, int n_groups, int batch, int mode, void* workspace,
+                                int64_t workspace_bytes, int layer_hi, int layer_lo, void* stream) {
+  if (!groups) { set_error("null groups"); return 1; }
+  return backbone_backward_impl(groups, n_groups, batch, mode, workspace, workspace_bytes, (cudaStream_t)stream, layer_hi,
+                                layer_lo);
 }
 
 int v2s_heads_loss_fwd_bwd(const float* head_params, float* head_grads, const float* feat_online,

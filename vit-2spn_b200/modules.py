@@ -256,6 +256,13 @@ def _run_backward(groups, batch, mode, ws):
           "backbone_backward")
 
 
+def _run_backward_range(groups, batch, mode, ws, layer_hi, layer_lo):
+    arr = (Group * len(groups))(*groups)
+    base, nbytes = _aligned(ws)
+    check(lib.v2s_backbone_backward_range(arr, len(groups), batch, mode, C.c_void_p(base), nbytes, int(layer_hi),
+                                          int(layer_lo), stream_ptr()), "backbone_backward_range")
+
+
 def _group(store, mode, x, slot, grads=None, hidden=None, feat=None, feat_stride=0, dfeat=None,
            dfeat_stride=0, dhidden=None):
     g = Group()
@@ -724,12 +731,14 @@ class DualStreamNetwork(nn.Module):
 
     # -- fused native step (no autograd graph): fwd + loss + bwd in the library --------------
     @_with_device_of(lambda self, x1, *a, **k: x1)
-    def ssp_step(self, x1, x2, accumulation_steps=1, grad_scale=1.0, with_backward=True):
+    def ssp_step(self, x1, x2, accumulation_steps=1, grad_scale=1.0, with_backward=True, grad_sync=None):
         """One micro-step of ref:ssp_vit2spn_tiny.py:209-213 — returns the loss tensor (already divided
         by ``accumulation_steps``, NOT multiplied by the loss scale); gradients are accumulated into ``.grad`` of
         the parameters.  ``grad_scale``: a float, a one-element CUDA tensor, or a ``torch.amp.GradScaler`` (fp16
         mode, ref:213 ``scaler.scale(loss).backward()``): tensor / scaler values are read on the device, no
-        host synchronisation."""
+        host synchronisation.  ``grad_sync`` (data parallel; pass it on optimizer-step boundaries only): a
+        ``vit2spn.parallel.OverlappedGradSync`` — the backward pass is issued in block ranges and each range's finished
+        gradient slice is all-reduced while the next range computes."""
         scale_t = None
         if isinstance(grad_scale, torch.amp.GradScaler):
             if grad_scale.is_enabled():
@@ -779,7 +788,14 @@ class DualStreamNetwork(nn.Module):
                     _group(st[0], mode, x1, 0, grads=st[0].grads(), dfeat=dfeat, dfeat_stride=384),
                     _group(st[1], mode, x2, 1, grads=st[1].grads(), dfeat=dfeat[:, 192:], dfeat_stride=384),
                 ]
-                _run_backward(bw, B, mode, ws)
+                if grad_sync is None:
+                    _run_backward(bw, B, mode, ws)
+                else:
+                    grad_sync.begin()
+                    grad_sync.heads_ready()                      # the head gradients are final before the backbones start
+                    for hi, lo in grad_sync.ranges:
+                        _run_backward_range(bw, B, mode, ws, hi, lo)
+                        grad_sync.range_ready(hi, lo)
         finally:
             self._release_workspace(ws)
         return loss[0]
