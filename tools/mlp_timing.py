@@ -65,8 +65,8 @@ def main():
     if os.environ.get("V2S_GEMM_DEBUG"):
         import ctypes as C
         names_mma = ["acc1_empty", "a1_full", "w_full(S1)", "acc2_empty", "a2_full", "w_full(S2)", "total", "tiles"]
-        names_epi = ["e2_done", "u_full", "acc1_full", "a2_free", "u_free", "acc2_full", "rs_full", "st_free/a2_free(E2)",
-                     "acc2 drain total", "total", "drain:acc2 wait+tmem ld", "drain:chunk loop", "drain:LN barrier"]
+        names_gelu = ["u_full(bwd)", "acc1_full", "a2_free", "u_free(fwd)", "total"]
+        names_drain = ["acc2_full", "rs_full", "dbuf_free", "busy (acc2 complete -> released)", "total"]
         for name, fn in (("fwd target", lambda: fwd(False)), ("fwd online", lambda: fwd(True)), ("bwd", bwd)):
             buf = (C.c_int64 * 32)()
             L.lib.v2s_debug_counters(buf)            # clear
@@ -75,8 +75,9 @@ def main():
             v = list(buf)
             nt = max(v[7], 1)
             print(f"-- {name}: CTA 0, {v[7]} tiles; cycles per tile")
-            print("   MMA warp waits:  " + "  ".join(f"{n} {v[i] / nt:.0f}" for i, n in enumerate(names_mma[:7])))
-            print("   epilogue waits:  " + "  ".join(f"{n} {v[8 + i] / nt:.0f}" for i, n in enumerate(names_epi)))
+            print("   MMA warp waits:     " + "  ".join(f"{n} {v[i] / nt:.0f}" for i, n in enumerate(names_mma[:7])))
+            print("   GELU thread waits:  " + "  ".join(f"{n} {v[8 + i] / nt:.0f}" for i, n in enumerate(names_gelu)))
+            print("   drain thread waits: " + "  ".join(f"{n} {v[13 + i] / nt:.0f}" for i, n in enumerate(names_drain)))
 
 
 if __name__ == "__main__":

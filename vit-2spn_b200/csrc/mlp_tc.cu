@@ -4,27 +4,37 @@
 //                                                   (+ LayerNorm of x_out = LN1 of the next block, fused)
 //   backward (dgrad chain of the same two layers)   du = (dx W2) * gelu'(u);  dxn2 = du W1
 //
-// Persistent CTA (640 threads, one per SM) over the (backbone, 128-row m-tile) jobs.  The intermediate dimension is
-// walked in six chunks of 128 columns:
-//   stage 1   acc1[c&1] (TMEM, 128 cols, double-buffered) = A1[128x192] * B1_chunk          12 UMMAs 128x128x16
-//   epilogue  all 16 epilogue warps take the chunk together (thread = one row x 32 columns): bias+GELU or gelu'(u)
-//             product -> 16-bit -> written as the K-major SWIZZLE_128B A operand of stage 2 into two [128 x 64]
-//             k-block tiles in shared memory
-//   stage 2   acc2 (TMEM, 192 cols) += A2_chunk[128x128] * B2_chunk                          8 UMMAs 128x192x16
-//   after six chunks the epilogue warps drain acc2: forward = + bias + fp32 residual -> x_out, row statistics,
-//   normalised 16-bit row; backward = 16-bit dxn2.
-// The MMA warp issues S1(c+1) before S2(c), so the next accumulator is ready when the epilogue warps finish a chunk.
+// Persistent CTA (768 threads, one per SM) over the (backbone, 128-row m-tile) jobs.  The intermediate dimension is
+// walked in twelve chunks of 64 columns; EVERY hand-over between the roles is double-buffered, so that the three
+// throughput limits of the kernel (tensor pipe, the issue slots of the GELU warps, L2 -> shared-memory weight
+// traffic) overlap instead of adding up:
+//   stage 1   acc1 (TMEM, 128 cols) = A1[128x192] * B1 of a SUPER-chunk (two chunks)         12 UMMAs 128x128x16
+//             (a UMMA costs about 75 + 0.37 N cycles here: N = 64 instructions made the kernel tensor-pipe bound.)
+//             The accumulator is single-buffered but never a bottleneck: the GELU warps pull the whole super-chunk
+//             into registers at once and hand the columns back within ~300 cycles.
+//   GELU      16 warps (thread = one row x 16 columns of each chunk): bias+GELU or gelu'(u) product -> 16-bit -> the
+//             K-major SWIZZLE_128B A operand of stage 2, one [128 x 64] k-block tile A2[c&1] in shared memory
+//   stage 2   acc2[tile&1] (TMEM, 2 x 192 cols) += A2_chunk[128x64] * B2_chunk               4 UMMAs 128x192x16
+//   drain     a separate warpgroup (thread = one row) empties acc2 of tile i while the other roles already work on
+//             tile i+1: forward = + bias + fp32 residual -> x_out, row statistics (the row is parked in its TMEM
+//             columns between the statistics pass and the normalise pass), normalised 16-bit row; backward = 16-bit
+//             dxn2.  (Measured on the previous single-acc2 version of this kernel: the drain, done by the GELU
+//             warps at the end of every tile, was 34 % of the tile time and left the tensor pipe idle.)
+// The MMA warp issues S2(2k-1), S1(k+1), S2(2k) while the GELU warps work on super-chunk k: every wait it meets
+// was satisfied well before.
 //
 // Global traffic of the epilogues goes through TMA only (a thread-per-row access pattern costs 32 LSU wavefronts
-// per instruction: measured 2-3x the whole kernel).  Four 16 KB "epilogue buffers" EB0..3:
-//   EB0/EB1  the A2 k-block tiles; the same tiles are the source of the TMA stores of h (forward, online
-//            backbones only) / du (backward): no separate staging
+// per instruction).  Six 16 KB "epilogue buffers":
+//   EB0/EB1  the A2 k-block tile of even / odd chunks; the same tiles are the source of the TMA stores of h
+//            (forward, online backbones only) / du (backward): no separate staging
 //   EB2/EB3  forward: staging of the pre-GELU activation u (stored for the backward pass of the online backbones);
-//            backward: the u tiles, TMA-loaded one chunk ahead
-//   while acc2 is drained no chunk epilogue runs, so all four buffers stage the residual (TMA load, updated in
-//   place, TMA store) and the normalised rows.
-// A store warp owns every TMA store / epilogue load and the buffer recycling; weights stream from L2 through a
-// 4-slot TMA ring (W1 / W2 chunks: 576 KB per m-tile); A1 (48 KB) is resident per m-tile.
+//            backward: the u tiles, TMA-loaded two chunks ahead
+//   EB4/EB5  the drain's ring: residual chunk in (TMA load) -> updated in place -> x_out chunk out (TMA store);
+//            then the normalised / dxn2 tiles
+// Roles: warp 0 TMA producer (A1 per tile, one 24 KB weight slot per chunk stage, 3-slot ring), warp 1 MMA issuer,
+// warp 2 chunk stores (h, u / du; backward: also the u-tile loads), warp 3 drain stores (x_out, xn / dxn2; forward:
+// also the residual loads, issued the moment the buffer's previous store has been read), warps 4..19 GELU,
+// warps 20..23 drain.
 #include <string.h>
 
 #include "gemm_tc.cuh"
@@ -37,26 +47,28 @@ namespace v2s {
 namespace {
 
 constexpr int BM = 128;                    // rows per m-tile
-constexpr int CW = 128;                    // chunk width along the 768-wide intermediate dimension
-constexpr int NCH = DF / CW;               // 6 chunks
+constexpr int CW = 64;                     // chunk width along the 768-wide intermediate dimension
+constexpr int NCH = DF / CW;               // 12 chunks
 constexpr int KB1 = D / 64;                // 3 k-blocks in stage 1 (K = 192)
-constexpr int KB2 = CW / 64;               // 2 k-blocks per chunk in stage 2
 constexpr int KBLK = BM * 128;             // one [128 rows x 128 B] tile: 16384 B
 constexpr int A1_BYTES = KB1 * KBLK;       // 49152
-constexpr int W_SLOT = 24576;              // holds a stage-1 B k-block (16 KB) or a stage-2 B k-block (24 KB)
+constexpr int SW = 2 * CW;                 // stage 1 runs over super-chunks of two chunks: one N = 128 UMMA series
+constexpr int NSC = DF / SW;               // 6 super-chunks per tile
+constexpr int W_SLOT = 24576;              // holds a stage-1 B k-block [128 x 64] (16 KB) or a stage-2 B block [192 x 64] (24 KB)
 constexpr int W_SLOTS = 3;
 constexpr int OFF_W = A1_BYTES;
 constexpr int N_EB = 6;
-constexpr int OFF_EB = OFF_W + W_SLOTS * W_SLOT;       // 122880: EB0..5
+constexpr int OFF_EB = OFF_W + W_SLOTS * W_SLOT;       // 122880
 constexpr int OFF_BAR = OFF_EB + N_EB * KBLK;          // 221184
-constexpr int OFF_LN = OFF_BAR + 1024;                 // [4 column quarters][128 rows] float2
-constexpr int SMEM_BYTES = OFF_LN + 4 * BM * 8 + 1024;
-constexpr int TM_ACC2 = 256;               // TMEM columns: acc1[0] 0..127, acc1[1] 128..255, acc2 256..447
-constexpr int N_THREADS = 640;             // producer, MMA, store warp, spare warp, 16 epilogue warps
-constexpr int EPI_THREADS = 512;
-constexpr int XCH = D / 32;                // 6 column chunks of 32 when acc2 is drained
+constexpr int SMEM_BYTES = OFF_BAR + 1024 + 1024;
+constexpr int TM_ACC2 = 128;               // TMEM columns: acc1 0..127 (one super-chunk), acc2[s] at 128 + 192 s
+constexpr int N_THREADS = 768;             // 24 warps (see the role list above): 80 registers per thread
+constexpr int GELU_THREADS = 512;
+constexpr int DRAIN_THREADS = 128;
+constexpr int XCH = D / 32;                // 6 column chunks of 32 fp32 when acc2 is drained (forward)
 static_assert(SMEM_BYTES <= 232448, "shared-memory budget");
 static_assert(OFF_W % 1024 == 0 && OFF_EB % 1024 == 0 && W_SLOT % 1024 == 0, "swizzled tiles need 1024-byte alignment");
+static_assert(NCH % 2 == 0, "per-buffer phase bookkeeping assumes an even number of chunks per tile");
 
 struct alignas(64) MlpParams {
   CUtensorMap tmA[MAXG], tmB1[MAXG], tmB2[MAXG];
@@ -70,7 +82,7 @@ struct alignas(64) MlpParams {
   int has_h[MAXG], has_u[MAXG], has_ln[MAXG];
   int M, tiles_m, total_tiles, late_wait;
   int* err_flag;
-  long long* dbg;   // optional cycle counters of CTA 0 (V2S_GEMM_DEBUG): [0..7] MMA warp waits, [8..19] epilogue thread waits
+  long long* dbg;   // optional cycle counters of CTA 0 (V2S_GEMM_DEBUG): see the end of each role
 };
 
 template <int MODE, typename LP, bool DBG>
@@ -79,23 +91,20 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* a1_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* a1_empty = a1_full + 1;
-  uint64_t* w_full = a1_empty + 1;          // [4]
-  uint64_t* w_empty = w_full + W_SLOTS;     // [4]
-  uint64_t* acc1_full = w_empty + W_SLOTS;  // [2]
-  uint64_t* acc1_empty = acc1_full + 2;     // [2] one arrival per epilogue warp
-  uint64_t* a2_full = acc1_empty + 2;       // [2] 256 arrivals: the threads that write the k-block tile
-  uint64_t* a2_free = a2_full + 2;          // [2] 2 arrivals: stage-2 UMMAs retired + store warp (h / du store has read it)
-  uint64_t* u_full = a2_free + 2;           // [2] forward: 256 arrivals (u staged); backward: TMA load of the u tile landed
-  uint64_t* u_free = u_full + 2;            // [2] forward: store warp (u store has read it); backward: 256 readers done
-  uint64_t* acc2_full = u_free + 2;
-  uint64_t* acc2_empty = acc2_full + 1;     // one arrival per epilogue warp
-  uint64_t* rs_full = acc2_empty + 1;       // [6] residual chunk k landed in its buffer
-  uint64_t* st_full = rs_full + XCH;        // [6] 512 arrivals: output chunk k finished in its buffer
-  uint64_t* xn_free = st_full + XCH;        // store warp: the three buffers of the normalised row / dxn2 tiles may be overwritten
-  uint64_t* xn_full = xn_free + 1;          // 512 arrivals: those three tiles are written
-  uint64_t* e2_done = xn_full + 1;          // store warp: every store of the tile's acc2 drain has read its buffer
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(e2_done + 1);
-  float2* ln_part = reinterpret_cast<float2*>(smem + OFF_LN);
+  uint64_t* w_full = a1_empty + 1;          // [3]
+  uint64_t* w_empty = w_full + W_SLOTS;     // [3]
+  uint64_t* acc1_full = w_empty + W_SLOTS;  // [2] ([0] used) stage-1 UMMAs of the super-chunk retired
+  uint64_t* acc1_empty = acc1_full + 2;     // [2] ([0] used) one arrival per GELU warp: the super-chunk is in registers
+  uint64_t* a2_full = acc1_empty + 2;       // [2] 512 arrivals: the A2 tile of the chunk is written
+  uint64_t* a2_free = a2_full + 2;          // [2] 2 arrivals: stage-2 UMMAs retired + chunk-store warp (h / du store has read it)
+  uint64_t* u_full = a2_free + 2;           // [2] forward: 512 arrivals (u staged); backward: the u tile landed (TMA)
+  uint64_t* u_free = u_full + 2;            // [2] forward: chunk-store warp (u store has read it); backward: 512 readers done
+  uint64_t* acc2_full = u_free + 2;         // [2] all stage-2 UMMAs of the tile retired
+  uint64_t* acc2_empty = acc2_full + 2;     // [2] one arrival per drain warp
+  uint64_t* rs_full = acc2_empty + 2;       // [2] forward: residual chunk landed in EB4 / EB5
+  uint64_t* dst_full = rs_full + 2;         // [2] 128 arrivals: the drain threads finished a chunk / tile in the buffer
+  uint64_t* dbuf_free = dst_full + 2;       // [2] drain-store warp: the store has read the buffer
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(dbuf_free + 2);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
 
@@ -109,12 +118,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
     for (int s = 0; s < W_SLOTS; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&acc1_full[s], 1); ptx::mbar_init(&acc1_empty[s], 16);
-      ptx::mbar_init(&a2_full[s], 256); ptx::mbar_init(&a2_free[s], 2);
-      ptx::mbar_init(&u_full[s], MODE == MLP_FWD ? 256 : 1); ptx::mbar_init(&u_free[s], MODE == MLP_FWD ? 1 : 256);
+      ptx::mbar_init(&a2_full[s], GELU_THREADS); ptx::mbar_init(&a2_free[s], 2);
+      ptx::mbar_init(&u_full[s], MODE == MLP_FWD ? GELU_THREADS : 1);
+      ptx::mbar_init(&u_free[s], MODE == MLP_FWD ? 1 : GELU_THREADS);
+      ptx::mbar_init(&acc2_full[s], 1); ptx::mbar_init(&acc2_empty[s], 4);
+      ptx::mbar_init(&rs_full[s], 1); ptx::mbar_init(&dst_full[s], DRAIN_THREADS); ptx::mbar_init(&dbuf_free[s], 1);
     }
-    ptx::mbar_init(acc2_full, 1); ptx::mbar_init(acc2_empty, 16);
-    for (int s = 0; s < XCH; ++s) { ptx::mbar_init(&rs_full[s], 1); ptx::mbar_init(&st_full[s], EPI_THREADS); }
-    ptx::mbar_init(xn_free, 1); ptx::mbar_init(xn_full, EPI_THREADS); ptx::mbar_init(e2_done, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -137,7 +146,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
     mt = t - g * p.tiles_m;
   };
   uint8_t* const eb = smem + OFF_EB;
-  long long tk[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long t_begin = DBG ? clock64() : 0;
 #define V2S_WAIT(slot, bar, par, code)                                   \
   do {                                                                  \
@@ -147,49 +156,44 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
   } while (0)
 
   if (warp == 0) {
-    // ================= TMA producer: A1 per tile, weight k-blocks in the order the MMA warp consumes them =========
+    // ================= TMA producer: A1 per tile, one weight slot per chunk stage in the MMA warp's order =========
     int ws = 0; uint32_t wph = 0;
     auto advance = [&]() { if (++ws == W_SLOTS) { ws = 0; wph ^= 1; } };
-    auto load_b1 = [&](int g, int j) {
+    auto load_b1 = [&](int g, int k) {          // stage-1 operand of super-chunk k: three k-block slots
 #pragma unroll 1
       for (int kb = 0; kb < KB1; ++kb) {
         ptx::mbar_wait(&w_empty[ws], wph ^ 1, p.err_flag, 41);
         if (ptx::elect_one()) {
           uint8_t* slot = smem + OFF_W + ws * W_SLOT;
-          ptx::mbar_arrive_expect_tx(&w_full[ws], CW * 128);
-          if (MODE == MLP_FWD) {      // W1 rows [j*128, +128), k-block kb: K-major
-            ptx::tma_load_2d(slot, &p.tmB1[g], &w_full[ws], kb * 64, j * CW);
-          } else {                    // W2 k-rows [kb*64, +64), columns [j*128, +128): MN-major, two 64-column boxes
-            ptx::tma_load_2d(slot, &p.tmB1[g], &w_full[ws], j * CW, kb * 64);
-            ptx::tma_load_2d(slot + 8192, &p.tmB1[g], &w_full[ws], j * CW + 64, kb * 64);
+          ptx::mbar_arrive_expect_tx(&w_full[ws], SW * 128);
+          if (MODE == MLP_FWD) {      // W1 rows [k*128, +128), k-block kb: K-major [128 x 64]
+            ptx::tma_load_2d(slot, &p.tmB1[g], &w_full[ws], kb * 64, k * SW);
+          } else {                    // W2 k-rows [kb*64, +64), columns [k*128, +128): MN-major, two [64 x 64] boxes
+            ptx::tma_load_2d(slot, &p.tmB1[g], &w_full[ws], k * SW, kb * 64);
+            ptx::tma_load_2d(slot + 8192, &p.tmB1[g], &w_full[ws], k * SW + 64, kb * 64);
           }
         }
         __syncwarp();
         advance();
       }
     };
-    auto load_b2 = [&](int g, int j) {
-#pragma unroll 1
-      for (int kb = 0; kb < KB2; ++kb) {
-        ptx::mbar_wait(&w_empty[ws], wph ^ 1, p.err_flag, 42);
-        if (ptx::elect_one()) {
-          uint8_t* slot = smem + OFF_W + ws * W_SLOT;
-          ptx::mbar_arrive_expect_tx(&w_full[ws], D * 128);
-          if (MODE == MLP_FWD) {      // W2 all 192 rows, k columns [j*128 + kb*64, +64): K-major
-            ptx::tma_load_2d(slot, &p.tmB2[g], &w_full[ws], j * CW + kb * 64, 0);
-          } else {                    // W1 k-rows [j*128 + kb*64, +64), all 192 columns: MN-major, three boxes
-            ptx::tma_load_2d(slot, &p.tmB2[g], &w_full[ws], 0, j * CW + kb * 64);
-            ptx::tma_load_2d(slot + 8192, &p.tmB2[g], &w_full[ws], 64, j * CW + kb * 64);
-            ptx::tma_load_2d(slot + 16384, &p.tmB2[g], &w_full[ws], 128, j * CW + kb * 64);
-          }
+    auto load_b2 = [&](int g, int j) {          // stage-2 operand of chunk j: one slot
+      ptx::mbar_wait(&w_empty[ws], wph ^ 1, p.err_flag, 42);
+      if (ptx::elect_one()) {
+        uint8_t* slot = smem + OFF_W + ws * W_SLOT;
+        ptx::mbar_arrive_expect_tx(&w_full[ws], W_SLOT);
+        if (MODE == MLP_FWD) {      // W2 all 192 rows, k columns [j*64, +64): K-major [192 x 64]
+          ptx::tma_load_2d(slot, &p.tmB2[g], &w_full[ws], j * CW, 0);
+        } else {                    // W1 k-rows [j*64, +64), all 192 columns: MN-major, three [64 x 64] boxes
+          ptx::tma_load_2d(slot, &p.tmB2[g], &w_full[ws], 0, j * CW);
+          ptx::tma_load_2d(slot + 8192, &p.tmB2[g], &w_full[ws], 64, j * CW);
+          ptx::tma_load_2d(slot + 16384, &p.tmB2[g], &w_full[ws], 128, j * CW);
         }
-        __syncwarp();
-        advance();
       }
+      __syncwarp();
+      advance();
     };
-    // stage-2 operands lag two chunks behind stage-1 operands (the MMA warp's order): (g, j) of the last two chunks
-    int pg1 = -1, pj1 = 0, pg2 = -1, pj2 = 0;
-    for (int i = 0; i < n_my; ++i) {
+    auto load_a1 = [&](int i) {
       int g, mt;
       tile_at(i, g, mt);
       ptx::mbar_wait(a1_empty, (i & 1) ^ 1, p.err_flag, 43);
@@ -199,31 +203,35 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
         for (int kb = 0; kb < KB1; ++kb) ptx::tma_load_2d(smem + kb * KBLK, &p.tmA[g], a1_full, kb * 64, mt * BM);
       }
       __syncwarp();
+    };
+    // the MMA warp's order over the global super-chunk index K (tile K / 6, super-chunk K % 6):
+    //   S1(0);  for K: [S2(2K-1)]  [S1(K+1)]  S2(2K);  S2(last)
+    const int n_sc = n_my * NSC;
+    auto grp = [&](int K) { int g, mt; tile_at(K / NSC, g, mt); return g; };
+    if (n_sc > 0) { load_a1(0); load_b1(grp(0), 0); }
 #pragma unroll 1
-      for (int j = 0; j < NCH; ++j) {
-        load_b1(g, j);
-        if (pg2 >= 0) load_b2(pg2, pj2);
-        pg2 = pg1; pj2 = pj1; pg1 = g; pj1 = j;
+    for (int K = 0; K < n_sc; ++K) {
+      if (K >= 1) load_b2(grp(K - 1), 2 * ((K - 1) % NSC) + 1);
+      if (K + 1 < n_sc) {
+        if ((K + 1) % NSC == 0) load_a1((K + 1) / NSC);
+        load_b1(grp(K + 1), (K + 1) % NSC);
       }
+      load_b2(grp(K), 2 * (K % NSC));
     }
-    if (pg2 >= 0) load_b2(pg2, pj2);
-    if (pg1 >= 0) load_b2(pg1, pj1);
+    if (n_sc > 0) load_b2(grp(n_sc - 1), 2 * ((n_sc - 1) % NSC) + 1);
   } else if (warp == 1) {
     // ================= MMA issuer: S1(c), then S2(c-2) =================
-    // (S1(c+1) only needs the accumulator drained by the chunk epilogue c-1, which happens at its very start; issuing
-    //  it ahead of S2(c-1), which needs that epilogue's END, has the next accumulator ready a whole chunk early)
     constexpr uint32_t b_mn = (MODE == MLP_BWD) ? 1u : 0u;
-    const uint32_t idesc1 = make_idesc_lp(LP::kIdescFmt, BM, CW, 0, b_mn);
     const uint32_t idesc2 = make_idesc_lp(LP::kIdescFmt, BM, D, 0, b_mn);
     const uint32_t sbase = ptx::smem_u32(smem);
     const uint32_t b_lbo = b_mn ? 8192u : 16u, b_step = b_mn ? (2048u >> 4) : (32u >> 4);
     int ws = 0; uint32_t wph = 0;
     auto advance = [&]() { if (++ws == W_SLOTS) { ws = 0; wph ^= 1; } };
-    auto stage1 = [&](int i, int j, int c) {
-      const int b = c & 1;
-      V2S_WAIT(0, &acc1_empty[b], ((c >> 1) & 1) ^ 1, 44);
-      if (j == 0) V2S_WAIT(1, a1_full, i & 1, 45);
-      const uint32_t d_tmem = tmem_base + b * CW;
+    const uint32_t idesc1 = make_idesc_lp(LP::kIdescFmt, BM, SW, 0, b_mn);
+    auto stage1 = [&](int K) {                  // super-chunk K (global index)
+      const int i = K / NSC, k = K - i * NSC;
+      V2S_WAIT(0, acc1_empty, (K & 1) ^ 1, 44);
+      if (k == 0) V2S_WAIT(1, a1_full, i & 1, 45);
 #pragma unroll 1
       for (int kb = 0; kb < KB1; ++kb) {
         V2S_WAIT(2, &w_full[ws], wph, 46);
@@ -232,363 +240,363 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
         const uint32_t b_lo = ptx::desc_lo(sbase + OFF_W + ws * W_SLOT, b_lbo);
         if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            ptx::umma_bf16_lohi(d_tmem, a_lo + k * 2, b_lo + k * b_step, ptx::DESC_HI_SW128_SBO1024, idesc1,
-                                (kb > 0 || k > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk)
+            ptx::umma_bf16_lohi(tmem_base, a_lo + kk * 2, b_lo + kk * b_step, ptx::DESC_HI_SW128_SBO1024, idesc1,
+                                (kb > 0 || kk > 0) ? 1u : 0u);
           ptx::umma_commit(&w_empty[ws]);
           if (kb == KB1 - 1) {
-            ptx::umma_commit(&acc1_full[b]);
-            if (j == NCH - 1) ptx::umma_commit(a1_empty);      // the tile's A1 is dead once these retire
+            ptx::umma_commit(acc1_full);
+            if (k == NSC - 1) ptx::umma_commit(a1_empty);      // the tile's A1 is dead once these retire
           }
         }
         __syncwarp();
         advance();
       }
     };
-    auto stage2 = [&](int i, int j, int c) {
-      if (j == 0) V2S_WAIT(3, acc2_empty, (i & 1) ^ 1, 47);
-      const uint32_t d_tmem = tmem_base + TM_ACC2;
-#pragma unroll 1
-      for (int kb = 0; kb < KB2; ++kb) {
-        V2S_WAIT(4, &a2_full[kb], c & 1, 48);
-        V2S_WAIT(5, &w_full[ws], wph, 49);
-        ptx::tc_fence_after();
-        const uint32_t a_lo = ptx::desc_lo(sbase + OFF_EB + kb * KBLK, 16);
-        const uint32_t b_lo = ptx::desc_lo(sbase + OFF_W + ws * W_SLOT, b_lbo);
-        if (ptx::elect_one()) {
+    auto stage2 = [&](int c) {                  // chunk c (global index)
+      const int i = c / NCH, j = c - i * NCH;
+      const int s = i & 1, b = c & 1;
+      if (j == 0) V2S_WAIT(3, &acc2_empty[s], ((i >> 1) & 1) ^ 1, 47);
+      V2S_WAIT(4, &a2_full[b], (c >> 1) & 1, 48);
+      V2S_WAIT(5, &w_full[ws], wph, 49);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + TM_ACC2 + s * D;
+      const uint32_t a_lo = ptx::desc_lo(sbase + OFF_EB + b * KBLK, 16);
+      const uint32_t b_lo = ptx::desc_lo(sbase + OFF_W + ws * W_SLOT, b_lbo);
+      if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            ptx::umma_bf16_lohi(d_tmem, a_lo + k * 2, b_lo + k * b_step, ptx::DESC_HI_SW128_SBO1024, idesc2,
-                                (j > 0 || kb > 0 || k > 0) ? 1u : 0u);
-          ptx::umma_commit(&w_empty[ws]);
-          ptx::umma_commit(&a2_free[kb]);
-          if (j == NCH - 1 && kb == KB2 - 1) ptx::umma_commit(acc2_full);
-        }
-        __syncwarp();
-        advance();
+        for (int kk = 0; kk < 4; ++kk)
+          ptx::umma_bf16_lohi(d_tmem, a_lo + kk * 2, b_lo + kk * b_step, ptx::DESC_HI_SW128_SBO1024, idesc2,
+                              (j > 0 || kk > 0) ? 1u : 0u);
+        ptx::umma_commit(&w_empty[ws]);
+        ptx::umma_commit(&a2_free[b]);
+        if (j == NCH - 1) ptx::umma_commit(&acc2_full[s]);
       }
+      __syncwarp();
+      advance();
     };
-    int c = 0, pi1 = -1, pj1 = 0, pi2 = -1, pj2 = 0;
-    for (int i = 0; i < n_my; ++i) {
+    const int n_sc = n_my * NSC;
+    if (n_sc > 0) stage1(0);
 #pragma unroll 1
-      for (int j = 0; j < NCH; ++j, ++c) {
-        stage1(i, j, c);
-        if (pi2 >= 0) stage2(pi2, pj2, c - 2);
-        pi2 = pi1; pj2 = pj1; pi1 = i; pj1 = j;
-      }
+    for (int K = 0; K < n_sc; ++K) {
+      if (K >= 1) stage2(2 * K - 1);
+      if (K + 1 < n_sc) stage1(K + 1);
+      stage2(2 * K);
     }
-    if (pi2 >= 0) stage2(pi2, pj2, c - 2);
-    if (pi1 >= 0) stage2(pi1, pj1, c - 1);
+    if (n_sc > 0) stage2(2 * n_sc - 1);
     if (DBG && blockIdx.x == 0 && lane == 0) {
       for (int k = 0; k < 6; ++k) p.dbg[k] = tk[k];
       p.dbg[6] = clock64() - t_begin; p.dbg[7] = n_my;
     }
   } else if (warp == 2) {
-    // ================= store warp: every TMA store, the epilogue-side TMA loads, buffer recycling ==============
-    // (lane 0 issues: bulk async-groups are per thread)
-    int c = 0, nu = 0, nl = 0;
-    if (MODE == MLP_BWD && n_my > 0 && lane == 0) {     // u tiles of the very first chunk
-      int g, mt;
-      tile_at(0, g, mt);
-      for (int kb = 0; kb < 2; ++kb) {
-        ptx::mbar_arrive_expect_tx(&u_full[kb], KBLK);
-        ptx::tma_load_2d(eb + (2 + kb) * KBLK, &p.tmU[g], &u_full[kb], kb * 64, mt * BM);
-      }
+    // ================= chunk-store warp: h / u (forward, online backbones), du (backward) =================
+    // (lane 0 issues: bulk async-groups are per thread).  One store group per chunk; a chunk's buffers are handed
+    // back while the next chunk's group is in flight.
+    int c = 0, nut = 0;
+    const int n_chunks = n_my * NCH;
+    auto load_u = [&](int cc) {       // backward: u tile of chunk cc into EB2 / EB3 (lane 0)
+      const int ti = cc / NCH, jj = cc - ti * NCH;
+      int g2, mt2;
+      tile_at(ti, g2, mt2);
+      ptx::mbar_arrive_expect_tx(&u_full[cc & 1], KBLK);
+      ptx::tma_load_2d(eb + (2 + (cc & 1)) * KBLK, &p.tmU[g2], &u_full[cc & 1], jj * CW, mt2 * BM);
+    };
+    if (MODE == MLP_BWD && lane == 0) {
+      if (n_chunks > 0) load_u(0);
+      if (n_chunks > 1) load_u(1);
     }
     __syncwarp();
     for (int i = 0; i < n_my; ++i) {
       int g, mt;
       tile_at(i, g, mt);
       const int m0 = mt * BM;
-      const bool has_h = p.has_h[g] != 0, has_u = p.has_u[g] != 0, has_ln = p.has_ln[g] != 0;
-      if (MODE == MLP_FWD && lane == 0) {
-        // residual chunks 0, 1 of this tile into their dedicated buffers EB4 / EB5, long before the drain needs them
-        for (int k = 0; k < 2; ++k) {
-          ptx::mbar_arrive_expect_tx(&rs_full[k], KBLK);
-          ptx::tma_load_2d(eb + (4 + k) * KBLK, &p.tmRes[g], &rs_full[k], k * 32, m0);
-        }
-      }
-      __syncwarp();
+      const bool has_h = p.has_h[g] != 0, has_u = MODE == MLP_FWD && p.has_u[g] != 0;
+      const bool stores = has_h || has_u;
 #pragma unroll 1
       for (int j = 0; j < NCH; ++j, ++c) {
-        if (MODE == MLP_BWD) {
-          // u tiles of the next chunk, as soon as this chunk's readers have them in registers
-          int g2 = g, mt2 = mt, j2 = j + 1;
-          bool have_next = true;
-          if (j2 == NCH) { j2 = 0; have_next = i + 1 < n_my; if (have_next) tile_at(i + 1, g2, mt2); }
-          if (have_next) {
-            for (int kb = 0; kb < 2; ++kb) {
-              ptx::mbar_wait(&u_free[kb], c & 1, p.err_flag, 53);
-              if (lane == 0) {
-                ptx::mbar_arrive_expect_tx(&u_full[kb], KBLK);
-                ptx::tma_load_2d(eb + (2 + kb) * KBLK, &p.tmU[g2], &u_full[kb], j2 * CW + kb * 64, mt2 * BM);
-              }
-              __syncwarp();
+        const int b = c & 1;
+        if (MODE == MLP_BWD && c + 2 < n_chunks) {
+          // the readers of chunk c have its u in registers (start of their chunk): fetch the u of chunk c + 2
+          ptx::mbar_wait(&u_free[b], (c >> 1) & 1, p.err_flag, 53);
+          if (lane == 0) load_u(c + 2);
+          __syncwarp();
+        }
+        ptx::mbar_wait(&a2_full[b], (c >> 1) & 1, p.err_flag, 54);
+        if (has_u) ptx::mbar_wait(&u_full[b], (nut * (NCH / 2) + (j >> 1)) & 1, p.err_flag, 55);
+        if (lane == 0) {
+          if (stores) {
+            if (has_h) ptx::tma_store_2d(&p.tmH[g], eb + b * KBLK, j * CW, m0);
+            if (has_u) ptx::tma_store_2d(&p.tmU[g], eb + (2 + b) * KBLK, j * CW, m0);
+            ptx::tma_commit_group();
+            if (j > 0) {                          // the previous chunk's stores have read their buffers
+              ptx::tma_wait_group_read<1>();
+              ptx::mbar_arrive(&a2_free[b ^ 1]);
+              if (has_u) ptx::mbar_arrive(&u_free[b ^ 1]);
             }
+            if (j == NCH - 1) {
+              ptx::tma_wait_group_read<0>();
+              ptx::mbar_arrive(&a2_free[b]);
+              if (has_u) ptx::mbar_arrive(&u_free[b]);
+            }
+          } else {
+            ptx::mbar_arrive(&a2_free[b]);
           }
-        }
-        ptx::mbar_wait(&a2_full[0], c & 1, p.err_flag, 54);
-        ptx::mbar_wait(&a2_full[1], c & 1, p.err_flag, 54);
-        if (has_h && lane == 0) {
-          ptx::tma_store_2d(&p.tmH[g], eb, j * CW, m0);
-          ptx::tma_store_2d(&p.tmH[g], eb + KBLK, j * CW + 64, m0);
-          ptx::tma_commit_group();
-        }
-        __syncwarp();
-        if (MODE == MLP_FWD && has_u) {
-          ptx::mbar_wait(&u_full[0], nu & 1, p.err_flag, 55);
-          ptx::mbar_wait(&u_full[1], nu & 1, p.err_flag, 55);
-          if (lane == 0) {
-            ptx::tma_store_2d(&p.tmU[g], eb + 2 * KBLK, j * CW, m0);
-            ptx::tma_store_2d(&p.tmU[g], eb + 3 * KBLK, j * CW + 64, m0);
-            ptx::tma_commit_group();
-          }
-          __syncwarp();
-          ++nu;
-        }
-        if (lane == 0) {
-          if (has_h || (MODE == MLP_FWD && has_u)) ptx::tma_wait_group_read<0>();
-          ptx::mbar_arrive(&a2_free[0]); ptx::mbar_arrive(&a2_free[1]);
-          if (MODE == MLP_FWD && has_u) { ptx::mbar_arrive(&u_free[0]); ptx::mbar_arrive(&u_free[1]); }
         }
         __syncwarp();
       }
-      // ---- acc2 drain ----
-      ptx::mbar_wait(acc2_full, i & 1, p.err_flag, 56);      // all stage-2 UMMAs of the tile retired: EB0..3 are idle
-      if (MODE == MLP_FWD) {
-        // chunk k lives in buffer EB[k < 2 ? 4 + k : k - 2]: six buffers for six chunks, no recycling inside a tile
-        if (lane == 0) {
-          for (int k = 2; k < XCH; ++k) {
-            ptx::mbar_arrive_expect_tx(&rs_full[k], KBLK);
-            ptx::tma_load_2d(eb + (k - 2) * KBLK, &p.tmRes[g], &rs_full[k], k * 32, m0);
-          }
-        }
-        __syncwarp();
-#pragma unroll 1
-        for (int k = 0; k < XCH; ++k) {
-          ptx::mbar_wait(&st_full[k], i & 1, p.err_flag, 57);
-          if (lane == 0) {
-            ptx::tma_store_2d(&p.tmOut[g], eb + (k < 2 ? 4 + k : k - 2) * KBLK, k * 32, m0);
-            ptx::tma_commit_group();
-          }
-          __syncwarp();
-        }
-        if (has_ln) {
-          if (lane == 0) {
-            ptx::tma_wait_group_read<3>();        // the stores of chunks 0..2 have read EB4, EB5, EB0
-            ptx::mbar_arrive(xn_free);
-          }
-          __syncwarp();
-          ptx::mbar_wait(xn_full, nl & 1, p.err_flag, 58);
-          ++nl;
-          if (lane == 0) {
-            ptx::tma_store_2d(&p.tmXn[g], eb + 4 * KBLK, 0, m0);
-            ptx::tma_store_2d(&p.tmXn[g], eb + 5 * KBLK, 64, m0);
-            ptx::tma_store_2d(&p.tmXn[g], eb, 128, m0);
-            ptx::tma_commit_group();
-          }
-          __syncwarp();
-        }
-      } else {
-        ptx::mbar_wait(xn_full, i & 1, p.err_flag, 59);
-        if (lane == 0) {
-          ptx::tma_store_2d(&p.tmOut[g], eb + 4 * KBLK, 0, m0);
-          ptx::tma_store_2d(&p.tmOut[g], eb + 5 * KBLK, 64, m0);
-          ptx::tma_store_2d(&p.tmOut[g], eb, 128, m0);
-          ptx::tma_commit_group();
-        }
-        __syncwarp();
-      }
-      if (lane == 0) {
-        ptx::tma_wait_group_read<0>();
-        ptx::mbar_arrive(e2_done);
-      }
-      __syncwarp();
+      if (has_u) ++nut;
     }
     if (lane == 0) ptx::tma_wait_group<0>();
     __syncwarp();
-  } else if (warp >= 4) {
-    // ================= epilogue warps =================
+  } else if (warp == 3) {
+    // ================= drain-store warp: x_out chunks and normalised tiles (forward), dxn2 tiles (backward) =======
+    // forward: the residual chunk that uses a buffer next is fetched right here, the moment the buffer's previous
+    // store has been read: chunks 0, 1 of a tile are in place long before its accumulator is complete.
+    int use0 = 0, use1 = 0;
+    auto load_res = [&](int ti, int k) {      // lane 0
+      int g2, mt2;
+      tile_at(ti, g2, mt2);
+      ptx::mbar_arrive_expect_tx(&rs_full[k & 1], KBLK);
+      ptx::tma_load_2d(eb + (4 + (k & 1)) * KBLK, &p.tmRes[g2], &rs_full[k & 1], k * 32, mt2 * BM);
+    };
+    if (MODE == MLP_FWD && n_my > 0 && lane == 0) { load_res(0, 0); load_res(0, 1); }
+    __syncwarp();
+    for (int i = 0; i < n_my; ++i) {
+      int g, mt;
+      tile_at(i, g, mt);
+      const int m0 = mt * BM;
+      const int n_out = MODE == MLP_FWD ? XCH : 0;
+      const int n_lp = MODE == MLP_FWD ? (p.has_ln[g] != 0 ? 3 : 0) : 3;
+      const int n_all = n_out + n_lp;
+#pragma unroll 1
+      for (int k = 0; k < n_all; ++k) {
+        const int t = k - n_out;                    // >= 0: 16-bit tile t
+        const int b = (k < n_out ? k : t) & 1;
+        ptx::mbar_wait(&dst_full[b], (b ? use1 : use0) & 1, p.err_flag, 57);
+        if (lane == 0) {
+          if (k < n_out) ptx::tma_store_2d(&p.tmOut[g], eb + (4 + b) * KBLK, k * 32, m0);
+          else ptx::tma_store_2d(MODE == MLP_FWD ? &p.tmXn[g] : &p.tmOut[g], eb + (4 + b) * KBLK, t * 64, m0);
+          ptx::tma_commit_group();
+          ptx::tma_wait_group_read<0>();
+          ptx::mbar_arrive(&dbuf_free[b]);
+          if (MODE == MLP_FWD) {
+            // next use of buffer b: residual chunk k + 2 of this tile, or chunk b of the next tile when this was the
+            // buffer's last use in the tile (uses of a tile: b0 = chunks 0 2 4 [tiles 0 2], b1 = chunks 1 3 5 [tile 1])
+            if (k + 2 < n_out) load_res(i, k + 2);
+            else if (i + 1 < n_my) {
+              const bool last_use = n_lp == 0 ? true : (b == 0 ? t == 2 : t == 1);
+              if (last_use) load_res(i + 1, b);
+            }
+          }
+        }
+        __syncwarp();
+        use0 += b ^ 1; use1 += b;
+      }
+    }
+    if (lane == 0) ptx::tma_wait_group<0>();
+    __syncwarp();
+  } else if (warp >= 4 && warp < 20) {
+    // ================= GELU warps =================
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    const int cq = (warp - 4) >> 2;              // column quarter
-    const int kbq = cq >> 1;                     // k-block tile of the chunk this thread writes
+    const int cq = (warp - 4) >> 2;              // column quarter: 16 of the chunk's 64 columns
     const int row = q * 32 + lane;
     const int rx = row & 7;
     const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t eb_row = ptx::smem_u32(eb) + row * 128;      // this thread's row in EB0
-    int c = 0, nu = 0, nl = 0;
+    const uint32_t pc0 = ((2 * cq) ^ rx) << 4, pc1 = ((2 * cq + 1) ^ rx) << 4;   // its two 16-byte pieces of a tile row
+    int c = 0, nut = 0;
+    uint32_t rr[32];
     for (int i = 0; i < n_my; ++i) {
       int g, mt;
       tile_at(i, g, mt);
-      const int64_t grow = (int64_t)mt * BM + row;
-      const bool has_u = p.has_u[g] != 0, has_ln = p.has_ln[g] != 0;
+      const bool has_u = MODE == MLP_FWD && p.has_u[g] != 0;
 #pragma unroll 1
       for (int j = 0; j < NCH; ++j, ++c) {
         const int b = c & 1;
-        const int col0 = j * CW + cq * 32;                      // this thread's 32 columns of the 768-wide dimension
-        uint4 ux[4];
+        uint4 ux0, ux1;
         if (MODE == MLP_BWD) {                                  // pre-GELU activation of the forward pass
-          V2S_WAIT(1, &u_full[kbq], c & 1, 61);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) ux[t] = ptx::lds128(eb_row + (2 + kbq) * KBLK + ((((cq & 1) * 4 + t) ^ rx) << 4));
-          // The tile is handed back to the TMA engine (next chunk's u): the loads above must have READ shared memory
-          // before the arrival is visible.  Nothing below depends on their data yet, and the hardware lets the
-          // barrier arrival overtake loads that are merely issued (observed: a few rows picked up the next chunk's u),
-          // so wait for them explicitly.
+          V2S_WAIT(0, &u_full[b], (c >> 1) & 1, 61);
+          ux0 = ptx::lds128(eb_row + (2 + b) * KBLK + pc0);
+          ux1 = ptx::lds128(eb_row + (2 + b) * KBLK + pc1);
+          // The tile is handed back to the TMA engine (the u of chunk c + 2): the loads above must have READ shared
+          // memory before the arrival is visible.  Nothing below depends on their data yet, and the hardware lets the
+          // barrier arrival overtake loads that are merely issued, so wait for them explicitly.
           __threadfence_block();
-          ptx::mbar_arrive(&u_free[kbq]);
+          ptx::mbar_arrive(&u_free[b]);
         }
-        V2S_WAIT(2, &acc1_full[b], (c >> 1) & 1, 50);
-        ptx::tc_fence_after();
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tl + b * CW + cq * 32, r);
-        ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        if (lane == 0) ptx::mbar_arrive(&acc1_empty[b]);
-        uint32_t o[16], pu[16];
-        if (MODE == MLP_FWD) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.b1[g] + col0);
-          float v[32];
+        if (b == 0) {          // a new super-chunk: both halves into registers, the accumulator back to the MMA warp
+          V2S_WAIT(1, acc1_full, (c >> 1) & 1, 50);
+          ptx::tc_fence_after();
+          ptx::tmem_ld_32x16(tl + cq * 16, rr);
+          ptx::tmem_ld_32x16(tl + CW + cq * 16, rr + 16);
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          if (lane == 0) ptx::mbar_arrive(acc1_empty);
+        }
+        uint32_t r[16];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
+        for (int e = 0; e < 16; ++e) r[e] = b ? rr[16 + e] : rr[e];
+        uint32_t o[8], pu[8];
+        if (MODE == MLP_FWD) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.b1[g] + j * CW + cq * 16);
+          float v[16];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
             const float4 bb = __ldg(b4 + t);
             v[4 * t] = __uint_as_float(r[4 * t]) + bb.x; v[4 * t + 1] = __uint_as_float(r[4 * t + 1]) + bb.y;
             v[4 * t + 2] = __uint_as_float(r[4 * t + 2]) + bb.z; v[4 * t + 3] = __uint_as_float(r[4 * t + 3]) + bb.w;
           }
           if (has_u) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) pu[k] = LP::pack(v[2 * k], v[2 * k + 1]);
+            for (int k = 0; k < 8; ++k) pu[k] = LP::pack(v[2 * k], v[2 * k + 1]);
           }
 #pragma unroll
-          for (int k = 0; k < 16; ++k) o[k] = LP::pack(gelu_fast(v[2 * k]), gelu_fast(v[2 * k + 1]));
+          for (int k = 0; k < 8; ++k) o[k] = LP::pack(gelu_fast(v[2 * k]), gelu_fast(v[2 * k + 1]));
         } else {
+          const uint32_t w[8] = {ux0.x, ux0.y, ux0.z, ux0.w, ux1.x, ux1.y, ux1.z, ux1.w};
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const uint32_t w[4] = {ux[t].x, ux[t].y, ux[t].z, ux[t].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              o[4 * t + e] = LP::pack(__uint_as_float(r[8 * t + 2 * e]) * gelu_grad_fast(LP::lo(w[e])),
-                                      __uint_as_float(r[8 * t + 2 * e + 1]) * gelu_grad_fast(LP::hi(w[e])));
-          }
+          for (int e = 0; e < 8; ++e)
+            o[e] = LP::pack(__uint_as_float(r[2 * e]) * gelu_grad_fast(LP::lo(w[e])),
+                            __uint_as_float(r[2 * e + 1]) * gelu_grad_fast(LP::hi(w[e])));
         }
-        // A operand of stage 2: k-block tile kbq of the chunk, 16-byte pieces (cq & 1) * 4 + t of this row
-        if (j == 0 && i > 0) V2S_WAIT(0, e2_done, (i - 1) & 1, 60);   // the previous tile's drain has left the buffers
-        V2S_WAIT(3, &a2_free[kbq], (c & 1) ^ 1, 51);
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-          ptx::sts128(eb_row + kbq * KBLK + ((((cq & 1) * 4 + t) ^ rx) << 4), o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
-        ptx::fence_proxy_async();
-        ptx::mbar_arrive(&a2_full[kbq]);
-        if (MODE == MLP_FWD && has_u) {
-          V2S_WAIT(4, &u_free[kbq], (nu & 1) ^ 1, 62);
-#pragma unroll
-          for (int t = 0; t < 4; ++t)
-            ptx::sts128(eb_row + (2 + kbq) * KBLK + ((((cq & 1) * 4 + t) ^ rx) << 4), pu[4 * t], pu[4 * t + 1], pu[4 * t + 2],
-                        pu[4 * t + 3]);
+        // A operand of stage 2: the chunk's k-block tile, 16-byte pieces 2 cq, 2 cq + 1 of this row
+        V2S_WAIT(2, &a2_free[b], ((c >> 1) & 1) ^ 1, 51);
+        ptx::sts128(eb_row + b * KBLK + pc0, o[0], o[1], o[2], o[3]);
+        ptx::sts128(eb_row + b * KBLK + pc1, o[4], o[5], o[6], o[7]);
+        if (has_u) {      // one proxy fence for both tiles (the fence is the expensive part)
+          V2S_WAIT(3, &u_free[b], ((nut * (NCH / 2) + (j >> 1)) & 1) ^ 1, 62);
+          ptx::sts128(eb_row + (2 + b) * KBLK + pc0, pu[0], pu[1], pu[2], pu[3]);
+          ptx::sts128(eb_row + (2 + b) * KBLK + pc1, pu[4], pu[5], pu[6], pu[7]);
           ptx::fence_proxy_async();
-          ptx::mbar_arrive(&u_full[kbq]);
-          ++nu;
+          ptx::mbar_arrive(&a2_full[b]);
+          ptx::mbar_arrive(&u_full[b]);
+        } else {
+          ptx::fence_proxy_async();
+          ptx::mbar_arrive(&a2_full[b]);
         }
       }
-      // ---- drain acc2: in every 32-column chunk k this thread owns columns 32 k + 8 cq .. + 7 of its row ----
-      const long long t_e2 = DBG ? clock64() : 0;
-      V2S_WAIT(5, acc2_full, i & 1, 52);
+      if (has_u) ++nut;
+    }
+    if (DBG && blockIdx.x == 0 && threadIdx.x == 128) {
+      for (int k = 0; k < 4; ++k) p.dbg[8 + k] = tk[k];
+      p.dbg[12] = clock64() - t_begin;
+    }
+  } else if (warp >= 20 && warp < 24) {
+    // ================= drain warps: thread = one row of the tile =================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int rx = row & 7;
+    const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC2;
+    const uint32_t eb_row = ptx::smem_u32(eb) + 4 * KBLK + row * 128;      // this thread's row in EB4
+    int use0 = 0, use1 = 0, nres0 = 0, nres1 = 0;
+    for (int i = 0; i < n_my; ++i) {
+      int g, mt;
+      tile_at(i, g, mt);
+      const int s = i & 1;
+      const int64_t grow = (int64_t)mt * BM + row;
+      const uint32_t ta = tl + s * D;
+      V2S_WAIT(4, &acc2_full[s], (i >> 1) & 1, 52);
+      const long long t_d0 = DBG ? clock64() : 0;
       ptx::tc_fence_after();
-      uint32_t r[48];
-#pragma unroll
-      for (int k = 0; k < XCH; ++k) ptx::tmem_ld_32x8(tl + TM_ACC2 + k * 32 + cq * 8, r + 8 * k);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      if (lane == 0) ptx::mbar_arrive(acc2_empty);
-      long long t_ph = DBG ? clock64() : 0;
-      if (DBG) tk[9] += t_ph - t_e2;
       if (MODE == MLP_FWD) {
-        float v[48];
+        const bool has_ln = p.has_ln[g] != 0;
         float s1 = 0.f, s2 = 0.f;
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < XCH; ++k) {
-          const int bq = k < 2 ? 4 + k : k - 2;
-          const float4 ba = __ldg(reinterpret_cast<const float4*>(p.b2[g] + k * 32 + cq * 8));
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2[g] + k * 32 + cq * 8 + 4));
-          V2S_WAIT(6, &rs_full[k], i & 1, 63);
-          const uint32_t s0 = eb_row + bq * KBLK + (((2 * cq) ^ rx) << 4), s1a = eb_row + bq * KBLK + (((2 * cq + 1) ^ rx) << 4);
-          const float4 xa = ptx::lds128f(s0), xb = ptx::lds128f(s1a);
-          float* x = v + 8 * k;
-          x[0] = __uint_as_float(r[8 * k]) + ba.x + xa.x; x[1] = __uint_as_float(r[8 * k + 1]) + ba.y + xa.y;
-          x[2] = __uint_as_float(r[8 * k + 2]) + ba.z + xa.z; x[3] = __uint_as_float(r[8 * k + 3]) + ba.w + xa.w;
-          x[4] = __uint_as_float(r[8 * k + 4]) + bb.x + xb.x; x[5] = __uint_as_float(r[8 * k + 5]) + bb.y + xb.y;
-          x[6] = __uint_as_float(r[8 * k + 6]) + bb.z + xb.z; x[7] = __uint_as_float(r[8 * k + 7]) + bb.w + xb.w;
-          ptx::sts128f(s0, x[0], x[1], x[2], x[3]);
-          ptx::sts128f(s1a, x[4], x[5], x[6], x[7]);
-          if (k & 1) {       // one proxy fence per pair of chunks
-            ptx::fence_proxy_async();
-            ptx::mbar_arrive(&st_full[k - 1]);
-            ptx::mbar_arrive(&st_full[k]);
+          const int b = k & 1;
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(ta + k * 32, r);
+          const float4* b4 = reinterpret_cast<const float4*>(p.b2[g] + k * 32);
+          V2S_WAIT(5, &rs_full[b], (b ? nres1 : nres0) & 1, 63);
+          nres0 += b ^ 1; nres1 += b;
+          ptx::tmem_ld_wait();
+          const uint32_t sb = eb_row + b * KBLK;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float4 bb = __ldg(b4 + t);
+            const uint32_t sa = sb + ((t ^ rx) << 4);
+            const float4 xr = ptx::lds128f(sa);
+            const float x0 = __uint_as_float(r[4 * t]) + bb.x + xr.x, x1 = __uint_as_float(r[4 * t + 1]) + bb.y + xr.y;
+            const float x2 = __uint_as_float(r[4 * t + 2]) + bb.z + xr.z, x3 = __uint_as_float(r[4 * t + 3]) + bb.w + xr.w;
+            ptx::sts128f(sa, x0, x1, x2, x3);
+            s1 += (x0 + x1) + (x2 + x3);
+            s2 = fmaf(x0, x0, s2); s2 = fmaf(x1, x1, s2); s2 = fmaf(x2, x2, s2); s2 = fmaf(x3, x3, s2);
+            r[4 * t] = __float_as_uint(x0); r[4 * t + 1] = __float_as_uint(x1);
+            r[4 * t + 2] = __float_as_uint(x2); r[4 * t + 3] = __float_as_uint(x3);
           }
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { s1 += x[e]; s2 = fmaf(x[e], x[e], s2); }
+          ptx::fence_proxy_async();
+          ptx::mbar_arrive(&dst_full[b]);
+          use0 += b ^ 1; use1 += b;
+          if (has_ln) ptx::tmem_st_32x32(ta + k * 32, r);       // park the finished row chunk for the normalise pass
         }
-        if (DBG) { const long long t1 = clock64(); tk[10] += t1 - t_ph; t_ph = t1; }
         if (has_ln) {
-          // LayerNorm over the 192-wide row: four threads per row exchange partial sums through shared memory
-          ln_part[cq * BM + row] = make_float2(s1, s2);
-          ptx::bar_sync(1, EPI_THREADS);
-          if (DBG) { const long long t1 = clock64(); tk[11] += t1 - t_ph; t_ph = t1; }
-          s1 = 0.f; s2 = 0.f;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { const float2 o2 = ln_part[k * BM + row]; s1 += o2.x; s2 += o2.y; }
           const float mean = s1 * (1.0f / D);
           const float var = fmaxf(s2 * (1.0f / D) - mean * mean, 0.f);
           const float rstd = 1.0f / sqrtf(var + LN_EPS);
-          if (cq == 0 && grow < p.M && p.ln_mean[g] != nullptr) { p.ln_mean[g][grow] = mean; p.ln_rstd[g][grow] = rstd; }
-          V2S_WAIT(7, xn_free, nl & 1, 64);
-          ++nl;
-#pragma unroll
+          if (grow < p.M && p.ln_mean[g] != nullptr) { p.ln_mean[g][grow] = mean; p.ln_rstd[g][grow] = rstd; }
+          ptx::tmem_st_wait();
+#pragma unroll 1
           for (int t = 0; t < 3; ++t) {
-            const int bq = t < 2 ? 4 + t : 0;
-            uint32_t w[8];
+            const int b = t & 1;
+            const uint32_t sb = eb_row + b * KBLK;
+#pragma unroll 1
+            for (int hf = 0; hf < 2; ++hf) {
+              uint32_t r[32];
+              ptx::tmem_ld_32x32(ta + t * 64 + hf * 32, r);
+              const float4* g4 = reinterpret_cast<const float4*>(p.ln_gamma[g] + t * 64 + hf * 32);
+              const float4* e4 = reinterpret_cast<const float4*>(p.ln_beta[g] + t * 64 + hf * 32);
+              if (hf == 0) V2S_WAIT(6, &dbuf_free[b], ((b ? use1 : use0) & 1) ^ 1, 64);     // the buffer's previous store has read it
+              ptx::tmem_ld_wait();
 #pragma unroll
-            for (int hk = 0; hk < 2; ++hk) {
-              const int k = 2 * t + hk;
-              const float4 ga = __ldg(reinterpret_cast<const float4*>(p.ln_gamma[g] + k * 32 + cq * 8));
-              const float4 gb = __ldg(reinterpret_cast<const float4*>(p.ln_gamma[g] + k * 32 + cq * 8 + 4));
-              const float4 ea = __ldg(reinterpret_cast<const float4*>(p.ln_beta[g] + k * 32 + cq * 8));
-              const float4 eb4 = __ldg(reinterpret_cast<const float4*>(p.ln_beta[g] + k * 32 + cq * 8 + 4));
-              const float* x = v + 8 * k;
-              w[4 * hk] = LP::pack((x[0] - mean) * rstd * ga.x + ea.x, (x[1] - mean) * rstd * ga.y + ea.y);
-              w[4 * hk + 1] = LP::pack((x[2] - mean) * rstd * ga.z + ea.z, (x[3] - mean) * rstd * ga.w + ea.w);
-              w[4 * hk + 2] = LP::pack((x[4] - mean) * rstd * gb.x + eb4.x, (x[5] - mean) * rstd * gb.y + eb4.y);
-              w[4 * hk + 3] = LP::pack((x[6] - mean) * rstd * gb.z + eb4.z, (x[7] - mean) * rstd * gb.w + eb4.w);
+              for (int e = 0; e < 4; ++e) {
+                const float4 ga = __ldg(g4 + 2 * e), gb = __ldg(g4 + 2 * e + 1);
+                const float4 ea = __ldg(e4 + 2 * e), eb4 = __ldg(e4 + 2 * e + 1);
+                const uint32_t* x = r + 8 * e;
+                const uint32_t w0 = LP::pack((__uint_as_float(x[0]) - mean) * rstd * ga.x + ea.x, (__uint_as_float(x[1]) - mean) * rstd * ga.y + ea.y);
+                const uint32_t w1 = LP::pack((__uint_as_float(x[2]) - mean) * rstd * ga.z + ea.z, (__uint_as_float(x[3]) - mean) * rstd * ga.w + ea.w);
+                const uint32_t w2 = LP::pack((__uint_as_float(x[4]) - mean) * rstd * gb.x + eb4.x, (__uint_as_float(x[5]) - mean) * rstd * gb.y + eb4.y);
+                const uint32_t w3 = LP::pack((__uint_as_float(x[6]) - mean) * rstd * gb.z + eb4.z, (__uint_as_float(x[7]) - mean) * rstd * gb.w + eb4.w);
+                ptx::sts128(sb + (((hf * 4 + e) ^ rx) << 4), w0, w1, w2, w3);
+              }
             }
-            // tile t holds columns [64 t, +64): chunk 2t -> 16-byte piece cq, chunk 2t+1 -> piece 4 + cq
-            ptx::sts128(eb_row + bq * KBLK + ((cq ^ rx) << 4), w[0], w[1], w[2], w[3]);
-            ptx::sts128(eb_row + bq * KBLK + (((4 + cq) ^ rx) << 4), w[4], w[5], w[6], w[7]);
+            ptx::fence_proxy_async();
+            ptx::mbar_arrive(&dst_full[b]);
+            use0 += b ^ 1; use1 += b;
           }
-          ptx::fence_proxy_async();
-          ptx::mbar_arrive(xn_full);
         }
       } else {
-        V2S_WAIT(7, &a2_free[0], (c & 1) ^ 1, 65);       // EB0: the last chunk's du store and UMMAs have read it
-#pragma unroll
+#pragma unroll 1
         for (int t = 0; t < 3; ++t) {
-          const int bq = t < 2 ? 4 + t : 0;
-          const uint32_t* x = r + 16 * t;
-          ptx::sts128(eb_row + bq * KBLK + ((cq ^ rx) << 4), LP::pack(__uint_as_float(x[0]), __uint_as_float(x[1])),
-                      LP::pack(__uint_as_float(x[2]), __uint_as_float(x[3])), LP::pack(__uint_as_float(x[4]), __uint_as_float(x[5])),
-                      LP::pack(__uint_as_float(x[6]), __uint_as_float(x[7])));
-          ptx::sts128(eb_row + bq * KBLK + (((4 + cq) ^ rx) << 4), LP::pack(__uint_as_float(x[8]), __uint_as_float(x[9])),
-                      LP::pack(__uint_as_float(x[10]), __uint_as_float(x[11])), LP::pack(__uint_as_float(x[12]), __uint_as_float(x[13])),
-                      LP::pack(__uint_as_float(x[14]), __uint_as_float(x[15])));
+          const int b = t & 1;
+          const uint32_t sb = eb_row + b * KBLK;
+#pragma unroll 1
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(ta + t * 64 + hf * 32, r);
+            if (hf == 0) V2S_WAIT(6, &dbuf_free[b], ((b ? use1 : use0) & 1) ^ 1, 65);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t* x = r + 8 * e;
+              ptx::sts128(sb + (((hf * 4 + e) ^ rx) << 4), LP::pack(__uint_as_float(x[0]), __uint_as_float(x[1])),
+                          LP::pack(__uint_as_float(x[2]), __uint_as_float(x[3])), LP::pack(__uint_as_float(x[4]), __uint_as_float(x[5])),
+                          LP::pack(__uint_as_float(x[6]), __uint_as_float(x[7])));
+            }
+          }
+          ptx::fence_proxy_async();
+          ptx::mbar_arrive(&dst_full[b]);
+          use0 += b ^ 1; use1 += b;
         }
-        ptx::fence_proxy_async();
-        ptx::mbar_arrive(xn_full);
       }
-      if (DBG) tk[8] += clock64() - t_e2;
+      // every tcgen05.ld of this tile's accumulator has completed (wait::ld above): hand it back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc2_empty[s]);
+      if (DBG) tk[7] += clock64() - t_d0;
     }
-    if (DBG && blockIdx.x == 0 && threadIdx.x == 128) {
-      for (int k = 0; k < 9; ++k) p.dbg[8 + k] = tk[k];
+    if (DBG && blockIdx.x == 0 && threadIdx.x == 640) {
+      p.dbg[13] = tk[4]; p.dbg[14] = tk[5]; p.dbg[15] = tk[6]; p.dbg[16] = tk[7];
       p.dbg[17] = clock64() - t_begin;
-      p.dbg[18] = tk[9]; p.dbg[19] = tk[10]; p.dbg[20] = tk[11];
     }
   }
 #undef V2S_WAIT
@@ -634,7 +642,7 @@ int launch_mlp_tc(const MlpDesc& d, cudaStream_t stream) {
     V2S_TRY(tmap_get_2d(&p.tmA[g], d.a[g], D, d.M, D, 64, BM, true, 128));
     if (d.mode == MLP_FWD) {
       if (!d.b1[g] || !d.b2[g] || !d.resid[g]) { set_error("mlp_tc: forward needs biases and the residual"); return 1; }
-      V2S_TRY(tmap_get_2d(&p.tmB1[g], d.w1[g], D, DF, D, 64, CW, true, 128));       // W1 [768,192]: rows x k
+      V2S_TRY(tmap_get_2d(&p.tmB1[g], d.w1[g], D, DF, D, 64, SW, true, 128));       // W1 [768,192]: rows x k
       V2S_TRY(tmap_get_2d(&p.tmB2[g], d.w2[g], DF, D, DF, 64, D, true, 128));       // W2 [192,768]: rows x k
       V2S_TRY(tmap_get_2d(&p.tmRes[g], d.resid[g], D, d.M, D, 32, BM, false, 128));
       V2S_TRY(tmap_get_2d(&p.tmOut[g], d.out[g], D, d.M, D, 32, BM, false, 128));
