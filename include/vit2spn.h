@@ -149,6 +149,17 @@ int v2s_heads_backward(const float* head_params, float* head_grads, const float*
 int v2s_cosine_loss(const float* pred, const float* target_proj, float* loss, float* dpred, int batch,
                     int accumulation_steps, float grad_scale, void* stream);
 
+/* InfoNCE with global negatives (BASELINE north_star (3) and config 3; the reference itself has no such loss —
+ * ref:ssp_vit2spn_tiny.py:174,211 is the negative-free cosine loss above — so this is an opt-in mode):
+ *   logits[i][j] = cos(pred_i, keys_j) / temperature over ALL n_keys gathered target projections (the host all-gathers
+ *   target_proj over the data-parallel ranks: keys = [n_keys,128], this rank's positives are rows label_offset + i),
+ *   loss = mean_i CE(logits[i], label_offset + i) / accumulation_steps, dpred = grad_scale * d loss / d pred (keys are
+ *   detached like ref:158).  Similarity, temperature scale, row log-sum-exp, cross-entropy and backward are one kernel.
+ *   row_loss: scratch [batch]; grad_scale_dev: optional device-resident extra factor (GradScaler), may be NULL. */
+int v2s_infonce_loss(const float* pred, const float* keys, float* loss, float* row_loss, float* dpred, int batch,
+                     int n_keys, int64_t label_offset, float temperature, int accumulation_steps, float grad_scale,
+                     const float* grad_scale_dev, void* stream);
+
 /* dropout multipliers for the projection head: out[i] = keep ? 1/(1-p) : 0, counter-based RNG */
 int v2s_dropout_mask(float* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
 

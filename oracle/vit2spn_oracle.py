@@ -340,6 +340,21 @@ def ssp_loss(pred, tgt, accumulation_steps: int = 1):
     return -cos.mean() / accumulation_steps
 
 
+def infonce_loss(pred, keys, label_offset: int = 0, temperature: float = 0.2, accumulation_steps: int = 1):
+    """InfoNCE over gathered target projections — BASELINE north_star (3) / config 3.  **No reference counterpart**
+    (the reference loss is the negative-free cosine of ref:174,211), so this restatement IS the
+    definition the CUDA kernel (kernels.cu infonce_row_kernel) is checked against: parity unpinned by the reference.
+    ``logits[i][j] = cos(pred_i, keys_j) / temperature`` with each norm clamped at 1e-8 like
+    ``nn.CosineSimilarity`` (ref:174); the positive of local row i is key ``label_offset + i``; keys are detached
+    (ref:158)."""
+    eps = 1e-8
+    ph = pred / pred.norm(dim=1, keepdim=True).clamp_min(eps)
+    kh = keys.detach() / keys.detach().norm(dim=1, keepdim=True).clamp_min(eps)
+    logits = ph @ kh.t() / temperature
+    labels = torch.arange(pred.shape[0], device=pred.device) + label_offset
+    return torch.nn.functional.cross_entropy(logits, labels) / accumulation_steps
+
+
 def trainable_names():
     """Parameters that receive a gradient: both online backbones minus final LN + pooler
     (never used, grad None — SURVEY D6), plus the two heads.  400 tensors, 11 606 528 elements."""

@@ -854,6 +854,14 @@ int v2s_cosine_loss(const float* pred, const float* target_proj, float* loss, fl
   return launch_cosine_loss(pred, target_proj, loss, dpred, batch, accumulation_steps, grad_scale, (cudaStream_t)stream);
 }
 
+int v2s_infonce_loss(const float* pred, const float* keys, float* loss, float* row_loss, float* dpred, int batch,
+                     int n_keys, int64_t label_offset, float temperature, int accumulation_steps, float grad_scale,
+                     const float* grad_scale_dev, void* stream) {
+  if (!pred || !keys || !loss || !row_loss || batch < 1 || accumulation_steps < 1) { set_error("infonce_loss: bad argument"); return 1; }
+  return launch_infonce_loss(pred, keys, loss, row_loss, dpred, batch, n_keys, label_offset, temperature, accumulation_steps,
+                             grad_scale, (cudaStream_t)stream, grad_scale_dev);
+}
+
 int v2s_dropout_mask(float* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
   if (!mask || n < 0 || p < 0.f || p >= 1.f) { set_error("dropout_mask: bad argument"); return 1; }
   if (n == 0) return 0;

@@ -531,6 +531,111 @@ __global__ void __launch_bounds__(256) cosine_loss_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------
+// InfoNCE with global negatives (north_star (3); no reference counterpart, SURVEY D2/D3 — an opt-in loss, never the
+// default).  One CTA per local row i: the row of the cosine-similarity matrix p_i . z_j / (|p_i| |z_j| tau) against ALL
+// gathered target projections, its log-sum-exp, the cross-entropy against the positive (column label_offset + i) and
+// the gradient w.r.t. p_i (z is detached, ref:158) — similarity "GEMM", temperature scale, row logsumexp, CE and its
+// backward in one launch; the N x 128 key matrix (512 KB at 8 x 128 keys) streams from L2.
+//   loss = mean_i( lse_i - logit_i,label ) / accum   (row_loss[i] holds the per-row term; summed by a second tiny launch
+//   in a fixed order, so the result is bit-reproducible)
+// ------------------------------------------------------------------------------------------
+constexpr int NCE_THREADS = 256;
+__global__ void __launch_bounds__(NCE_THREADS) infonce_row_kernel(const float* __restrict__ p, const float* __restrict__ z,
+                                                                   float* __restrict__ row_loss, float* __restrict__ dp,
+                                                                   int n_keys, long long label_offset, float inv_tau,
+                                                                   float grad_mul, const float* __restrict__ grad_scale_dev) {
+  extern __shared__ float nce_sm[];
+  float* logit = nce_sm;                 // [n_keys]
+  float* invn = nce_sm + n_keys;         // [n_keys] 1 / max(|z_j|, eps)
+  __shared__ float red[NCE_THREADS / 32];
+  __shared__ float ph[V2S_PROJ_OUT];     // normalised p_i
+  __shared__ float gh[2][V2S_PROJ_OUT];
+  __shared__ float bc[2];
+  const int i = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float eps = 1e-8f;
+  // ---- p_i / max(|p_i|, eps) ----
+  float pn2 = 0.f;
+  if (warp == 0) {
+    const float4 pv = reinterpret_cast<const float4*>(p + (int64_t)i * V2S_PROJ_OUT)[lane];
+    pn2 = warp_sum(pv.x * pv.x + pv.y * pv.y + pv.z * pv.z + pv.w * pv.w);
+    const float inv = 1.0f / fmaxf(sqrtf(pn2), eps);
+    reinterpret_cast<float4*>(ph)[lane] = make_float4(pv.x * inv, pv.y * inv, pv.z * inv, pv.w * inv);
+    if (lane == 0) bc[0] = pn2;
+  }
+  __syncthreads();
+  pn2 = bc[0];
+  const float4 pq = reinterpret_cast<const float4*>(ph)[lane];
+  // ---- logits: one warp per key row (coalesced 512-byte reads) ----
+  float mx = -INFINITY;
+  for (int j = warp; j < n_keys; j += NCE_THREADS / 32) {
+    const float4 zv = reinterpret_cast<const float4*>(z + (int64_t)j * V2S_PROJ_OUT)[lane];
+    const float dot = warp_sum(pq.x * zv.x + pq.y * zv.y + pq.z * zv.z + pq.w * zv.w);
+    const float zz = warp_sum(zv.x * zv.x + zv.y * zv.y + zv.z * zv.z + zv.w * zv.w);
+    const float iz = 1.0f / fmaxf(sqrtf(zz), eps);
+    const float lg = dot * iz * inv_tau;
+    if (lane == 0) { logit[j] = lg; invn[j] = iz; }
+    mx = fmaxf(mx, lg);
+  }
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < NCE_THREADS / 32; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float se = 0.f;
+  for (int j = threadIdx.x; j < n_keys; j += NCE_THREADS) se += __expf(logit[j] - mx);
+  se = warp_sum(se);
+  if (lane == 0) red[warp] = se;
+  __syncthreads();
+  se = 0.f;
+#pragma unroll
+  for (int w = 0; w < NCE_THREADS / 32; ++w) se += red[w];     // fixed order: every thread gets the same sum
+  const float lse = mx + __logf(se);
+  const int label = (int)(label_offset + i);
+  if (threadIdx.x == 0) row_loss[i] = lse - logit[label];
+  if (dp == nullptr) return;
+  // ---- d loss_i / d p_hat = (1/tau) sum_j (softmax_ij - [j == label]) z_hat_j; thread = (dimension, key parity) ----
+  const int d = threadIdx.x & (V2S_PROJ_OUT - 1), par = threadIdx.x >> 7;
+  float g = 0.f;
+  for (int j = par; j < n_keys; j += 2) {
+    const float s = __expf(logit[j] - lse) - (j == label ? 1.0f : 0.0f);
+    g = fmaf(s * invn[j], __ldg(z + (int64_t)j * V2S_PROJ_OUT + d), g);
+  }
+  gh[par][d] = g;
+  __syncthreads();
+  if (threadIdx.x < V2S_PROJ_OUT) {
+    g = (gh[0][d] + gh[1][d]) * inv_tau;
+    // through p_hat = p / max(|p|, eps):  (g - [|p| > eps] p_hat (p_hat . g)) / max(|p|, eps)
+    const float pd = ph[d];
+    float dot = warp_sum(pd * g);
+    if (lane == 0) red[warp] = dot;
+  }
+  __syncthreads();
+  if (threadIdx.x < V2S_PROJ_OUT) {
+    const float dot = red[0] + red[1] + red[2] + red[3];
+    const float pn = sqrtf(pn2);
+    const float proj = pn > eps ? ph[d] * dot : 0.f;
+    const float sc = grad_mul * (grad_scale_dev ? __ldg(grad_scale_dev) : 1.0f) / fmaxf(pn, eps);
+    dp[(int64_t)i * V2S_PROJ_OUT + d] = (g - proj) * sc;
+  }
+}
+
+__global__ void __launch_bounds__(256) infonce_mean_kernel(const float* __restrict__ row_loss, float* loss, int B, float inv_count) {
+  __shared__ float part[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < B; i += 256) acc += row_loss[i];
+  acc = warp_sum(acc);
+  if (lane == 0) part[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    *loss = t * inv_count;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Adam (torch.optim.Adam semantics) over up to 4 flat ranges; optional bf16 shadow refresh
 // ------------------------------------------------------------------------------------------
 struct AdamRanges {
@@ -837,6 +942,22 @@ int launch_cosine_loss(const float* p, const float* z, float* loss, float* dp, i
                        cudaStream_t s, const float* grad_scale_dev) {
   const float inv_count = 1.0f / ((float)B * (float)accum);
   cosine_loss_kernel<<<1, 256, 0, s>>>(p, z, loss, dp, B, inv_count, grad_scale, grad_scale_dev);
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_infonce_loss(const float* p, const float* z_all, float* loss, float* row_loss, float* dp, int B, int n_keys,
+                        long long label_offset, float temperature, int accum, float grad_scale, cudaStream_t s,
+                        const float* grad_scale_dev) {
+  if (n_keys < 1 || n_keys > 6000) { set_error("infonce: 1..6000 keys (got %d)", n_keys); return 1; }
+  if (label_offset < 0 || label_offset + B > n_keys) { set_error("infonce: the positives [%lld, +%d) are not among the %d keys", label_offset, B, n_keys); return 1; }
+  if (!(temperature > 0.f)) { set_error("infonce: temperature must be positive"); return 1; }
+  const float inv_count = 1.0f / ((float)B * (float)accum);
+  infonce_row_kernel<<<B, NCE_THREADS, (size_t)n_keys * 2 * sizeof(float), s>>>(p, z_all, row_loss, dp, n_keys, label_offset,
+                                                                               1.0f / temperature, inv_count * grad_scale,
+                                                                               grad_scale_dev);
+  V2S_LAUNCH_CHECK();
+  infonce_mean_kernel<<<1, 256, 0, s>>>(row_loss, loss, B, inv_count);
   V2S_LAUNCH_CHECK();
   return 0;
 }

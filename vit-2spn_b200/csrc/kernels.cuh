@@ -42,6 +42,9 @@ int launch_attn_fwd_tc(const void* const* qkv, void* const* ctx, float* const* l
 int launch_attn_bwd_tc(const void* const* qkv, const void* const* ctx, const float* const* lse,
                        const void* const* dctx, void* const* dqkv, int groups, int B, cudaStream_t s, int lp_f16 = 0);
 
+int launch_infonce_loss(const float* p, const float* z_all, float* loss, float* row_loss, float* dp, int B, int n_keys,
+                        long long label_offset, float temperature, int accum, float grad_scale, cudaStream_t s,
+                        const float* grad_scale_dev = nullptr);
 int launch_cosine_loss(const float* p, const float* z, float* loss, float* dp, int B, int accum,
                        float grad_scale, cudaStream_t s, const float* grad_scale_dev = nullptr);
 int launch_adam(const v2s_range_t* ranges, int n, int64_t step, double lr, double b1, double b2, double eps,

@@ -630,6 +630,37 @@ class _DualStreamFn(torch.autograd.Function):
         return None, None, None, None, None
 
 
+def gather_keys(target_proj, group=None):
+    """All-gather of the (detached) target projections over the data-parallel ranks (NCCL over NVLink on GPUs, gloo in
+    the CPU tests): returns (keys [world * B, 128], offset of this rank's rows).  One process: the tensor itself."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return target_proj, 0
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    keys = torch.empty(world * target_proj.shape[0], target_proj.shape[1], dtype=target_proj.dtype, device=target_proj.device)
+    dist.all_gather_into_tensor(keys, target_proj.contiguous(), group=group)
+    return keys, rank * target_proj.shape[0]
+
+
+class InfoNCELoss(nn.Module):
+    """Opt-in contrastive criterion with global negatives (north_star (3)); NOT the reference's loss (ref:174 is
+    ``nn.CosineSimilarity``).  ``forward(pred, target_proj)`` gathers the target projections of all ranks and returns
+    the cross-entropy of ``cos(pred_i, key_j) / temperature`` against each row's own target (autograd path; the fused
+    path is ``DualStreamNetwork.loss_mode = "infonce"``, which ``train_self_supervised`` selects for this criterion)."""
+
+    def __init__(self, temperature=0.2, group=None):
+        super().__init__()
+        self.temperature, self.group = float(temperature), group
+
+    def forward(self, pred, target_proj):
+        keys, off = gather_keys(target_proj.detach(), self.group)
+        eps = 1e-8
+        ph = pred / pred.norm(dim=1, keepdim=True).clamp_min(eps)
+        kh = keys / keys.norm(dim=1, keepdim=True).clamp_min(eps)
+        labels = torch.arange(pred.shape[0], device=pred.device) + off
+        return torch.nn.functional.cross_entropy(ph @ kh.t() / self.temperature, labels)
+
+
 class DualStreamNetwork(nn.Module):
     """ref:ssp_vit2spn_tiny.py:121-166.  Same attributes, ``state_dict`` keys and parameter order."""
 
@@ -658,6 +689,12 @@ class DualStreamNetwork(nn.Module):
         self._head_store = FlatStore(head_params, _lib.heads_layout(), _lib.HEADS_NUMEL, _lib.HEADS_NUMEL)
         self.compute_mode = None
         self.momentum = momentum
+        # loss of the fused step: "cosine" = the reference's negative-free loss (ref:174,211; the default, always);
+        # "infonce" = opt-in InfoNCE over the target projections of ALL data-parallel ranks (north_star (3); no
+        # reference counterpart)
+        self.loss_mode = "cosine"
+        self.temperature = 0.2
+        self.nce_group = None          # process group whose ranks contribute keys (None = default group)
         self._ws = {}
         self._ws_busy = set()
         self._fixed_masks = None       # tests: (mask_online, mask_target) consumed instead of the RNG
@@ -773,7 +810,23 @@ class DualStreamNetwork(nn.Module):
             loss, dfeat = out[:1], out[4:].view(B, 384)
             base, nbytes = _aligned(ws)
             hg = hs.grads() if with_backward else None
-            if scale_t is not None:
+            if self.loss_mode == "infonce":
+                pred = torch.empty(B, 128, dtype=torch.float32, device=dev)
+                tgt = torch.empty(B, 128, dtype=torch.float32, device=dev)
+                check(lib.v2s_heads_forward(ptr(hs.flat), ptr(feat_o), ptr(feat_t), ptr(mask_o), ptr(mask_t), ptr(pred),
+                                            ptr(tgt), B, C.c_void_p(base), nbytes, stream_ptr()), "heads_forward")
+                keys, off = gather_keys(tgt, self.nce_group)
+                dpred = torch.empty(B, 128, dtype=torch.float32, device=dev) if with_backward else None
+                row_loss = torch.empty(B, dtype=torch.float32, device=dev)
+                check(lib.v2s_infonce_loss(ptr(pred), ptr(keys), ptr(loss), ptr(row_loss), ptr(dpred), B, keys.shape[0], off,
+                                           float(self.temperature), int(accumulation_steps), float(grad_scale),
+                                           ptr(scale_t), stream_ptr()), "infonce_loss")
+                if with_backward:
+                    check(lib.v2s_heads_backward(ptr(hs.flat), ptr(hg), ptr(feat_o), ptr(mask_o), ptr(dpred), ptr(dfeat), B,
+                                                 C.c_void_p(base), nbytes, stream_ptr()), "heads_backward")
+            elif self.loss_mode != "cosine":
+                raise ValueError(f"loss_mode {self.loss_mode!r}: 'cosine' (reference) or 'infonce'")
+            elif scale_t is not None:
                 check(lib.v2s_heads_loss_fwd_bwd_amp(ptr(hs.flat), ptr(hg), ptr(feat_o), ptr(feat_t), ptr(mask_o),
                                                      ptr(mask_t), ptr(dfeat), None, None, ptr(loss), B,
                                                      int(accumulation_steps), ptr(scale_t), 1 if with_backward else 0,

@@ -57,6 +57,11 @@ def train_self_supervised(model, dataloader, epochs, optimizer, criterion, check
     model, optimizer, start_epoch, _ = load_checkpoint(model, optimizer, checkpoint_path, device)
     device = device or next(model.parameters()).device
     fused = isinstance(criterion, nn.CosineSimilarity) and criterion.dim == 1 and hasattr(model, "ssp_step")
+    from .modules import InfoNCELoss
+    if isinstance(criterion, InfoNCELoss) and hasattr(model, "ssp_step"):      # opt-in, never the reference recipe
+        model.loss_mode, model.temperature, model.nce_group, fused = "infonce", criterion.temperature, criterion.group, True
+    elif hasattr(model, "loss_mode"):
+        model.loss_mode = "cosine"
     if scaler is None and getattr(model, "compute_mode", None) == "fp16" or \
             (scaler is None and getattr(model, "compute_mode", None) is None and _default_mode() == "fp16"):
         scaler = torch.amp.GradScaler("cuda")                      # ref:175
@@ -74,7 +79,7 @@ def train_self_supervised(model, dataloader, epochs, optimizer, criterion, check
                 loss = model.ssp_step(view1, view2, accumulation_steps, grad_scale=scaler if use_scaler else 1.0)
             else:
                 pred, tgt = model(view1, view2)
-                loss = -torch.mean(criterion(pred, tgt)) / accumulation_steps
+                loss = (criterion(pred, tgt) if isinstance(criterion, InfoNCELoss) else -torch.mean(criterion(pred, tgt))) / accumulation_steps
                 (scaler.scale(loss) if use_scaler else loss).backward()
             if (i + 1) % accumulation_steps == 0 or (i + 1) == n:
                 if use_scaler:
