@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ssp", choices=["ssp", "accum8", "finetune", "eval1024"])
+    ap.add_argument("--loss", default="cosine", choices=["cosine", "infonce"],
+                    help="cosine = the reference's loss (ref:174,211; default); infonce = opt-in global-negative InfoNCE "
+                         "(BASELINE config 3: all-gather of the target projections over the ranks)")
     ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default 128; eval1024: 1024)")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=32, help="bounded CPU sample (pairs per CPU step)")
@@ -270,6 +273,7 @@ def main():
     sync = None
     if args.workload in ("ssp", "accum8"):
         model = vit2spn.DualStreamNetwork().to(dev).train()
+        model.loss_mode = args.loss
         vit2spn.parallel.broadcast_parameters(model)     # identical replicas
         opt = vit2spn.FusedAdam(model.parameters(), lr=1e-4)
         if world > 1 and not args.no_overlap:
@@ -292,7 +296,9 @@ def main():
             return loss
         units_per_step, unit, flop_per_unit = B * micro, "pairs/s", FLOP_PER_PAIR
         metric = METRIC
-        workload = ("ViT-Tiny dual-stream SSP full step (4 backbones fwd, 2 bwd, heads, cosine loss, Adam lr 1e-4, EMA 0.999), "
+        loss_name = "cosine loss" if args.loss == "cosine" else ("InfoNCE loss (temperature 0.2) over the target projections "
+                                                                  "all-gathered from every rank (NCCL)")
+        workload = (f"ViT-Tiny dual-stream SSP full step (4 backbones fwd, 2 bwd, heads, {loss_name}, Adam lr 1e-4, EMA 0.999), "
                     + ("accumulation 1, batch 128/GPU (BASELINE config 2)" if micro == 1 else
                        "reference recipe: 8 accumulated micro-steps of 128 pairs per optimizer step (ref:39,215)"))
     elif args.workload == "finetune":
