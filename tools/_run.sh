@@ -1,2 +1,2 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests/test_infonce.py tests/test_abi.py -q -s 2>&1 | grep -E "infonce|passed|failed|Error|assert" | head -40
+V2S_GEMM_DEBUG=1 timeout 120 python tools/attn_timing.py 2>&1 | tail -25
