@@ -44,4 +44,5 @@ us = e0.elapsed_time(e1) * 100
 _lib.check(_lib.lib.v2s_debug_counters(buf))
 d = list(buf)
 names = ["wait_s", "P", "wait_load", "wait_dp", "dS", "wait_dq", "dQ_stage_store", "wait_kv", "dKdV_drain"]
-print(f"bwd B={B}: {us:.1f} us per launch; thread 32 of CTA 0 (both tiles): " + "  ".join(f"{n} {v}" for n, v in zip(names, d[16:25])) + f"  D {d[26]}  total {d[25]}")
+nj = max(d[27], 1)
+print(f"bwd B={B}: {us:.1f} us per launch; thread 32 of CTA 0, cycles per job (both tiles; {nj} jobs): " + "  ".join(f"{n} {v // nj}" for n, v in zip(names, d[16:25])) + f"  D {d[26] // nj}  total {d[25] // nj}")

@@ -515,8 +515,14 @@ __global__ void __launch_bounds__(PF_THREADS, 1) attn_fwd_persist_kernel(const _
 }
 
 // ---- backward ---------------------------------------------------------------------------------
-// One CTA per (head, image, backbone); the two 128-row query tiles are processed one after the
-// other while dK / dV accumulate in tensor memory across both.
+// Persistent CTAs (one per SM) over the (head, image, backbone) jobs; the two 128-row query tiles of a job are processed
+// one after the other while dK / dV accumulate in tensor memory across both.  A job is a serial chain (S -> P -> dP -> dS
+// -> dQ, dK, dV) that needs almost all of shared memory (212 KB: the transposed uses of P and dS must come from shared
+// memory), so nothing of the NEXT job can be resident early except what the chain has already released: its K and V are
+// loaded as soon as the last dQ UMMAs have retired (they overlap the dQ / dK / dV drains), its Q tile after the last dK
+// UMMAs; everything else the job will need (its first dO tile, the second Q / dO tiles) is prefetched into L2 a job /
+// a tile ahead, so that the loads the chain does wait for are L2 hits (measured before: 35 % of a job was waiting for
+// DRAM-latency TMA loads, one CTA per job).
 //   S  = Q_t K^T                      (UMMA 128x208x64)         -> P = exp2(S*c - lse*log2e)  (bf16, smem)
 //   dP = dO_t V^T                     (UMMA 128x208x64)         -> dS = P * (dP - D) / 8      (bf16, smem)
 //   dV += P^T dO_t,  dK += dS^T Q_t   (UMMA 128x64x128, A MN-major = the same smem tiles read transposed)
@@ -538,6 +544,7 @@ struct alignas(64) AttnBwdParams {
   CUtensorMap tmQ[MAXG], tmKV[MAXG], tmDO[MAXG], tmDQKV[MAXG];
   const bf16* ctx[MAXG];
   const float* lse[MAXG];
+  int B, total_jobs;
   int* err_flag;
   long long* dbg;   // optional phase cycle counters of CTA 0 (V2S_GEMM_DEBUG): [16..27]
 };
@@ -567,8 +574,15 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
   uint64_t* bar_dq = bar_ds + 2;      // [2]
   uint64_t* bar_kv = bar_dq + 2;      // [2] all MMAs of the tile retired
   uint64_t* bar_free = bar_kv + 2;    // [1] count 256: tile-0 buffers and TMEM[0,208) reusable
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_free + 1);
-  const int h = blockIdx.x, b = blockIdx.y, g = blockIdx.z;
+  uint64_t* bar_done = bar_free + 1;  // [1] count 256: the dQ store of the job's second tile has read its staging tile
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_done + 1);
+  const int njobs = ((int)blockIdx.x < p.total_jobs) ? (p.total_jobs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  auto decode = [&](int n, int& h, int& b, int& g) {
+    const int J = blockIdx.x + n * gridDim.x;
+    h = J % NH;
+    const int r = J / NH;
+    b = r % p.B; g = r / p.B;
+  };
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
 
   if (warp == 0) {
@@ -579,6 +593,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
         ptx::mbar_init(&bar_kv[t], 1);
       }
       ptx::mbar_init(bar_free, 256);
+      ptx::mbar_init(bar_done, 256);
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -610,62 +625,104 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
     const uint32_t idesc_s = make_idesc_lp(LP::kIdescFmt, QT, KPAD, 0, 0);
     const uint32_t idesc_dq = make_idesc_lp(LP::kIdescFmt, QT, DH, 0, 1);
     const uint32_t idesc_kv = make_idesc_lp(LP::kIdescFmt, QT, DH, 1, 1);
-#pragma unroll 1
-    for (int t = 0; t < 2; ++t) {
-      if (t == 1) {
-        ptx::mbar_wait(&bar_kv[0], 0, p.err_flag, 21);     // tile-0 MMAs no longer read Q/dO/P/dS
-        ptx::mbar_wait(bar_free, 0, p.err_flag, 22);       // dQ_0 drained, staging store done
-      }
+    constexpr uint32_t LOAD0_BYTES = 2 * Q_TILE_BYTES + 2 * KV_TILE_BYTES;
+    if (njobs > 0) {      // the first job: everything at once
+      int h, b, g;
+      decode(0, h, b, g);
       if (ptx::elect_one()) {
-        ptx::mbar_arrive_expect_tx(&bar_load[t], 2 * Q_TILE_BYTES + (t == 0 ? 2 * KV_TILE_BYTES : 0));
-        ptx::tma_load_3d(smem + B_OFF_Q, &p.tmQ[g], &bar_load[t], h * DH, t * QT, b);
-        ptx::tma_load_3d(smem + B_OFF_DO, &p.tmDO[g], &bar_load[t], h * DH, t * QT, b);
-        if (t == 0) {
-          ptx::tma_load_3d(smem + B_OFF_K, &p.tmKV[g], &bar_load[t], D + h * DH, 0, b);
-          ptx::tma_load_3d(smem + B_OFF_V, &p.tmKV[g], &bar_load[t], 2 * D + h * DH, 0, b);
+        ptx::mbar_arrive_expect_tx(&bar_load[0], LOAD0_BYTES);
+        ptx::tma_load_3d(smem + B_OFF_Q, &p.tmQ[g], &bar_load[0], h * DH, 0, b);
+        ptx::tma_load_3d(smem + B_OFF_DO, &p.tmDO[g], &bar_load[0], h * DH, 0, b);
+        ptx::tma_load_3d(smem + B_OFF_K, &p.tmKV[g], &bar_load[0], D + h * DH, 0, b);
+        ptx::tma_load_3d(smem + B_OFF_V, &p.tmKV[g], &bar_load[0], 2 * D + h * DH, 0, b);
+      }
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int n = 0; n < njobs; ++n) {
+      const uint32_t ph = n & 1;
+      int h, b, g, h2 = 0, b2 = 0, g2 = 0;
+      decode(n, h, b, g);
+      const bool has_next = n + 1 < njobs;
+      if (has_next) decode(n + 1, h2, b2, g2);
+      if (ptx::elect_one()) {      // into L2 now, into shared memory when the chain gets there
+        ptx::tma_prefetch_3d(&p.tmQ[g], h * DH, QT, b);
+        ptx::tma_prefetch_3d(&p.tmDO[g], h * DH, QT, b);
+        if (has_next) {
+          ptx::tma_prefetch_3d(&p.tmDO[g2], h2 * DH, 0, b2);
+          ptx::tma_prefetch_3d(&p.tmQ[g2], h2 * DH, 0, b2);
         }
       }
       __syncwarp();
-      ptx::mbar_wait(&bar_load[t], 0, p.err_flag, 23);
-      ptx::tc_fence_after();
-      if (ptx::elect_one()) {      // S = Q_t K^T
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        if (t == 1) {
+          ptx::mbar_wait(&bar_kv[0], ph, p.err_flag, 21);     // tile-0 MMAs no longer read Q/dO/P/dS
+          ptx::mbar_wait(bar_free, ph, p.err_flag, 22);       // dQ_0 drained, staging store done
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(&bar_load[1], 2 * Q_TILE_BYTES);
+            ptx::tma_load_3d(smem + B_OFF_Q, &p.tmQ[g], &bar_load[1], h * DH, QT, b);
+            ptx::tma_load_3d(smem + B_OFF_DO, &p.tmDO[g], &bar_load[1], h * DH, QT, b);
+          }
+          __syncwarp();
+        }
+        ptx::mbar_wait(&bar_load[t], ph, p.err_flag, 23);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {      // S = Q_t K^T
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) mma(tmem_base, sq + k * 32, 16, sk + k * 32, 16, idesc_s, k > 0);
-        ptx::umma_commit(&bar_s[t]);
+          for (int k = 0; k < DH / 16; ++k) mma(tmem_base, sq + k * 32, 16, sk + k * 32, 16, idesc_s, k > 0);
+          ptx::umma_commit(&bar_s[t]);
+        }
+        __syncwarp();
+        // P ready -> dP = dO_t V^T (over S's columns) and dV += P^T dO_t
+        ptx::mbar_wait(&bar_p[t], ph, p.err_flag, 24);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) mma(tmem_base, sdo + k * 32, 16, sv + k * 32, 16, idesc_s, k > 0);
+          ptx::umma_commit(&bar_dp[t]);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int k = 0; k < QT / 16; ++k)
+              mma(tmem_base + TM_DV + mt * DH, sp + 2 * mt * (QT * 128) + k * 2048, QT * 128, sdo + k * 2048, 8192,
+                  idesc_kv, (t > 0 || k > 0));
+        }
+        __syncwarp();
+        // dS ready -> dQ_t = dS K (over dP's columns) and dK += dS^T Q_t
+        ptx::mbar_wait(&bar_ds[t], ph, p.err_flag, 25);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int j = 0; j < KPAD / 16; ++j)
+            mma(tmem_base, sds + (j >> 2) * (QT * 128) + (j & 3) * 32, 16, sk + j * 2048, 8192, idesc_dq, j > 0);
+          ptx::umma_commit(&bar_dq[t]);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int k = 0; k < QT / 16; ++k)
+              mma(tmem_base + TM_DK + mt * DH, sds + 2 * mt * (QT * 128) + k * 2048, QT * 128, sq + k * 2048, 8192,
+                  idesc_kv, (t > 0 || k > 0));
+          ptx::umma_commit(&bar_kv[t]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      // P ready → dP = dO_t V^T (over S's columns) and dV += P^T dO_t
-      ptx::mbar_wait(&bar_p[t], 0, p.err_flag, 24);
-      ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k) mma(tmem_base, sdo + k * 32, 16, sv + k * 32, 16, idesc_s, k > 0);
-        ptx::umma_commit(&bar_dp[t]);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-          for (int k = 0; k < QT / 16; ++k)
-            mma(tmem_base + TM_DV + mt * DH, sp + 2 * mt * (QT * 128) + k * 2048, QT * 128, sdo + k * 2048, 8192,
-                idesc_kv, (t > 0 || k > 0));
+      if (has_next) {
+        // the next job's operands, each as soon as the chain has released its buffer (one barrier phase for all four)
+        ptx::mbar_wait(&bar_dq[1], ph, p.err_flag, 19);       // S_1, dP_1, dV, dQ_1 retired: K and V are dead
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(&bar_load[0], LOAD0_BYTES);
+          ptx::tma_load_3d(smem + B_OFF_K, &p.tmKV[g2], &bar_load[0], D + h2 * DH, 0, b2);
+          ptx::tma_load_3d(smem + B_OFF_V, &p.tmKV[g2], &bar_load[0], 2 * D + h2 * DH, 0, b2);
+        }
+        __syncwarp();
+        ptx::mbar_wait(&bar_kv[1], ph, p.err_flag, 20);       // dK retired: Q is dead
+        if (ptx::elect_one()) ptx::tma_load_3d(smem + B_OFF_Q, &p.tmQ[g2], &bar_load[0], h2 * DH, 0, b2);
+        __syncwarp();
+        ptx::mbar_wait(bar_done, ph, p.err_flag, 18);         // the dQ_1 store has read its staging tile (the dO buffer)
+        if (ptx::elect_one()) ptx::tma_load_3d(smem + B_OFF_DO, &p.tmDO[g2], &bar_load[0], h2 * DH, 0, b2);
+        __syncwarp();
       }
-      __syncwarp();
-      // dS ready → dQ_t = dS K (over dP's columns) and dK += dS^T Q_t
-      ptx::mbar_wait(&bar_ds[t], 0, p.err_flag, 25);
-      ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-#pragma unroll
-        for (int j = 0; j < KPAD / 16; ++j)
-          mma(tmem_base, sds + (j >> 2) * (QT * 128) + (j & 3) * 32, 16, sk + j * 2048, 8192, idesc_dq, j > 0);
-        ptx::umma_commit(&bar_dq[t]);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-          for (int k = 0; k < QT / 16; ++k)
-            mma(tmem_base + TM_DK + mt * DH, sds + 2 * mt * (QT * 128) + k * 2048, QT * 128, sq + k * 2048, 8192,
-                idesc_kv, (t > 0 || k > 0));
-        ptx::umma_commit(&bar_kv[t]);
-      }
-      __syncwarp();
     }
   } else {
     const int q = warp & 3;                      // TMEM lane quarter
@@ -682,20 +739,33 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
     long long c0 = DBG ? clock64() : 0, c1;
     const long long t_begin = c0;
 #define V2S_TICK(k) if (DBG) { c1 = clock64(); tk[k] += c1 - c0; c0 = c1; }
+    // The O row (for D = rowsum(dO * O)) and the row's log-sum-exp come from global memory.  Their loads are issued one
+    // tile ahead into registers (this warp role has 200+ registers to spare), so the DRAM latency is never on the chain.
+    uint4 ov[8];
+    float lse_nxt = 0.f;
+    auto fetch_row = [&](int n2, int t2) {
+      int h2, b2, g2;
+      decode(n2, h2, b2, g2);
+      const int qr = t2 * QT + row;
+      if (qr < NT) {
+        const uint4* orow = reinterpret_cast<const uint4*>(p.ctx[g2] + ((int64_t)b2 * NT + qr) * D + h2 * DH);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) ov[c] = __ldg(orow + c);
+        lse_nxt = __ldg(p.lse[g2] + ((int64_t)b2 * NH + h2) * NT + qr);
+      }
+    };
+    if (njobs > 0) fetch_row(0, 0);
+#pragma unroll 1
+    for (int n = 0; n < njobs; ++n) {
+    const uint32_t ph = n & 1;
+    int h, b, g;
+    decode(n, h, b, g);
     for (int t = 0; t < 2; ++t) {
       const int qrow = t * QT + row;
       const bool valid = qrow < NT;
       // padding query rows (>= 197): lse2 = +huge makes every p underflow to exactly 0, no per-element row mask needed
-      const float lse2 = valid ? p.lse[g][((int64_t)b * NH + h) * NT + qrow] * LOG2E : 3.0e38f;
-      // the O row comes from global memory: issue its loads before waiting for the TMA tiles, so that both
-      // latencies overlap; D is then computed while the S = Q K^T UMMAs run
-      uint4 ov[8];
-      if (valid) {
-        const uint4* orow = reinterpret_cast<const uint4*>(p.ctx[g] + ((int64_t)b * NT + qrow) * D + h * DH);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) ov[c] = __ldg(orow + c);
-      }
-      ptx::mbar_wait(&bar_load[t], 0, p.err_flag, 30);
+      const float lse2 = valid ? lse_nxt * LOG2E : 3.0e38f;
+      ptx::mbar_wait(&bar_load[t], ph, p.err_flag, 30);
       V2S_TICK(2)
       // ---- D = rowsum(dO * O) (both halves compute it) ----
       float Dr = 0.f;
@@ -711,9 +781,11 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
           }
         }
       }
+      if (t == 0) fetch_row(n, 1);
+      else if (n + 1 < njobs) fetch_row(n + 1, 0);
       V2S_TICK(9)
       // ---- P = exp(S/8 - lse) ----
-      ptx::mbar_wait(&bar_s[t], 0, p.err_flag, 26);
+      ptx::mbar_wait(&bar_s[t], ph, p.err_flag, 26);
       V2S_TICK(0)
       ptx::tc_fence_after();
 #pragma unroll 1
@@ -758,7 +830,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
       V2S_TICK(1)
       // ---- dS = P * (dP - D) / 8 ----
       const float mDs = -Dr * SCALE;
-      ptx::mbar_wait(&bar_dp[t], 0, p.err_flag, 27);
+      ptx::mbar_wait(&bar_dp[t], ph, p.err_flag, 27);
       V2S_TICK(3)
       ptx::tc_fence_after();
 #pragma unroll 1
@@ -804,7 +876,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
       ptx::mbar_arrive(&bar_ds[t]);
       V2S_TICK(4)
       // ---- dQ_t: TMEM [0,64) → bf16 → staged in the (dead) dO buffer → TMA store ----
-      ptx::mbar_wait(&bar_dq[t], 0, p.err_flag, 28);
+      ptx::mbar_wait(&bar_dq[t], ph, p.err_flag, 28);
       V2S_TICK(5)
       ptx::tc_fence_after();
       ptx::tmem_ld_32x32(tlane + half * 32, r);
@@ -829,11 +901,11 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
         ptx::tma_commit_group();
         ptx::tma_wait_group_read<0>();
       }
-      if (t == 0) ptx::mbar_arrive(bar_free);
+      ptx::mbar_arrive(t == 0 ? bar_free : bar_done);     // (thread 32: after its store has read the staging tile)
       V2S_TICK(6)
     }
     // ---- dK, dV: TMEM → bf16 → staged in the P buffer → TMA store (rows = keys) ----
-    ptx::mbar_wait(&bar_kv[1], 0, p.err_flag, 29);       // every MMA has retired
+    ptx::mbar_wait(&bar_kv[1], ph, p.err_flag, 29);      // every MMA of the job has retired
     V2S_TICK(7)
     ptx::tc_fence_after();
 #pragma unroll 1
@@ -862,14 +934,19 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
           ptx::tma_store_3d(&p.tmDQKV[g], smem + B_OFF_P + (which * 2 + mt) * Q_TILE_BYTES,
                             (1 + which) * D + h * DH, mt * QT, b);
       ptx::tma_commit_group();
-      ptx::tma_wait_group<0>();
+      ptx::tma_wait_group_read<0>();
     }
+    // the next job's P pass overwrites the staging tiles: nobody leaves before the stores have read them
+    ptx::bar_sync(1, 256);
     V2S_TICK(8)
+    }   // jobs
+    if (threadIdx.x == 32) ptx::tma_wait_group<0>();
 #undef V2S_TICK
-    if (DBG && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 32) {
+    if (DBG && blockIdx.x == 0 && threadIdx.x == 32) {
       for (int k = 0; k < 9; ++k) p.dbg[16 + k] = tk[k];
       p.dbg[25] = clock64() - t_begin;
       p.dbg[26] = tk[9];
+      p.dbg[27] = njobs;
     }
   }
   ptx::tc_fence_before();
@@ -948,6 +1025,8 @@ int launch_attn_bwd_tc(const void* const* qkv, const void* const* ctx, const flo
     p.lse[g] = lse[g];
   }
   p.dbg = tc_dbg_counters();
+  p.B = B;
+  p.total_jobs = NH * B * groups;
   static bool attr[MAX_DEVICES] = {false};
   if (!attr[cur_device()]) {
     V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, LpBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
@@ -956,7 +1035,8 @@ int launch_attn_bwd_tc(const void* const* qkv, const void* const* ctx, const flo
     V2S_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<true, LpF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
     attr[cur_device()] = true;
   }
-  const dim3 grid(NH, B, groups);
+  const int sms = tc_num_sms();
+  const dim3 grid(p.total_jobs < sms ? p.total_jobs : sms);
   if (lp_f16) {
     if (p.dbg) V2S_CUDA_OK(launch_pdl(attn_bwd_tc_kernel<true, LpF16>, grid, dim3(B_THREADS), (size_t)B_SMEM, s, p));
     else V2S_CUDA_OK(launch_pdl(attn_bwd_tc_kernel<false, LpF16>, grid, dim3(B_THREADS), (size_t)B_SMEM, s, p));
