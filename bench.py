@@ -23,8 +23,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 # random-init ViT-Tiny weights by specification (north_star: no ImageNet checkpoint offline)
 os.environ.setdefault("V2S_ALLOW_RANDOM_INIT", "1")
+COMM_SMS = int(os.environ.get("V2S_COMM_SMS", "8"))
 # the gradient all-reduce overlaps the backward pass on the SMs the compute grids leave free (parallel.py)
-os.environ.setdefault("NCCL_MAX_CTAS", "8")
+os.environ.setdefault("NCCL_MAX_CTAS", str(COMM_SMS))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
@@ -32,7 +33,7 @@ FLOP_PER_PAIR = 19.945e9          # algorithmic FLOPs of one p
 FLOP_PER_IMAGE_FT = 7.463e9       # fine-tune step per image, FLOP_PER_IMAGE_FWD forward only
 FLOP_PER_IMAGE_FWD = 2.507e9
 METRIC = "dual-view SSP pairs/sec, ViT-Tiny b128/GPU"
-COMM_SMS = 8
+SYNC_SPLITS = tuple(int(x) for x in os.environ.get("V2S_SYNC_SPLITS", "8,4").split(","))
 
 
 def parse():
@@ -277,7 +278,7 @@ def main():
         vit2spn.parallel.broadcast_parameters(model)     # identical replicas
         opt = vit2spn.FusedAdam(model.parameters(), lr=1e-4)
         if world > 1 and not args.no_overlap:
-            sync = vit2spn.parallel.OverlappedGradSync(model, splits=(8, 4), comm_sms=COMM_SMS)
+            sync = vit2spn.parallel.OverlappedGradSync(model, splits=SYNC_SPLITS, comm_sms=COMM_SMS)
         micro = 8 if args.workload == "accum8" else 1
 
         def step(a, b):
@@ -528,7 +529,7 @@ def main():
     if rank == 0:
         par = f"dp{world}"
         if world > 1:
-            par += (" (gradient all-reduce in 4 buckets overlapped with backward, 1/world folded into Adam)" if sync is not None
+            par += (f" (gradient all-reduce in {len(SYNC_SPLITS) + 1} block ranges + heads overlapped with backward, {COMM_SMS} SMs left to NCCL, 1/world folded into Adam)" if sync is not None
                     else " (3 flat all-reduces after backward)")
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,

@@ -1,9 +1,15 @@
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r02_f_attn_bwd_persist.json 2> gpurun_out/bench_f.err; tail -c 300 gpurun_out/bench_f.err
-python - <<'PY'
+run() { # name, env...
+  name=$1; shift
+  env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 20 --warmup 5 --no-e2e > gpurun_out/bench_n8_$name.json 2> gpurun_out/bench_n8_$name.err
+  python - <<PY
 import json
-for l in open('gpurun_out/bench_r02_f_attn_bwd_persist.json'):
+for l in open('gpurun_out/bench_n8_$name.json'):
     if l.startswith('{'):
-        d=json.loads(l); print(d['value'], d['ms_per_step'], d['e2e']['value']); print({k:round(v['ms_per_step'],3) for k,v in d['roofline']['classes'].items()})
+        d=json.loads(l); print('$name', d['value'], d['ms_per_step'])
 PY
+}
+run c4_62 V2S_COMM_SMS=4 V2S_SYNC_SPLITS=6,2
+run c2_62 V2S_COMM_SMS=2 V2S_SYNC_SPLITS=6,2
+run c8_62 V2S_COMM_SMS=8 V2S_SYNC_SPLITS=6,2
+run c4_731 V2S_COMM_SMS=4 V2S_SYNC_SPLITS=7,3,1

@@ -69,7 +69,11 @@ class OverlappedGradSync:
 
     The compute kernels are persistent grids of one 227-KB-shared-memory CTA per SM, so a NCCL kernel cannot co-reside
     with them: while collectives are in flight the library sizes its grids to ``#SMs - comm_sms``
-    (``v2s_set_sm_limit``) and NCCL (``NCCL_MAX_CTAS``, set by the caller before init) runs on the SMs left free."""
+    (``v2s_set_sm_limit``) and NCCL (``NCCL_MAX_CTAS``, set by the caller before init) runs on the SMs left free.
+    Shrinking the grids costs ``comm_sms / #SMs`` of every kernel launched meanwhile, so the limit is set as late as
+    possible: at the first ``range_ready``, together with the (small) head bucket.  Measured on 8 B200s (ms/step, 6.96
+    on one GPU): 8 SMs for NCCL 7.19-7.21 with ranges (12,8,4,0) or (12,6,2,0); 4 SMs 7.25; 2 SMs 7.75 (NCCL too slow
+    to hide); four ranges (12,7,3,1,0) with 4 SMs 7.43."""
 
     def __init__(self, model, group=None, splits=(8, 4), comm_sms=8):
         from . import _lib
@@ -90,21 +94,30 @@ class OverlappedGradSync:
         return store.flat_grad[a:b]
 
     def begin(self):
-        from . import _lib
         self._works = []
-        if self.world > 1 and self.comm_sms > 0:
+        self._limited = False
+        self._heads_pending = False
+
+    def _limit(self):
+        from . import _lib
+        if not self._limited and self.world > 1 and self.comm_sms > 0:
             if self._sms is None:
                 self._sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
             _lib.check(_lib.lib.v2s_set_sm_limit(self._sms - self.comm_sms), "set_sm_limit")
+        self._limited = True
 
     def _reduce(self, t):
         if self.world > 1:
             self._works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def heads_ready(self):
-        self._reduce(self.model._head_store.flat_grad)
+        self._heads_pending = True      # sent with the first block range (see the class note)
 
     def range_ready(self, hi, lo):
+        self._limit()
+        if self._heads_pending:
+            self._reduce(self.model._head_store.flat_grad)
+            self._heads_pending = False
         for s in self.model._stores()[:2][::-1]:
             self._reduce(self._slice(s, hi, lo))
 
@@ -112,6 +125,9 @@ class OverlappedGradSync:
         """Join every collective on the current stream; the gradients hold the SUM over ranks (1/world is folded into
         the optimizer if given, else applied here)."""
         from . import _lib
+        if getattr(self, "_heads_pending", False):
+            self._reduce(self.model._head_store.flat_grad)
+            self._heads_pending = False
         for w in self._works:
             w.wait()
         self._works = []
