@@ -552,7 +552,7 @@ def test_repeatability_under_overlapped_launches(dev):
 @pytest.mark.parametrize("batch", [1, 33])
 def test_odd_batches_bf16_vs_fp32_check_mode(dev, batch):
     """Batches that leave partial 128-row tiles and fewer attention jobs than SMs (B=1: 24 jobs): the bf16
-    tensor-core path against this library's own fp32 check mode (itself pinned to the oracle above)."""
+    tensor-core path against this library's own fp32 check mode, and both against the oracle."""
     from oracle import vit2spn_oracle as orc
     state = orc.init_state(11, 0.02)
     x1, x2 = orc.synthetic_views(batch, seed=9)
@@ -566,6 +566,17 @@ def test_odd_batches_bf16_vs_fp32_check_mode(dev, batch):
     g_rel, worst = _rel_l2(res["bf16"][1], {k: v.cpu() for k, v in res["fp32"][1].items()})
     # bf16 rounding noise in the gradient averages out over the batch (2.8e-2 at B=3, 5.8e-2 at B=1, 4e-3 at B=128)
     assert g_rel <= (4e-2 if batch >= 16 else 1e-1), (g_rel, worst)
+    # ... and both modes against the ORACLE at the same ragged sizes: the fp32 check mode at the north_star fp32 gates,
+    # the bf16 mode against the oracle's bf16 rounding model (same rounding points, different summation order)
+    o_loss, o_g = _gpu_oracle(orc, state, x1, x2, dev, "fp32")
+    r_loss, r_g = _gpu_oracle(orc, state, x1, x2, dev, "rounded")
+    f_rel, _ = _rel_l2(res["fp32"][1], o_g)
+    b_rel, bworst = _rel_l2(res["bf16"][1], r_g)
+    lf = abs(res["fp32"][0] - o_loss) / abs(o_loss)
+    lb = abs(res["bf16"][0] - r_loss) / abs(r_loss)
+    print(f"[B={batch}] fp32 mode vs oracle: loss {lf:.1e}, grads {f_rel:.1e}; bf16 mode vs rounding model: loss {lb:.1e}, grads {b_rel:.1e}")
+    assert lf <= 1e-5 and f_rel <= 1e-4
+    assert lb <= 1e-3 and b_rel <= 2e-2, (lb, b_rel, bworst)
     from vit2spn import _lib
     assert _lib.lib.v2s_debug_flag() == 0
 
