@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--loss", default="cosine", choices=["cosine", "infonce"],
                     help="cosine = the reference's loss (ref:174,211; default); infonce = opt-in global-negative InfoNCE "
                          "(BASELINE config 3: all-gather of the target projections over the ranks)")
+    ap.add_argument("--graph", action="store_true", help="replay the micro-step from a CUDA graph (ssp_step_graphed; 1 GPU)")
     ap.add_argument("--batch", type=int, default=None, help="samples per GPU (default 128; eval1024: 1024)")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=32, help="bounded CPU sample (pairs per CPU step)")
@@ -285,7 +286,10 @@ def main():
             loss = None
             for i in range(micro):
                 last = i == micro - 1
-                loss = model.ssp_step(a, b, accumulation_steps=micro, grad_sync=sync if (last and world > 1) else None)
+                if args.graph and world == 1:
+                    loss = model.ssp_step_graphed(a, b, accumulation_steps=micro)
+                else:
+                    loss = model.ssp_step(a, b, accumulation_steps=micro, grad_sync=sync if (last and world > 1) else None)
             if world > 1:
                 if sync is not None:
                     sync.finish(opt)
@@ -301,7 +305,8 @@ def main():
                                                                   "all-gathered from every rank (NCCL)")
         workload = (f"ViT-Tiny dual-stream SSP full step (4 backbones fwd, 2 bwd, heads, {loss_name}, Adam lr 1e-4, EMA 0.999), "
                     + ("accumulation 1, batch 128/GPU (BASELINE config 2)" if micro == 1 else
-                       "reference recipe: 8 accumulated micro-steps of 128 pairs per optimizer step (ref:39,215)"))
+                       "reference recipe: 8 accumulated micro-steps of 128 pairs per optimizer step (ref:39,215)")
+                    + ("; micro-step replayed from a CUDA graph" if args.graph and world == 1 else ""))
     elif args.workload == "finetune":
         model = vit2spn.FineTunedModel(num_classes=4).to(dev).train()
         opt = vit2spn.FusedAdam(model.parameters(), lr=1e-4, weight_decay=1e-4)          # ref:octmnist_ft_vit2spn.py:192
@@ -357,11 +362,12 @@ def main():
     warm = max(args.warmup, 3)
     for _ in range(warm):
         step(x1, x2)
-    l0 = _lib.lib.v2s_launch_count()
+    l0 = _lib.lib.v2s_launch_count() + getattr(model, "graph_replayed_kernels", 0)
     sampler.mark_begin()
     ms_total = timed(lambda: step(x1, x2), args.steps)
     sampler.mark_end()
-    launches = int(_lib.lib.v2s_launch_count() - l0)
+    # kernels of this library launched in the timed region (those replayed from a CUDA graph included)
+    launches = int(_lib.lib.v2s_launch_count() + getattr(model, "graph_replayed_kernels", 0) - l0)
     # host-side cost of enqueueing one step (no device wait inside): tells CPU-bound from GPU-bound
     torch.cuda.synchronize()
     h0 = time.perf_counter()

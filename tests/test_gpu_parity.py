@@ -793,3 +793,38 @@ def test_fp16_mode_meets_the_loss_gate_and_grad_scaler_recipe(dev):
     assert torch.equal(snap, model.online_network_1.vit._store.flat), "the update must be skipped on overflow"
     assert big.get_scale() == 2.0 ** 39
     assert float(opt.state_dict()["state"][0]["step"]) == 1.0          # a skipped step does not count (as torch's fused Adam)
+
+
+def test_graphed_step_equals_eager_step(dev):
+    """ssp_step_graphed: the micro-step replayed from a CUDA graph accumulates the same gradients and returns the same
+    loss as the eager launch sequence (fp32 check mode: no atomics, bit-equal), over several replays with different
+    inputs and across optimizer steps (fp32 check mode, to summation-order noise); dropout stays random per replay."""
+    import vit2spn
+    from oracle import vit2spn_oracle as orc
+    state = orc.init_state(5, 0.02)
+    xs = [tuple(t.to(dev) for t in orc.synthetic_views(4, seed=s)) for s in (1, 2, 3)]
+    res = {}
+    for kind in ("eager", "graph"):
+        model = _build(state, dev, "fp32")
+        opt = vit2spn.FusedAdam(model.parameters(), lr=1e-4)
+        opt.zero_grad()
+        losses = []
+        for it, (a, b) in enumerate(xs * 2):
+            step = model.ssp_step if kind == "eager" else model.ssp_step_graphed
+            losses.append(step(a, b, accumulation_steps=2).clone())
+            if it % 2 == 1:
+                opt.step(); opt.zero_grad(); model.update_target_network()
+        res[kind] = (torch.stack(losses), torch.cat([s.flat for s in model._stores()] + [model._head_store.flat]).clone())
+    # (split-K accumulations use atomics: equal to summation-order noise, not bit for bit)
+    assert float((res["eager"][0] - res["graph"][0]).abs().max()) <= 1e-6, (res["eager"][0], res["graph"][0])
+    # Adam normalises by sqrt(v): elements whose gradient is summation noise may move by a fraction of lr = 1e-4
+    assert float((res["eager"][1] - res["graph"][1]).abs().max()) <= 2e-5
+    assert float((res["eager"][1] - res["graph"][1]).abs().mean()) <= 1e-8
+    # bf16 with dropout: replays draw fresh masks (losses differ between two replays on the same input)
+    model = _build(state, dev, "bf16")
+    model.projection_head[2].p = 0.3
+    a, b = xs[0]
+    l = [float(model.ssp_step_graphed(a, b)) for _ in range(4)]
+    assert len(set(l[1:])) > 1, l
+    from vit2spn import _lib
+    assert _lib.lib.v2s_debug_flag() == 0

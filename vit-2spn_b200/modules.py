@@ -706,6 +706,7 @@ class DualStreamNetwork(nn.Module):
             self._head_store.reflatten()
             self._ws.clear()
             self._ws_busy.clear()
+            self.__dict__.pop("_graphs", None)
         return r
 
     def _mode(self):
@@ -852,6 +853,59 @@ class DualStreamNetwork(nn.Module):
         finally:
             self._release_workspace(ws)
         return loss[0]
+
+
+    # -- the same micro-step replayed from a CUDA graph ------------------------------------------------------------
+    def ssp_step_graphed(self, x1, x2, accumulation_steps=1):
+        """``ssp_step`` captured once per (shape, compute mode, accumulation_steps, loss mode) into a CUDA graph and
+        replayed: the ~200 kernel launches of a micro-step (with their programmatic-dependent-launch edges) cost one
+        ``cudaGraphLaunch`` of host time instead of ~2 ms of enqueueing, which is what bounds small batches (BASELINE
+        config 1: B = 8) and hosts that drive many ranks.  The first call with a new key runs eagerly (it also sets up
+        workspaces and kernel attributes) and records the graph for the following ones.  Inputs are copied into the
+        graph's own buffers (0.05 ms at B = 128); dropout masks are drawn outside the graph before every replay, so
+        every step still sees fresh masks; the returned loss tensor is the graph's output buffer (overwritten by the
+        next replay).  Not for ``grad_sync`` / GradScaler steps — use ``ssp_step`` there."""
+        x1, x2 = _check_images(x1), _check_images(x2)
+        drop = self.projection_head[2]
+        dropout_on = self._fixed_masks is None and self.training and drop.training and drop.p > 0.0
+        st, hs = self._stores(), self._head_store
+        for s_ in st + [hs]:
+            s_.ensure()                     # host-side state the eager step maintains: flat buffers, attached .grad views
+        ptrs = tuple(s_.flat.data_ptr() for s_ in st + [hs]) + tuple(s_.grads().data_ptr() for s_ in (st[0], st[1], hs))
+        key = (tuple(x1.shape), x1.device, self._mode(), int(accumulation_steps), self.loss_mode, float(self.temperature),
+               dropout_on, float(drop.p), self._fixed_masks is not None, ptrs)
+        graphs = self.__dict__.setdefault("_graphs", {})
+        if len(graphs) > 8:                 # parameters moved (.to(), re-flattening): stale graphs
+            graphs.clear()
+        ent = graphs.get(key)
+        if ent is None:
+            loss = self.ssp_step(x1, x2, accumulation_steps)          # eager: this call's result, and the warm-up
+            ent = {"x1": torch.empty_like(x1), "x2": torch.empty_like(x2), "masks": None}
+            if dropout_on:
+                ent["masks"] = torch.empty(2, x1.shape[0], 1024, dtype=torch.float32, device=x1.device)
+            saved = self._fixed_masks
+            if dropout_on:
+                self._fixed_masks = (ent["masks"][0], ent["masks"][1])
+            g = torch.cuda.CUDAGraph()
+            n0 = lib.v2s_launch_count()
+            try:
+                torch.cuda.synchronize(x1.device)
+                with torch.cuda.graph(g):
+                    ent["loss"] = self.ssp_step(ent["x1"], ent["x2"], accumulation_steps)
+            finally:
+                self._fixed_masks = saved
+            ent["graph"], ent["kernels"] = g, int(lib.v2s_launch_count() - n0)      # kernels one replay launches
+            graphs[key] = ent
+            return loss
+        ent["x1"].copy_(x1, non_blocking=True)
+        ent["x2"].copy_(x2, non_blocking=True)
+        if ent["masks"] is not None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            check(lib.v2s_dropout_mask(ptr(ent["masks"]), ent["masks"].numel(), float(drop.p), seed, 0, stream_ptr()),
+                  "dropout_mask")
+        ent["graph"].replay()
+        self.graph_replayed_kernels = getattr(self, "graph_replayed_kernels", 0) + ent["kernels"]
+        return ent["loss"]
 
 
 class SingleStreamNetwork(nn.Module):
