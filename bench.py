@@ -53,9 +53,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-input", default="u8", choices=["u8", "fp32"],
-                    help="host format of the e2e leg: raw uint8 28x28 source images (0.2 MB/step, resized on the GPU) or "
-                         "the reference DataLoader's fp32 views (154 MB/step)")
+    ap.add_argument("--e2e-input", default="auto", choices=["auto", "u8p", "u8", "fp32"],
+                    help="host format of the e2e leg: raw uint8 28x28 source images (0.2 MB/step) turned on the GPU into the "
+                         "16-bit patch matrix (u8p, one kernel; default where the step accepts it) or into fp32 views (u8), "
+                         "or the reference DataLoader's fp32 views (fp32, 154 MB/step)")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: plain all-reduce after backward instead of the overlapped one")
     return ap.parse_args()
 
@@ -383,8 +384,19 @@ def main():
     # ---- end to end through the public API with HOST buffers: every step copies its inputs from pinned host memory
     #      (double-buffered on a copy stream) and reads its result back on the host ------------------------------
     e2e = None
+    e2e_in = args.e2e_input
+    if e2e_in == "auto":      # the fused uint8 -> patch-matrix kernel where the step takes it (SSP step, 16-bit modes)
+        e2e_in = "u8p" if (args.workload in ("ssp", "accum8") and args.mode in ("bf16", "fp16")) else "u8"
     if not args.no_e2e:
-        if args.e2e_input == "u8":
+        if e2e_in == "u8p":
+            host = u8_host.pin_memory()
+            raw = [torch.empty_like(u8) for _ in range(2)]
+            lp_dtype = torch.bfloat16 if args.mode == "bf16" else torch.float16
+            bufs = [torch.empty(2, B, 196, 768, dtype=lp_dtype, device=dev) for _ in range(2)]
+            h2d = int(host.numel())
+            what = ("raw uint8 source images [2B,1,28,28] in pinned host memory → H2D → bilinear 224 / 3 channels / normalise / "
+                    "im2col in one kernel (v2s_preprocess_u8_patches: the 16-bit patch matrix the patch-embed GEMM reads) → step")
+        elif e2e_in == "u8":
             # the dataset's native format (28x28 uint8, ref:ssp_vit2spn_tiny.py:100-104): 2*B*784 bytes per step; the
             # resize / normalise of the reference's transform runs on the GPU inside the timed region
             host = u8_host.pin_memory()
@@ -405,7 +417,10 @@ def main():
         def upload(i):
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(done[i])
-                if args.e2e_input == "u8":
+                if e2e_in == "u8p":
+                    raw[i].copy_(host, non_blocking=True)
+                    vit2spn.preprocess_u8_patches(raw[i], out=bufs[i].view(2 * B, 196, 768))
+                elif e2e_in == "u8":
                     raw[i].copy_(host, non_blocking=True)
                     preprocess(raw[i], bufs[i])
                 else:

@@ -86,7 +86,10 @@ typedef struct v2s_group {
   const float* params;    /* flat fp32 parameters (layout above) */
   const void* params_lp;  /* bf16 copy of `params` (same element offsets); NULL in fp32 mode */
   float* grads;           /* flat fp32 gradient buffer, accumulated (+=); NULL if no backward */
-  const float* x;         /* images fp32 NCHW [batch,3,224,224] */
+  const void* x;          /* x_format 0: images fp32 NCHW [batch,3,224,224];  x_format 1: the patch matrix the patch-embed
+                           * GEMM reads, [batch*196, 768] in the mode's 16-bit format, k = c*256 + ky*16 + kx (what
+                           * v2s_preprocess_u8_patches writes) - it must stay valid until the backward call, which reads
+                           * it again for the patch-embedding weight gradient */
   float* hidden;          /* out (optional): hidden_states[-1], fp32 [batch,197,192] */
   float* feat;            /* out (optional): mean over tokens, row i at feat + i*feat_stride */
   int64_t feat_stride;    /* 192, or 384 when writing straight into the concatenated feature */
@@ -94,7 +97,7 @@ typedef struct v2s_group {
   int64_t dfeat_stride;
   const float* dhidden;   /* backward in (optional): d loss / d hidden [batch,197,192]; added */
   int32_t slot;           /* activation-stash slot (0..n_saved-1), or -1: nothing saved */
-  int32_t reserved;
+  int32_t x_format;       /* 0 or 1, see x (1: bf16 / fp16 modes only) */
 } v2s_group_t;
 
 /* ViTBackbone.forward for up to 4 backbones (ref:ssp_vit2spn_tiny.py:114-118; HF
@@ -212,6 +215,10 @@ int v2s_cast_lp(const float* src, void* dst, int64_t numel, int lp_format, void*
 /* synthetic OCTMNIST-shaped input pipeline (ref:ssp_vit2spn_tiny.py:84-96, deterministic part):
  * uint8 [batch,1,28,28] → bilinear 224x224 → 3 channels → ImageNet normalise → fp32 NCHW */
 int v2s_preprocess_u8(const uint8_t* src, float* dst, int batch, void* stream);
+/* the same pipeline written straight as the 16-bit patch matrix of v2s_group.x_format = 1 (skips the
+ * 77 MB fp32 image tensor per view and the im2col pass; bit-identical to v2s_preprocess_u8 + the library's own im2col):
+ * uint8 [n_images,1,28,28] -> [n_images*196, 768]; lp_format 0 = bf16, 1 = fp16 */
+int v2s_preprocess_u8_patches(const uint8_t* src, void* patch_rows, int n_images, int lp_format, void* stream);
 
 /* GPU half of the reference's augmentation pipeline, from `transforms.Resize((224, 224))` on
  * (ref:ssp_vit2spn_tiny.py:90-95): Pillow-exact BILINEAR resize of the 8-bit view (coefficient tables from the

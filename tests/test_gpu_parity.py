@@ -828,3 +828,40 @@ def test_graphed_step_equals_eager_step(dev):
     assert len(set(l[1:])) > 1, l
     from vit2spn import _lib
     assert _lib.lib.v2s_debug_flag() == 0
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+def test_patch_row_inputs_equal_image_inputs(dev, mode):
+    """uint8 source images -> 16-bit patch matrix in one kernel (v2s_preprocess_u8_patches, v2s_group.x_format
+    1) must give the step exactly what v2s_preprocess_u8 + the library's im2col give it: bit-equal loss (the forward pass has
+    no atomics), gradients to summation-order noise; fp32 mode refuses the format."""
+    import numpy as np
+    import vit2spn
+    from vit2spn import _lib
+    from oracle import vit2spn_oracle as orc
+    B = 5
+    state = orc.init_state(21, 0.02)
+    u8 = torch.from_numpy(np.random.default_rng(3).integers(0, 256, size=(2 * B, 1, 28, 28), dtype=np.uint8)).to(dev)
+    views = torch.empty(2 * B, 3, 224, 224, device=dev)
+    _lib.check(_lib.lib.v2s_preprocess_u8(_lib.ptr(u8), _lib.ptr(views), 2 * B, _lib.stream_ptr()))
+    lp = torch.bfloat16 if mode == "bf16" else torch.float16
+    rows = vit2spn.preprocess_u8_patches(u8, dtype=lp)
+    assert rows.shape == (2 * B, 196, 768) and rows.dtype == lp
+    # the patch matrix itself: images -> unfold(16) in (c, ky, kx) order -> 16-bit
+    ref = torch.nn.functional.unfold(views, kernel_size=16, stride=16).transpose(1, 2).to(lp)
+    assert torch.equal(rows, ref)
+    res = {}
+    for kind in ("images", "rows"):
+        model = _build(state, dev, mode)
+        a, b = (views[:B], views[B:]) if kind == "images" else (rows[:B], rows[B:])
+        loss = model.ssp_step(a, b, accumulation_steps=1)
+        res[kind] = (loss.clone(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None})
+    assert torch.equal(res["images"][0], res["rows"][0])
+    g_rel, worst = _rel_l2(res["rows"][1], {k: v.cpu() for k, v in res["images"][1].items()})
+    assert g_rel <= 1e-3, (g_rel, worst)      # TMA reduce-add order of the split-K wgrads (same level run to run)
+    model = _build(state, dev, "fp32")
+    with pytest.raises((ValueError, RuntimeError)):
+        model.ssp_step(rows[:B], rows[B:])
+    with pytest.raises(ValueError):
+        _build(state, dev, "bf16" if mode == "fp16" else "fp16").ssp_step(rows[:B], rows[B:])
+    assert _lib.lib.v2s_debug_flag() == 0

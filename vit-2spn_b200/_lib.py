@@ -32,7 +32,7 @@ class Group(C.Structure):
         ("params", C.c_void_p), ("params_lp", C.c_void_p), ("grads", C.c_void_p), ("x", C.c_void_p),
         ("hidden", C.c_void_p), ("feat", C.c_void_p), ("feat_stride", C.c_int64),
         ("dfeat", C.c_void_p), ("dfeat_stride", C.c_int64), ("dhidden", C.c_void_p),
-        ("slot", C.c_int32), ("reserved", C.c_int32),
+        ("slot", C.c_int32), ("x_format", C.c_int32),
     ]
 
 
@@ -73,6 +73,7 @@ _SIGS = {
     "v2s_ema_update": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i, _i64, _d, _vp]),
     "v2s_cast_bf16": (C.c_int, [_vp, _vp, _i64, _vp]),
     "v2s_preprocess_u8": (C.c_int, [_vp, _vp, _i, _vp]),
+    "v2s_preprocess_u8_patches": (C.c_int, [_vp, _vp, _i, _i, _vp]),
     "v2s_augment_finish_u8": (C.c_int, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "v2s_test_gemm": (C.c_int, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "v2s_test_mlp": (C.c_int, [_i] + [_vp] * 14 + [_i, _i, _vp]),

@@ -227,6 +227,10 @@ static int backbone_forward_impl(const v2s_group_t* gs, int G, int B, int mode, 
     if (!gs[g].params || !gs[g].x) { set_error("backbone_forward: group %d has null params/x", g); return 1; }
     if (at && !gs[g].params_lp) { set_error("backbone_forward: the 16-bit modes need params_lp (group %d)", g); return 1; }
     if (gs[g].slot >= MAXG) { set_error("backbone_forward: bad slot"); return 1; }
+    if (gs[g].x_format != 0 && (gs[g].x_format != 1 || !at)) {
+      set_error("backbone_forward: group %d: x_format %d (1 = 16-bit patch rows, 16-bit modes only)", g, gs[g].x_format);
+      return 1;
+    }
   }
   const int64_t M = p.M, MP = p.MP;
 
@@ -240,15 +244,16 @@ static int backbone_forward_impl(const v2s_group_t* gs, int G, int B, int mode, 
   {
     const float* ux[MAXG]; void* uo[MAXG]; int nu = 0;
     for (int g = 0; g < G; ++g) {
+      if (gs[g].x_format == 1) { patches[g] = const_cast<void*>(gs[g].x); continue; }      // the caller's patch matrix
       patches[g] = saved(g) ? sb(g, p.s_patches) : fb(g, p.f_patches);
       int dup = -1;
       // a saved group must own its copy (it outlives the call); unsaved groups may alias
       if (!saved(g))
         for (int k = 0; k < g; ++k) if (gs[k].x == gs[g].x) { dup = k; break; }
       if (dup >= 0) { patches[g] = patches[dup]; continue; }
-      ux[nu] = gs[g].x; uo[nu] = patches[g]; ++nu;
+      ux[nu] = static_cast<const float*>(gs[g].x); uo[nu] = patches[g]; ++nu;
     }
-    V2S_TRY(launch_im2col(ux, uo, nu, B, at, st));
+    if (nu > 0) V2S_TRY(launch_im2col(ux, uo, nu, B, at, st));
   }
   float* x_cur[MAXG];
   {
@@ -581,7 +586,10 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
   // ---- embeddings: d pos, d cls, d patch bias, d patch weight ----
   if (layer_lo == 0) {
     const float* cdx[MAXG]; float* gr[MAXG]; void* pt[MAXG];
-    for (int g = 0; g < G; ++g) { cdx[g] = dx[g]; gr[g] = gs[g].grads; pt[g] = sb(g, p.s_patches); }
+    for (int g = 0; g < G; ++g) {
+      cdx[g] = dx[g]; gr[g] = gs[g].grads;
+      pt[g] = gs[g].x_format == 1 ? const_cast<void*>(gs[g].x) : static_cast<void*>(sb(g, p.s_patches));
+    }
     V2S_TRY(launch_embed_bwd(cdx, gr, G, B, st));
     if (tc) {          // compact the patch rows, then the ordinary tensor-core wgrad
       const void* src[MAXG];
@@ -929,6 +937,11 @@ int v2s_cast_bf16(const float* src, void* dst, int64_t numel, void* stream) {
   if (!src || !dst || numel < 0) { set_error("cast: bad argument"); return 1; }
   if (numel == 0) return 0;
   return launch_cast_bf16(src, dst, numel, (cudaStream_t)stream);
+}
+
+int v2s_preprocess_u8_patches(const uint8_t* src, void* patch_rows, int n_images, int lp_format, void* stream) {
+  if (!src || !patch_rows || n_images < 1 || (lp_format != 0 && lp_format != 1)) { set_error("preprocess_patches: bad argument"); return 1; }
+  return launch_preprocess_u8_patches(src, patch_rows, n_images, lp_format, (cudaStream_t)stream);
 }
 
 int v2s_preprocess_u8(const uint8_t* src, float* dst, int batch, void* stream) {

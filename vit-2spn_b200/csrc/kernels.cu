@@ -793,6 +793,38 @@ __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ src, float* __r
   }
 }
 
+// the same values written as the patch matrix [B*196, 768] (k = c*256 + ky*16 + kx) in a 16-bit format: one thread per
+// four consecutive kx of one (image, patch, channel, ky)
+template <typename T>
+__global__ void preprocess_u8_patches_kernel(const uint8_t* __restrict__ src, T* __restrict__ out, int B) {
+  const int64_t total = (int64_t)B * NP * (KPE / 4);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int kx4 = idx % 4, ky = (idx / 4) % 16, c = (idx / 64) % 3, pp = (idx / 192) % NP;
+    const int b = idx / (192 * NP);
+    const int yo = (pp / 14) * 16 + ky;
+    const float sc = 28.0f / 224.0f;
+    const float sy = fmaxf((yo + 0.5f) * sc - 0.5f, 0.f);
+    const int y0 = (int)sy, y1 = min(y0 + 1, 27);
+    const float ly = sy - y0;
+    const uint8_t* s = src + (int64_t)b * 784;
+    const float k = 1.0f / 255.0f;
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+    float r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int xo = (pp % 14) * 16 + kx4 * 4 + j;
+      const float sx = fmaxf((xo + 0.5f) * sc - 0.5f, 0.f);
+      const int x0 = (int)sx, x1 = min(x0 + 1, 27);
+      const float lx = sx - x0;
+      const float v00 = s[y0 * 28 + x0] * k, v01 = s[y0 * 28 + x1] * k, v10 = s[y1 * 28 + x0] * k, v11 = s[y1 * 28 + x1] * k;
+      const float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+      r[j] = (v - mean[c]) / stdv[c];
+    }
+    T* dst = out + ((int64_t)b * NP + pp) * KPE + c * 256 + ky * 16 + kx4 * 4;
+    dst[0] = from_f<T>(r[0]); dst[1] = from_f<T>(r[1]); dst[2] = from_f<T>(r[2]); dst[3] = from_f<T>(r[3]);
+  }
+}
+
 inline int grid_for(int64_t n, int threads, int max_blocks = 148 * 8) {
   int64_t b = (n + threads - 1) / threads;
   if (b > max_blocks) b = max_blocks;
@@ -1043,6 +1075,14 @@ int launch_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t s, int
 
 int launch_dropout_mask(float* mask, int64_t n, float p, uint64_t seed, uint64_t offset, cudaStream_t s) {
   dropout_mask_kernel<<<grid_for(n, 256), 256, 0, s>>>(mask, n, p, 1.0f / (1.0f - p), seed, offset);
+  V2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_preprocess_u8_patches(const uint8_t* src, void* out, int B, int lp_f16, cudaStream_t s) {
+  const int grid = grid_for((int64_t)B * NP * (KPE / 4), 256, 148 * 16);
+  if (lp_f16) preprocess_u8_patches_kernel<f16><<<grid, 256, 0, s>>>(src, static_cast<f16*>(out), B);
+  else preprocess_u8_patches_kernel<bf16><<<grid, 256, 0, s>>>(src, static_cast<bf16*>(out), B);
   V2S_LAUNCH_CHECK();
   return 0;
 }

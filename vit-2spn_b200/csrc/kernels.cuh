@@ -58,6 +58,7 @@ int launch_ema(float* const* tgt, const float* const* onl, void* const* tgt_lp, 
 int launch_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t s, int lp_f16 = 0);
 int launch_dropout_mask(float* mask, int64_t n, float p, uint64_t seed, uint64_t offset, cudaStream_t s);
 int launch_preprocess_u8(const uint8_t* src, float* dst, int B, cudaStream_t s);
+int launch_preprocess_u8_patches(const uint8_t* src, void* out, int B, int lp_f16, cudaStream_t s);
 int launch_augment_finish(const uint8_t* src, int n, int in_size, const int32_t* bounds, const int32_t* coefs, int ksize,
                           const float* k1d, const int32_t* erase, const float* mean3, const float* std3, float* dst,
                           cudaStream_t s);

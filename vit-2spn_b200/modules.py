@@ -235,11 +235,30 @@ def _new_workspace(device, batch, mode, n_groups, n_saved):
     return torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
 
 
-def _check_images(x):
+def _check_images(x, allow_patches=False):
+    if allow_patches and x.dim() == 3 and tuple(x.shape[1:]) == (196, 768) and x.dtype in (torch.bfloat16, torch.float16):
+        _require_cuda(x, "patch rows")          # the 16-bit patch matrix of preprocess_u8_patches (v2s_group.x_format 1)
+        return x.contiguous()
     if x.dim() != 4 or tuple(x.shape[1:]) != (3, 224, 224):
         raise ValueError(f"expected pixel_values of shape [B,3,224,224], got {tuple(x.shape)}")
     _require_cuda(x, "pixel_values")
     return x.contiguous().to(torch.float32)
+
+
+def preprocess_u8_patches(src_u8, dtype=torch.bfloat16, out=None):
+    """uint8 source images [N,1,28,28] (CUDA) -> the 16-bit patch matrix [N,196,768] that ``DualStreamNetwork.ssp_step``
+    accepts in place of fp32 images: bilinear 224x224, 3 channels, ImageNet normalise and the patch-embedding's im2col in
+    one kernel — bit-identical to ``v2s_preprocess_u8`` followed by the library's own im2col."""
+    _require_cuda(src_u8, "source images")
+    if src_u8.dtype != torch.uint8 or tuple(src_u8.shape[1:]) != (1, 28, 28):
+        raise ValueError(f"expected uint8 [N,1,28,28], got {src_u8.dtype} {tuple(src_u8.shape)}")
+    n = src_u8.shape[0]
+    if out is None:
+        out = torch.empty(n, 196, 768, dtype=dtype, device=src_u8.device)
+    with torch.cuda.device(src_u8.device):
+        check(lib.v2s_preprocess_u8_patches(ptr(src_u8.contiguous()), ptr(out), n, 1 if out.dtype == torch.float16 else 0,
+                                            stream_ptr()), "preprocess_u8_patches")
+    return out
 
 
 def _run_forward(groups, batch, mode, ws):
@@ -270,6 +289,11 @@ def _group(store, mode, x, slot, grads=None, hidden=None, feat=None, feat_stride
     g.params_lp = store.lp(fmt=_lp_format(mode)).data_ptr() if mode != _lib.MODE_FP32 else None
     g.grads = grads.data_ptr() if grads is not None else None
     g.x = x.data_ptr()
+    if x.dim() == 3:                             # 16-bit patch rows
+        want = {_lib.MODE_BF16: torch.bfloat16, _lib.MODE_FP16: torch.float16}.get(mode)
+        if x.dtype != want:
+            raise ValueError(f"patch-row inputs of dtype {x.dtype} do not match the compute mode ({[k for k, v in _MODE_NAMES.items() if v == mode][0]})")
+        g.x_format = 1
     g.hidden = hidden.data_ptr() if hidden is not None else None
     g.feat = feat.data_ptr() if feat is not None else None
     g.feat_stride = feat_stride
@@ -788,7 +812,7 @@ class DualStreamNetwork(nn.Module):
             scale_t, grad_scale = grad_scale.to(torch.float32), 1.0
             if not scale_t.is_cuda or scale_t.numel() != 1:
                 raise ValueError("grad_scale tensor must be a one-element CUDA tensor")
-        x1, x2 = _check_images(x1), _check_images(x2)
+        x1, x2 = _check_images(x1, True), _check_images(x2, True)
         st, hs = self._stores(), self._head_store
         for s in st:
             s.ensure()
@@ -865,7 +889,7 @@ class DualStreamNetwork(nn.Module):
         graph's own buffers (0.05 ms at B = 128); dropout masks are drawn outside the graph before every replay, so
         every step still sees fresh masks; the returned loss tensor is the graph's output buffer (overwritten by the
         next replay).  Not for ``grad_sync`` / GradScaler steps — use ``ssp_step`` there."""
-        x1, x2 = _check_images(x1), _check_images(x2)
+        x1, x2 = _check_images(x1, True), _check_images(x2, True)
         drop = self.projection_head[2]
         dropout_on = self._fixed_masks is None and self.training and drop.training and drop.p > 0.0
         st, hs = self._stores(), self._head_store
