@@ -176,7 +176,12 @@ int run_gemm(const GemmDesc& d, int ta, int tb, int to, cudaStream_t s, int cls 
     // second 16-bit tensor: gelu'(u) operand of the dgrad epilogue; the pre-GELU store only for groups that keep it
     if (d.epi == EPI_DGELU || (d.epi == EPI_BIAS_GELU && d.out[g])) bytes += (double)d.M * d.N * 2.0;
   }
-  prof::Scope scope(cls, 2.0 * d.M * d.N * (double)d.K * d.groups, s, bytes);
+  double flops = 2.0 * d.M * d.N * (double)d.K * d.groups;
+  if (d.M2 > 0) {      // two-problem wgrad launch: each half of the groups has its own shape
+    bytes = 0.5 * d.groups * (((double)d.M + d.N + d.M2 + d.N2) * d.K * ea + ((double)d.M * d.N + (double)d.M2 * d.N2) * eo);
+    flops = d.groups * ((double)d.M * d.N + (double)d.M2 * d.N2) * (double)d.K;
+  }
+  prof::Scope scope(cls, flops, s, bytes);
   int handled = 0;
   V2S_TRY(launch_gemm_tc(d, ta, tb, to, s, &handled));
   if (handled) return 0;
@@ -491,6 +496,30 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
     }
     return run_gemm(d, at, at, 0, st, prof::C_WGRAD);
   };
+  // two weight gradients of one block in ONE split-K launch (tensor-core path): the groups of the second problem
+  // follow those of the first (GemmDesc::M2 / N2).  Four ~20 us launches per block become two: one ramp / one tail,
+  // longer K ranges per CTA and a third less reduce-add traffic.
+  static const bool merge_wgrads = !getenv("V2S_NO_WGRAD_MERGE");
+  auto wgrad2 = [&](void* const* dy1, int n_out1, void* const* x1, int k_in1, int64_t goff1, int64_t bias1,
+                    void* const* dy2, int n_out2, void* const* x2, int k_in2, int64_t goff2, int64_t bias2) -> int {
+    if (!tc || !merge_wgrads || 2 * G > MAXG) {
+      V2S_TRY(wgrad(dy1, n_out1, x1, k_in1, goff1, false, bias1));
+      return wgrad(dy2, n_out2, x2, k_in2, goff2, false, bias2);
+    }
+    GemmDesc d = make_gemm_desc();
+    d.M = n_out1; d.N = k_in1; d.K = (int)M; d.groups = 2 * G;
+    d.a_rs = 1; d.a_cs = n_out1; d.b_rs = k_in1; d.b_cs = 1;
+    d.M2 = n_out2; d.N2 = k_in2;
+    d.epi = EPI_ACCUM; d.ldc = k_in1; d.split_k = split;
+    for (int g = 0; g < G; ++g) {
+      d.A[g] = dy1[g]; d.B[g] = x1[g]; d.out[g] = gs[g].grads + goff1;
+      d.rowsum_out[g] = bias1 >= 0 ? gs[g].grads + bias1 : nullptr;
+      d.A[G + g] = dy2[g]; d.B[G + g] = x2[g]; d.out[G + g] = gs[g].grads + goff2;
+      d.rowsum_out[G + g] = bias2 >= 0 ? gs[g].grads + bias2 : nullptr;
+    }
+    return run_gemm(d, at, at, 0, st, prof::C_WGRAD);
+  };
+  const bool merged = tc && merge_wgrads && 2 * G <= MAXG;
   // dX[M, K_in] = dY[M, N_out] * W[N_out, K_in]
   // late: the kernel launched just before this one is a wgrad whose inputs this GEMM shares, and nothing the wgrad
   // touches is written here (GemmDesc::late_wait)
@@ -526,12 +555,12 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
     // runs "late" (GemmDesc::late_wait): it does not drain that wgrad.  The mirrored order (wgrads late after the
     // chain kernels, dWo filling the attention kernel's partial last wave) measured the same or slightly slower.
     // ---- MLP ----
-    V2S_TRY(wgrad(dxlp, D, h, DF, lo + L_W2, false));                      // dW2 [192,768]
+    if (!(merged && mlp_fuse)) V2S_TRY(wgrad(dxlp, D, h, DF, lo + L_W2, false));      // dW2 [192,768]
     if (l == NL - 1) V2S_TRY(bias_grad(dxlp, D, lo + L_B2));               // lower blocks: fused into LN1-bwd above
     if (mlp_fuse) {
       // du = (dx W2) * gelu'(u) and d xn2 = du W1 chained on chip (du is still written once: dW1 needs it)
       MlpDesc d = make_mlp_desc();
-      d.mode = MLP_BWD; d.M = (int)M; d.groups = G; d.lp_f16 = at == AT_F16 ? 1 : 0; d.late_wait = (l != NL - 1 && !getenv("V2S_NO_LATE_WAIT")) ? 1 : 0;
+      d.mode = MLP_BWD; d.M = (int)M; d.groups = G; d.lp_f16 = at == AT_F16 ? 1 : 0; d.late_wait = (!merged && l != NL - 1 && !getenv("V2S_NO_LATE_WAIT")) ? 1 : 0;
       for (int g = 0; g < G; ++g) {
         d.a[g] = dxlp[g]; d.w1[g] = weight_ptr(gs[g], at, lo + L_W1); d.w2[g] = weight_ptr(gs[g], at, lo + L_W2);
         d.u[g] = u[g]; d.h[g] = big[g]; d.out[g] = tmp[g];
@@ -541,7 +570,10 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
                           ((double)M * D * 4 + (double)M * DF * 4 + 2.0 * D * DF * 2) * G);
         V2S_TRY(launch_mlp_tc(d, st));
       }
-      V2S_TRY(wgrad(big, DF, xn2, D, lo + L_W1, false, lo + L_B1));          // dW1 [768,192] and d b1
+      if (merged)      // dW2 [192,768] (the gradient dxlp is only overwritten by LN2-bwd below) with dW1 [768,192], d b1
+        V2S_TRY(wgrad2(dxlp, D, h, DF, lo + L_W2, -1, big, DF, xn2, D, lo + L_W1, lo + L_B1));
+      else
+        V2S_TRY(wgrad(big, DF, xn2, D, lo + L_W1, false, lo + L_B1));          // dW1 [768,192] and d b1
     } else {
     V2S_TRY(dgrad(dxlp, D, lo + L_W2, DF, big, EPI_DGELU, u, l != NL - 1));   // du = (dx W2) * gelu'(u)
     V2S_TRY(wgrad(big, DF, xn2, D, lo + L_W1, false, lo + L_B1));          // dW1 [768,192] and d b1
@@ -560,14 +592,17 @@ static int backbone_backward_impl(const v2s_group_t* gs_in, int G_in, int B, int
         V2S_TRY(launch_ln_bwd(dy, x, mu, rs, gm, dx, lp, dg, db, cs, G, (int)M, at, st)); }
     }
     // ---- attention ----
-    V2S_TRY(wgrad(dxlp, D, ctx, D, lo + L_WO, false));                     // dWo (d b_o: fused into LN2-bwd)
-    V2S_TRY(dgrad(dxlp, D, lo + L_WO, D, tmp, EPI_STORE, nullptr, true));  // d ctx
+    if (!merged) V2S_TRY(wgrad(dxlp, D, ctx, D, lo + L_WO, false));        // dWo (d b_o: fused into LN2-bwd)
+    V2S_TRY(dgrad(dxlp, D, lo + L_WO, D, tmp, EPI_STORE, nullptr, !merged));  // d ctx
     {
       const void *cq[MAXG], *cc[MAXG], *cd[MAXG]; const float* ls[MAXG];
       for (int g = 0; g < G; ++g) { cq[g] = qkv[g]; cc[g] = ctx[g]; cd[g] = tmp[g]; ls[g] = (const float*)sb(g, s.lse); }
       V2S_TRY(launch_attention_bwd(cq, cc, ls, cd, big, G, B, at, st));    // d qkv in `big` [M,576]
     }
-    V2S_TRY(wgrad(big, 3 * D, xn1, D, lo + L_WQKV, false, lo + L_BQKV));   // dWqkv [576,192] and d b_qkv
+    if (merged)        // dWo [192,192] (its gradient dxlp is only overwritten by LN1-bwd below) with dWqkv [576,192], d b_qkv
+      V2S_TRY(wgrad2(dxlp, D, ctx, D, lo + L_WO, -1, big, 3 * D, xn1, D, lo + L_WQKV, lo + L_BQKV));
+    else
+      V2S_TRY(wgrad(big, 3 * D, xn1, D, lo + L_WQKV, false, lo + L_BQKV));   // dWqkv [576,192] and d b_qkv
     V2S_TRY(dgrad(big, 3 * D, lo + L_WQKV, D, tmp, EPI_STORE, nullptr, true));   // d xn1
     {
       const void* dy[MAXG]; const float *x[MAXG], *mu[MAXG], *rs[MAXG], *gm[MAXG];

@@ -48,6 +48,10 @@ struct GemmDesc {
   // draining that kernel, wait for it just before exiting (see gemm_tc.cu)
   int late_wait;
   int lp_f16;       // tensor-core path: the 16-bit operands / outputs are fp16 (1) instead of bf16 (0)
+  // tensor-core split-K wgrad launches only: two different problems (same K = token dimension) in one launch.  Groups
+  // [0, groups / 2) use M, N and the strides above, groups [groups / 2, groups) use M2, N2 (a_cs = M2, b_rs = N2,
+  // ldc = N2: both operands token-major).  One launch ramp and one balanced wave instead of two.
+  int M2, N2;
 };
 
 inline GemmDesc make_gemm_desc() {

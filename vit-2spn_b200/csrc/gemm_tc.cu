@@ -70,6 +70,8 @@ struct alignas(64) TcParams {
   float* rowsum[MAXG];  // T_ACCUM: rowsum[m] += sum_k A(m,k), computed by an extra N=16 MMA against a ones tile
   int M, N, K;
   int tiles_m, tiles_n, splits, kb_total, kb_per_split, groups, total_tiles;
+  // hetero (split-K wgrad only): the second half of the groups has its own shape (GemmDesc::M2 / N2)
+  int hetero, M2, N2, tiles_m2, tiles_n2, base2;      // base2 = first tile index of the second half
   int a_mn, b_mn;
   int out2_mask;      // bit g: group g writes the secondary output (pre-GELU u)
   int b_stationary;   // K <= 192: the CTA keeps its [192 x K] B tile in smem and walks m-tiles only
@@ -160,6 +162,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     }
     const int t = blockIdx.x + i * gridDim.x;
     if (t >= p.total_tiles) return false;
+    if (p.hetero && t >= p.base2) {
+      const int per_group2 = p.tiles_m2 * p.splits * p.tiles_n2;
+      const int t2 = t - p.base2;
+      const int g2 = t2 / per_group2;
+      int r = t2 - g2 * per_group2;
+      g = p.groups / 2 + g2;
+      n_tile = r % p.tiles_n2; r /= p.tiles_n2;
+      split = r % p.splits;
+      m_tile = r / p.splits;
+      return true;
+    }
     g = t / tiles_per_group;
     int r = t - g * tiles_per_group;
     n_tile = r % p.tiles_n; r /= p.tiles_n;
@@ -167,6 +180,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
     m_tile = r / p.splits;
     return true;
   };
+  auto rows_of = [&](int g) { return (p.hetero && g >= p.groups / 2) ? p.M2 : p.M; };
+  auto cols_of = [&](int g) { return (p.hetero && g >= p.groups / 2) ? p.N2 : p.N; };
   // smem map of the operand region: streaming mode = 3 stages of [A 16 KB | B 24 KB];
   // B-stationary mode = [B tile: kb_total (<= 3) k-blocks x 24 KB] followed by a ring of A slots (16 KB)
   uint8_t* bres = smem;
@@ -321,7 +336,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
           if (!(DBG && (p.dbg_flags & (4 | 16)))) {
             if (c < N_CHUNKS) {
               const int col0 = n0 + c * CHUNK;
-              if (col0 < p.N) {
+              if (col0 < cols_of(g)) {
                 if (EPI == T_ACCUM) ptx::tma_reduce_add_2d(&p.tmOut[g], stg, col0, m0);
                 else ptx::tma_store_2d(&p.tmOut[g], stg, col0, m0);
                 if (write_u) ptx::tma_store_2d(&p.tmOut2[g], stg + 8192, col0, m0);
@@ -433,7 +448,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gemm_tc_kernel(const __grid_cons
             uint32_t rs[16];
             ptx::tmem_ld_32x16(tlane + BN, rs);
             ptx::tmem_ld_wait();
-            if (m0 + row < p.M) atomicAdd(p.rowsum[g] + m0 + row, __uint_as_float(rs[0]));
+            if (m0 + row < rows_of(g)) atomicAdd(p.rowsum[g] + m0 + row, __uint_as_float(rs[0]));
           }
           ptx::tc_fence_before();
           if (lane == 0) ptx::mbar_arrive(&tempty_bar[ge]);
@@ -821,10 +836,17 @@ int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t strea
   p.tiles_n = (d.N + BN - 1) / BN;
   p.kb_total = (d.K + BK - 1) / BK;
   p.splits = 1;
+  const bool hetero = epi == T_ACCUM && d.M2 > 0 && d.N2 > 0;
+  if (hetero) {
+    if ((d.groups & 1) || !a_mn || !b_mn || (d.M2 % 8) || (d.N2 % 8)) { set_error("gemm_tc: bad two-problem wgrad"); return 1; }
+    p.hetero = 1; p.M2 = d.M2; p.N2 = d.N2;
+    p.tiles_m2 = (d.M2 + BM - 1) / BM; p.tiles_n2 = (d.N2 + BN - 1) / BN;
+  }
   if (epi == T_ACCUM) {
     // split-K so that the launch is ONE balanced wave: base * splits <= #SMs (a second, partial wave of a few
     // tiles would double the makespan of these long-K tiles)
-    const int base = d.groups * p.tiles_m * p.tiles_n;
+    const int base = hetero ? (d.groups / 2) * (p.tiles_m * p.tiles_n + p.tiles_m2 * p.tiles_n2)
+                            : d.groups * p.tiles_m * p.tiles_n;
     int s = g_num_sms / base;
     const int max_s = p.kb_total / 4 > 0 ? p.kb_total / 4 : 1;
     if (s > max_s) s = max_s;
@@ -834,6 +856,10 @@ int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t strea
   p.kb_per_split = (p.kb_total + p.splits - 1) / p.splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
   p.total_tiles = d.groups * p.tiles_m * p.tiles_n * p.splits;
+  if (hetero) {
+    p.base2 = (d.groups / 2) * p.tiles_m * p.tiles_n * p.splits;
+    p.total_tiles = p.base2 + (d.groups / 2) * p.tiles_m2 * p.tiles_n2 * p.splits;
+  }
   p.a_mn = a_mn; p.b_mn = b_mn;
   const int combos = d.groups * p.tiles_n;
   if (epi != T_ACCUM && p.kb_total <= 3 && combos <= g_num_sms && !getenv("V2S_NO_BSTAT")) {
@@ -848,6 +874,14 @@ int launch_gemm_tc(const GemmDesc& d, int ta, int tb, int to, cudaStream_t strea
   p.dbg_flags = g_dbg_flags;
   const CUtensorMapSwizzle out_swz = out_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   for (int g = 0; g < d.groups; ++g) {
+    if (hetero && g >= d.groups / 2) {      // second problem: A [K, M2] and B [K, N2] token-major, out [M2, N2]
+      V2S_TRY(get_map(&p.tmA[g], d.A[g], d.M2, d.K, d.M2, 64, BK, true, CU_TENSOR_MAP_SWIZZLE_128B));
+      V2S_TRY(get_map(&p.tmB[g], d.B[g], d.N2, d.K, d.N2, 64, BK, true, CU_TENSOR_MAP_SWIZZLE_128B));
+      V2S_TRY(get_map(&p.tmOut[g], d.out[g], d.N2, d.M2, d.N2, CHUNK, BM, false, out_swz));
+      p.bias[g] = nullptr;
+      p.rowsum[g] = d.rowsum_out[g];
+      continue;
+    }
     if (!a_mn) V2S_TRY(get_map(&p.tmA[g], d.A[g], d.K, d.M, a_ld, BK, BM, true, CU_TENSOR_MAP_SWIZZLE_128B));
     else V2S_TRY(get_map(&p.tmA[g], d.A[g], d.M, d.K, a_ld, 64, BK, true, CU_TENSOR_MAP_SWIZZLE_128B));
     if (!b_mn) V2S_TRY(get_map(&p.tmB[g], d.B[g], d.K, d.N, b_ld, BK, BN, true, CU_TENSOR_MAP_SWIZZLE_128B));
