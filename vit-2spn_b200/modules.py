@@ -890,6 +890,11 @@ class DualStreamNetwork(nn.Module):
         every step still sees fresh masks; the returned loss tensor is the graph's output buffer (overwritten by the
         next replay).  Not for ``grad_sync`` / GradScaler steps — use ``ssp_step`` there."""
         x1, x2 = _check_images(x1, True), _check_images(x2, True)
+        if self.loss_mode == "infonce":
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.nce_group) > 1:
+                raise NotImplementedError("ssp_step_graphed: the key all-gather of the InfoNCE mode is not captured; "
+                                          "use ssp_step with more than one rank")
         drop = self.projection_head[2]
         dropout_on = self._fixed_masks is None and self.training and drop.training and drop.p > 0.0
         st, hs = self._stores(), self._head_store
