@@ -765,25 +765,6 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
       const bool valid = qrow < NT;
       // padding query rows (>= 197): lse2 = +huge makes every p underflow to exactly 0, no per-element row mask needed
       const float lse2 = valid ? lse_nxt * LOG2E : 3.0e38f;
-      ptx::mbar_wait(&bar_load[t], ph, p.err_flag, 30);
-      V2S_TICK(2)
-      // ---- D = rowsum(dO * O) (both halves compute it) ----
-      float Dr = 0.f;
-      if (valid) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 dv = *reinterpret_cast<const uint4*>(smem + B_OFF_DO + row * 128 + ((c ^ (row & 7)) << 4));
-          const uint32_t ow[4] = {ov[c].x, ov[c].y, ov[c].z, ov[c].w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            Dr = fmaf(LP::lo(ow[e]), LP::lo(dw[e]), Dr);
-            Dr = fmaf(LP::hi(ow[e]), LP::hi(dw[e]), Dr);
-          }
-        }
-      }
-      if (t == 0) fetch_row(n, 1);
-      else if (n + 1 < njobs) fetch_row(n + 1, 0);
-      V2S_TICK(9)
       // ---- P = exp(S/8 - lse) ----
       ptx::mbar_wait(&bar_s[t], ph, p.err_flag, 26);
       V2S_TICK(0)
@@ -828,6 +809,27 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bar_p[t]);
       V2S_TICK(1)
+      // D is only needed by the dS pass: computing it here puts it under the dP = dO V^T UMMAs instead of in front of
+      // the P pass (the S UMMAs of a tile are long done when the threads get to it)
+      ptx::mbar_wait(&bar_load[t], ph, p.err_flag, 30);
+      V2S_TICK(2)
+      // ---- D = rowsum(dO * O) (both halves compute it) ----
+      float Dr = 0.f;
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 dv = *reinterpret_cast<const uint4*>(smem + B_OFF_DO + row * 128 + ((c ^ (row & 7)) << 4));
+          const uint32_t ow[4] = {ov[c].x, ov[c].y, ov[c].z, ov[c].w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            Dr = fmaf(LP::lo(ow[e]), LP::lo(dw[e]), Dr);
+            Dr = fmaf(LP::hi(ow[e]), LP::hi(dw[e]), Dr);
+          }
+        }
+      }
+      if (t == 0) fetch_row(n, 1);
+      else if (n + 1 < njobs) fetch_row(n + 1, 0);
+      V2S_TICK(9)
       // ---- dS = P * (dP - D) / 8 ----
       const float mDs = -Dr * SCALE;
       ptx::mbar_wait(&bar_dp[t], ph, p.err_flag, 27);
