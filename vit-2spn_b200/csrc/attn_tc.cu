@@ -575,7 +575,9 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
   uint64_t* bar_kv = bar_dq + 2;      // [2] all MMAs of the tile retired
   uint64_t* bar_free = bar_kv + 2;    // [1] count 256: tile-0 buffers and TMEM[0,208) reusable
   uint64_t* bar_done = bar_free + 1;  // [1] count 256: the dQ store of the job's second tile has read its staging tile
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_done + 1);
+  uint64_t* bar_do = bar_done + 1;    // [2] the dO tile landed (its buffer is released last, so it has its own barrier:
+                                      //     S = Q K^T and the P pass do not wait for it)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_do + 2);
   const int njobs = ((int)blockIdx.x < p.total_jobs) ? (p.total_jobs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   auto decode = [&](int n, int& h, int& b, int& g) {
     const int J = blockIdx.x + n * gridDim.x;
@@ -590,7 +592,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
       for (int t = 0; t < 2; ++t) {
         ptx::mbar_init(&bar_load[t], 1); ptx::mbar_init(&bar_s[t], 1); ptx::mbar_init(&bar_p[t], 256);
         ptx::mbar_init(&bar_dp[t], 1); ptx::mbar_init(&bar_ds[t], 256); ptx::mbar_init(&bar_dq[t], 1);
-        ptx::mbar_init(&bar_kv[t], 1);
+        ptx::mbar_init(&bar_kv[t], 1); ptx::mbar_init(&bar_do[t], 1);
       }
       ptx::mbar_init(bar_free, 256);
       ptx::mbar_init(bar_done, 256);
@@ -625,14 +627,15 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
     const uint32_t idesc_s = make_idesc_lp(LP::kIdescFmt, QT, KPAD, 0, 0);
     const uint32_t idesc_dq = make_idesc_lp(LP::kIdescFmt, QT, DH, 0, 1);
     const uint32_t idesc_kv = make_idesc_lp(LP::kIdescFmt, QT, DH, 1, 1);
-    constexpr uint32_t LOAD0_BYTES = 2 * Q_TILE_BYTES + 2 * KV_TILE_BYTES;
+    constexpr uint32_t LOAD0_BYTES = Q_TILE_BYTES + 2 * KV_TILE_BYTES;
     if (njobs > 0) {      // the first job: everything at once
       int h, b, g;
       decode(0, h, b, g);
       if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(&bar_load[0], LOAD0_BYTES);
+        ptx::mbar_arrive_expect_tx(&bar_do[0], Q_TILE_BYTES);
         ptx::tma_load_3d(smem + B_OFF_Q, &p.tmQ[g], &bar_load[0], h * DH, 0, b);
-        ptx::tma_load_3d(smem + B_OFF_DO, &p.tmDO[g], &bar_load[0], h * DH, 0, b);
+        ptx::tma_load_3d(smem + B_OFF_DO, &p.tmDO[g], &bar_do[0], h * DH, 0, b);
         ptx::tma_load_3d(smem + B_OFF_K, &p.tmKV[g], &bar_load[0], D + h * DH, 0, b);
         ptx::tma_load_3d(smem + B_OFF_V, &p.tmKV[g], &bar_load[0], 2 * D + h * DH, 0, b);
       }
@@ -660,9 +663,10 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
           ptx::mbar_wait(&bar_kv[0], ph, p.err_flag, 21);     // tile-0 MMAs no longer read Q/dO/P/dS
           ptx::mbar_wait(bar_free, ph, p.err_flag, 22);       // dQ_0 drained, staging store done
           if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(&bar_load[1], 2 * Q_TILE_BYTES);
+            ptx::mbar_arrive_expect_tx(&bar_load[1], Q_TILE_BYTES);
+            ptx::mbar_arrive_expect_tx(&bar_do[1], Q_TILE_BYTES);
             ptx::tma_load_3d(smem + B_OFF_Q, &p.tmQ[g], &bar_load[1], h * DH, QT, b);
-            ptx::tma_load_3d(smem + B_OFF_DO, &p.tmDO[g], &bar_load[1], h * DH, QT, b);
+            ptx::tma_load_3d(smem + B_OFF_DO, &p.tmDO[g], &bar_do[1], h * DH, QT, b);
           }
           __syncwarp();
         }
@@ -676,6 +680,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
         __syncwarp();
         // P ready -> dP = dO_t V^T (over S's columns) and dV += P^T dO_t
         ptx::mbar_wait(&bar_p[t], ph, p.err_flag, 24);
+        ptx::mbar_wait(&bar_do[t], ph, p.err_flag, 17);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
 #pragma unroll
@@ -720,7 +725,10 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
         if (ptx::elect_one()) ptx::tma_load_3d(smem + B_OFF_Q, &p.tmQ[g2], &bar_load[0], h2 * DH, 0, b2);
         __syncwarp();
         ptx::mbar_wait(bar_done, ph, p.err_flag, 18);         // the dQ_1 store has read its staging tile (the dO buffer)
-        if (ptx::elect_one()) ptx::tma_load_3d(smem + B_OFF_DO, &p.tmDO[g2], &bar_load[0], h2 * DH, 0, b2);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(&bar_do[0], Q_TILE_BYTES);
+          ptx::tma_load_3d(smem + B_OFF_DO, &p.tmDO[g2], &bar_do[0], h2 * DH, 0, b2);
+        }
         __syncwarp();
       }
     }
@@ -811,7 +819,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_tc_kernel(const __grid_
       V2S_TICK(1)
       // D is only needed by the dS pass: computing it here puts it under the dP = dO V^T UMMAs instead of in front of
       // the P pass (the S UMMAs of a tile are long done when the threads get to it)
-      ptx::mbar_wait(&bar_load[t], ph, p.err_flag, 30);
+      ptx::mbar_wait(&bar_do[t], ph, p.err_flag, 30);
       V2S_TICK(2)
       // ---- D = rowsum(dO * O) (both halves compute it) ----
       float Dr = 0.f;
