@@ -522,7 +522,9 @@ __global__ void __launch_bounds__(PF_THREADS, 1) attn_fwd_persist_kernel(const _
 // loaded as soon as the last dQ UMMAs have retired (they overlap the dQ / dK / dV drains), its Q tile after the last dK
 // UMMAs; everything else the job will need (its first dO tile, the second Q / dO tiles) is prefetched into L2 a job /
 // a tile ahead, so that the loads the chain does wait for are L2 hits (measured before: 35 % of a job was waiting for
-// DRAM-latency TMA loads, one CTA per job).
+// DRAM-latency TMA loads, one CTA per job).  The dO tile, whose buffer (it doubles as the dQ staging tile) is released
+// last, signals its own barrier: only D, dP and dV wait for it, S = Q K^T and the P pass do not.  D = rowsum(dO * O) is
+// computed between the P pass and the dS pass, under the dP UMMAs.
 //   S  = Q_t K^T                      (UMMA 128x208x64)         -> P = exp2(S*c - lse*log2e)  (bf16, smem)
 //   dP = dO_t V^T                     (UMMA 128x208x64)         -> dS = P * (dP - D) / 8      (bf16, smem)
 //   dV += P^T dO_t,  dK += dS^T Q_t   (UMMA 128x64x128, A MN-major = the same smem tiles read transposed)
