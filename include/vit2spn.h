@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define V2S_ABI_VERSION 2
+#define V2S_ABI_VERSION 3 /* 3: v2s_infonce_loss, v2s_preprocess_u8_patches, v2s_group.x_format (was a reserved zero field) */
 
 /* compute modes */
 #define V2S_MODE_FP32 0 /* fp32 activations + fp32 SIMT GEMMs: the "fp32 check mode" of north_star */

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/vit2spn.h but not exported"
     assert set(vit2spn.EXPORTED) == set(syms), set(vit2spn.EXPORTED) ^ set(syms)
-    assert lib.v2s_abi_version() == 2        # 2: fp16 mode, amp entry points (round 2)
+    assert lib.v2s_abi_version() == 3        # 3: InfoNCE, uint8 -> patch-matrix input format (round 2); 2: fp16 mode, amp entry points
 
 
 def test_layout_matches_hf_parameter_order():
